@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the hybrid FEM + LSSVR hot path (BASELINE.json metric: element LSSVR solves/s, FP64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one synthetic mesh already resident in HBM:
+K1 coarse P1 solve -> K2+K3 per-element primal LSSVR + fine grid (+K5 error norms).  Workload at
+N = 1: BASELINE configs[2] ("primal LSSVR, 1e7 elements, degree 8, 32 fine points/element, 1 B200").
+For N > 1 every rank owns 1e7 contiguous elements of one global uniform mesh on [-1, 1] (weak
+scaling, the shape of configs[3]); the only exchanges are the SPIKE all-gather (4 doubles/rank) and
+the two error all-reduces.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'element_lssvr_solves_per_s'
+UNIT = 'element solves/s'
+M, NCOL, F, GAMMA, KFREQ = 9, 12, 32, 1e4, 1.0
+BYTES_PER_ELEMENT = 8 + 8 + 8 * F          # node + nodal value + fine row: 272 B
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--elements', type=int, default=10 ** 7, help='elements per GPU')
+    ap.add_argument('--error', default='fused', choices=['fused', 'separate', 'none'])
+    ap.add_argument('--coarse', default='assembled', choices=['assembled', 'flux'])
+    ap.add_argument('--store', type=int, default=0, help='primal store path: 0 auto, 1 direct, 2 smem, 3 tma')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='elements in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (numpy KKT restatement + SuperLU coarse solve), all host cores.
+def _cpu_chunk(args):
+    import numpy as np
+    from oracle import fem_p1, kkt
+    nodes, u = args
+    f = fem_p1.forcing(np.linspace(nodes[:-1], nodes[1:], NCOL, axis=0), KFREQ).T.copy()
+    coef = kkt.lssvr_primal_kkt_batch(nodes, u, f, M, GAMMA)
+    fine = kkt.evaluate_fine(coef, F)
+    x = kkt.fine_points(nodes, F)
+    d = fine - np.sin(KFREQ * np.pi * x)
+    return float(np.max(np.abs(d)))
+
+
+def cpu_reference_pass(sample, pool, cores):
+    """One pass of the hot path on `sample` elements with the oracle port; returns seconds."""
+    import numpy as np
+    from oracle import fem_p1
+    t0 = time.perf_counter()
+    nodes = np.linspace(-1.0, 1.0, sample + 1)
+    u = fem_p1.solve_fem_p1(nodes, KFREQ)             # SuperLU, what skfem.solve uses (P:138)
+    chunks = []
+    per = max(1, sample // (cores * 4))
+    for s in range(0, sample, per):
+        e = min(sample, s + per)
+        chunks.append((nodes[s:e + 1], u[s:e + 1]))
+    mx = max(pool.map(_cpu_chunk, chunks)) if pool is not None else max(map(_cpu_chunk, chunks))
+    return time.perf_counter() - t0, mx
+
+
+def cpu_slsqp_sample(n_elements=8):
+    """The reference's own formulation (SLSQP on the QP, P:84-91) restated in oracle/slsqp_port.py,
+    timed on a handful of elements: solves/s/core of the algorithm the reference actually runs."""
+    try:
+        import numpy as np
+        from oracle import fem_p1, slsqp_port
+    except Exception:
+        return None
+    nodes = np.linspace(-1.0, 1.0, 25)
+    u = fem_p1.solve_fem_p1(nodes)
+    t0 = time.perf_counter()
+    for i in range(n_elements):
+        slsqp_port.lssvr_primal_slsqp(lambda x: np.pi ** 2 * np.sin(np.pi * x), [nodes[i], nodes[i + 1]],
+                                      u[i], u[i + 1], 8, GAMMA)
+    return n_elements / (time.perf_counter() - t0)
+
+
+def run_cpu_baseline(sample, steps=1):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context('fork')
+    pool = ctx.Pool(cores) if cores > 1 else None
+    try:
+        cpu_reference_pass(min(sample, 20000), pool, cores)          # warm-up (imports, page-in)
+        times = []
+        for _ in range(steps):
+            t, mx = cpu_reference_pass(sample, pool, cores)
+            times.append(t)
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
+    return sample / (sum(times) / len(times)), cores, mx, times
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            p = [x.strip() for x in r.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx = float(p[2])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': (sm[len(sm) // 2] if sm else None), 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return json.load(fh)['hbm_gbs'], 'measured (MEASURED_PEAKS.json, burst copy)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hybrid_fem_lssvr_b200 import batch, _lib
+    from hybrid_fem_lssvr_b200 import dist as hdist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    E = args.elements
+    E_global = E * world
+    batch.set_option('primal_store', args.store)
+
+    nodes = hdist.local_nodes_linspace(-1.0, 1.0, E_global, world, rank, device=dev)
+    fine = torch.empty((E, F), dtype=torch.float64, device=dev)
+    u = torch.empty(E + 1, dtype=torch.float64, device=dev)
+    err3 = batch.new_error_accumulator(dev)
+    nerr = batch.new_error_accumulator(dev)
+    results = {}
+
+    def step():
+        err3.zero_()
+        if world > 1:
+            _, bc2 = hdist.fem_p1_solve_distributed(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u)
+        else:
+            batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u)
+            bc2 = None
+        batch.lssvr_primal_batch(nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, bc2=bc2,
+                                 want_coef=False, want_fine=True, fine_out=fine,
+                                 err3=err3 if args.error == 'fused' else None)
+        if args.error == 'separate':
+            batch.error_fine(nodes, fine, KFREQ, err3)
+        if world > 1 and args.error != 'none':
+            results['err'] = hdist.reduce_error(err3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t1 = time.perf_counter()
+    launches = _lib.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = E_global * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing of the dominant kernel (K2+K3, same launch as in the step), CUDA events
+    def time_kernel(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    reps = max(5, min(args.steps, 20))
+    k2_ms = time_kernel(lambda: batch.lssvr_primal_batch(
+        nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False, want_fine=True, fine_out=fine,
+        err3=err3 if args.error == 'fused' else None), reps)
+    k1_ms = time_kernel(lambda: batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u), reps)
+    k2_plain_ms = time_kernel(lambda: batch.lssvr_primal_batch(
+        nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False, want_fine=True, fine_out=fine), reps)
+    k5_ms = time_kernel(lambda: batch.error_fine(nodes, fine, KFREQ, nerr), max(3, reps // 2))
+    peak, peak_src = measured_peaks()
+    achieved = BYTES_PER_ELEMENT * E / (k2_ms * 1e-3) / 1e9
+
+    # ---- error norms of the last step (reported, not timed)
+    if world == 1:
+        l2, mx = batch.finish_error(err3) if args.error != 'none' else (None, None)
+    else:
+        l2, mx = (results['err'][0], results['err'][1]) if 'err' in results else (None, None)
+    nerr.zero_()
+    if world == 1:
+        nl2, nmx = batch.finish_error(batch.error_nodal(nodes, u, KFREQ, nerr))
+    else:
+        nl2 = nmx = None
+
+    # ---- FP64 FMA probe (no FP64 figure in MEASURED_PEAKS.json)
+    fp64_tflops = None
+    if rank == 0:
+        import ctypes as C
+        probe_out = torch.zeros(1, dtype=torch.float64, device=dev)
+        flops = C.c_double(0.0)
+        lib = _lib.load()
+
+        def probe():
+            _lib.check(lib.hfl_fp64_probe(148 * 8, 4096, batch._ptr(probe_out), C.byref(flops), batch._stream()), 'probe')
+        pm = time_kernel(probe, 5)
+        fp64_tflops = flops.value / (pm * 1e-3) / 1e12
+
+    # ---- end to end through the host-buffer API (pinned host mesh in, fine grid + norms out)
+    e2e = None
+    if not args.no_e2e:
+        from hybrid_fem_lssvr_b200 import host_api
+        runner = host_api.HostPipeline(E, M, GAMMA, NCOL, F, k_freq=KFREQ, coarse_solver=args.coarse, device=dev)
+        nodes_h = runner.pinned_nodes()
+        nodes_h.copy_(nodes.cpu())
+        for _ in range(2):
+            runner.run(nodes_h)
+        barrier()
+        reps_e = max(2, min(args.steps, 5))
+        te0 = time.perf_counter()
+        for _ in range(reps_e):
+            runner.run(nodes_h)
+        barrier()
+        te = (time.perf_counter() - te0) / reps_e
+        if world > 1:
+            t = torch.tensor([te], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = t.item()
+        e2e = {'value': E_global / te, 'unit': UNIT, 'h2d_bytes_per_step': runner.h2d_bytes,
+               'd2h_bytes_per_step': runner.d2h_bytes, 'ms_per_step': te * 1e3,
+               'note': 'pinned host nodes -> H2D -> K1 -> K2/K3/K5 in element chunks -> D2H of the whole fine grid '
+                       '+ error norms, copies overlapped with compute on two streams; wall clock with device sync'}
+        del runner
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        sample = args.cpu_sample or 2_000_000
+        v, cores, cmx, times = run_cpu_baseline(sample)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': '%d elements of the same uniform mesh family (M=9, N=12, F=32): SuperLU coarse solve + '
+                         'vectorised numpy KKT solves + fine grid + max error, %d processes, %.1f s'
+                         % (sample, cores, sum(times))}
+        s = cpu_slsqp_sample()
+        if s is not None:
+            cpu['reference_formulation_slsqp_solves_per_s_per_core'] = s
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[2]: primal LSSVR, %d elements/GPU, M=9 (degree 8), N=12, F=32, '
+                                   'uniform mesh on [-1,1], forcing pi^2 sin(pi x) on device; step = K1 coarse solve '
+                                   '(%s) + K2/K3 element solves with fine grid + K5 error norms (%s)'
+                                   % (E, args.coarse, args.error),
+                       'elements_per_gpu': E, 'elements_total': E_global, 'M': M, 'N_colloc': NCOL, 'F': F, 'gamma': GAMMA,
+                       'parallelism': 'contiguous element ranges x%d' % world,
+                       'l2_policy': 'inputs (160 MB) + outputs (2.56 GB) per step exceed the 126 MB L2; no explicit flush',
+                       'store_path': args.store},
+            'fine_points_per_s': value * F,
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'kernel': 'primal_kernel<M=9,FH=16,ERR=%s> (K2+K3%s)'
+                         % ('true' if args.error == 'fused' else 'false', '+K5' if args.error == 'fused' else ''),
+                         'algorithmic_bytes_per_element': BYTES_PER_ELEMENT, 'kernel_ms': k2_ms, 'peak_source': peak_src},
+            'kernels_ms': {'K1_coarse_solve': k1_ms, 'K2K3_primal_fine' + ('_K5' if args.error == 'fused' else ''): k2_ms,
+                           'K2K3_primal_fine_no_error': k2_plain_ms, 'K5_error_fine_standalone': k5_ms},
+            'fp64_fma_probe_tflops': fp64_tflops,
+            'errors_vs_sin': {'fine_l2': l2, 'fine_max': mx, 'nodal_l2': nl2, 'nodal_max': nmx},
+            'e2e': e2e,
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sample = args.cpu_sample or 1_000_000
+    run_cpu_baseline(20000)
+    t0 = time.perf_counter()
+    v, cores, mx, times = run_cpu_baseline(sample, steps=max(1, args.steps))
+    ms = 1e3 * sum(times) / len(times)
+    desc = ('%d elements per step of the uniform mesh family of BASELINE configs[2] (M=9, N=12, F=32): SuperLU coarse '
+            'solve + vectorised numpy KKT element solves + fine grid + max error' % sample)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': max(1, args.steps),
+        'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': 'BASELINE configs[2] on the host CPU, bounded sample: ' + desc},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc,
+                         'note': 'oracle port (closed-form KKT restatement of P:20-105 + restated P:117-145); the reference '
+                                 'scripts themselves cannot travel to the GPU box (no scikit-fem) and their SLSQP element '
+                                 'solve runs at ~3-15 solves/s/core (BASELINE.md)'},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'fine_max_error_vs_sin': mx, 'wall_s': time.perf_counter() - t0,
+    }
+    s = cpu_slsqp_sample()
+    if s is not None:
+        line['cpu_baseline']['reference_formulation_slsqp_solves_per_s_per_core'] = s
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

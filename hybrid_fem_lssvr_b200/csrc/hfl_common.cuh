@@ -1,0 +1,62 @@
+// Shared declarations of libhfl (sm_100a, FP64).  See include/hfl.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/hfl.h"
+
+namespace hfl {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int get_option_store();
+int sm_count();
+
+#define HFL_CUDA_CHECK(expr)                                                            \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            hfl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                           __FILE__, __LINE__);                                         \
+            return HFL_ERR_CUDA;                                                        \
+        }                                                                               \
+    } while (0)
+
+#define HFL_REQUIRE(cond, ...)                                                          \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            hfl::set_error(__VA_ARGS__);                                                \
+            return HFL_ERR_ARG;                                                         \
+        }                                                                               \
+    } while (0)
+
+// Number of even / odd Legendre indices k in [2, M-1] (the "bubble" unknowns per parity).
+__host__ __device__ constexpr int n_even(int M) { return (M - 1) / 2; }
+__host__ __device__ constexpr int n_odd(int M) { return (M - 2) / 2; }
+
+}  // namespace hfl
+
+// Plan: element-independent tables (host copies + device copies).
+struct hfl_plan {
+    int M, N, F;
+    double gamma;
+    int me, mo;   // even / odd bubble counts
+    int NH, FH;   // ceil(N/2) collocation pairs, ceil(F/2) fine pairs
+    // Pair tables on the non-negative half xi+ (ascending).  Pair weight (2, or 1 for the
+    // self-paired middle point of an odd count) is folded into De / Do.
+    std::vector<double> De;     // [NH][me]  w_j P''_{2+2a}(xi+_j)
+    std::vector<double> Do;     // [NH][mo]  w_j P''_{3+2b}(xi+_j)
+    std::vector<double> Ge;     // packed lower [me(me+1)/2]  sum_j P''_{2+2a} P''_{2+2a'}
+    std::vector<double> Go;     // packed lower [mo(mo+1)/2]
+    std::vector<double> fineE;  // [FH][me]    P_{2+2a}(xi+_i)
+    std::vector<double> fineO;  // [FH][mo+1]  {xi+_i, P_{3+2b}(xi+_i)}
+    // Full tables (dual path, generic kernels)
+    std::vector<double> D2;     // [N][M]  P_k''(xi_j)
+    std::vector<double> V;      // [F][M]  P_k(xi_i)
+    // Device block holding all of the above back to back
+    double* d_tables = nullptr;
+    size_t off_De, off_Do, off_Ge, off_Go, off_fineE, off_fineO, off_D2, off_V, n_tables;
+};

@@ -1,0 +1,605 @@
+// K2 + K3 (+ fused K5): batched per-element primal LSSVR solve with fine-grid reconstruction.
+//
+// Replaces the serial loop P:151-170 over lssvr_primal (P:20-105) and the structured part of
+// evaluate_solution (P:184-211).  The reference hands the QP
+//     min 1/2 |w|^2 + gamma/2 |e|^2   s.t.  -u''(x_j) - f(x_j) + e_j = 0,  u(x_L) = u_L, u(x_R) = u_R
+// to SLSQP; its unique minimiser is computed here in closed form, one element per thread:
+//
+//  * xi_j and the fine points are symmetric about the element centre and P_k has parity (-1)^k, so
+//    with the two boundary rows eliminated (w_0 = (u_L+u_R)/2 - sum_even w_k, w_1 = (u_R-u_L)/2 -
+//    sum_odd w_k) the normal equations split into an even and an odd SPD block
+//        (tau (I + 1 1^T) + G_par) w_par = tau g_par 1 - (h^2/4) D_par^T f_par,   tau = h^4 / (16 gamma)
+//    of sizes floor((M-1)/2) and floor((M-2)/2) (4 and 3 at M = 9).  G_par, D_par are
+//    element-independent tables; the element enters through tau, h^2 and the data.
+//  * each block is factorised per element (LDL^T in registers, reciprocal pivots), the factorisation is
+//    NOT shared between elements even on a uniform mesh.
+//  * forcing family (k pi)^2 sin(k pi x): f at the collocation points by the angle-addition rotation
+//    from one sincospi of the centre and one of the base angle (even part ~ cos, odd part ~ sin).
+//  * fine grid: u(+-xi) = E(xi) +- O(xi) with the basis values as immediate constant-bank operands
+//    (kernel parameter block), rows staged in swizzled shared memory and written by TMA tensor stores.
+#include "hfl_device.cuh"
+
+namespace hfl {
+
+struct PrimalArgs {
+    long long E;
+    const double* nodes;
+    const double* u;
+    const double* f;       // samples [N][E] or NULL
+    const double* bc2;     // optional {bc_left, bc_right}
+    double* coef;          // optional [E][M]
+    double* fine;          // optional [E][F]
+    int* status;           // optional [E]
+    double* err3;          // optional accumulators
+    const double* De;      // [NH][ME]
+    const double* Do;      // [NH][MO]
+    int N, NH, F;
+    int forcing;
+    double k_freq;
+    double kk;             // (k pi)^2
+    double c_tau;          // 1 / (16 gamma)
+    double cN;             // 0.5 / (N - 1)
+    double cF;             // 0.5 / (F - 1)
+};
+
+template <int M, int FH>
+struct PrimalTables {
+    static constexpr int ME = n_even(M), MO = n_odd(M);
+    double Ge[ME * (ME + 1) / 2];
+    double Go[MO > 0 ? MO * (MO + 1) / 2 : 1];
+    double fineE[FH > 0 ? FH : 1][ME];
+    double fineO[FH > 0 ? FH : 1][MO + 1];
+};
+
+enum { STORE_DIRECT = 1, STORE_SMEM = 2, STORE_TMA = 3 };
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+
+template <int STORE>
+__host__ __device__ constexpr int tile_bytes(int F) {
+    return STORE == STORE_TMA ? (F / 16) * 4096 : (STORE == STORE_SMEM ? 32 * (F + 2) * 8 : 0);
+}
+
+template <int M, int FH, bool ERR, int STORE>
+__global__ void __launch_bounds__(kThreads, 3)
+primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
+              const __grid_constant__ CUtensorMap tmap) {
+    constexpr int ME = n_even(M), MO = n_odd(M);
+    constexpr int F = 2 * FH;
+    constexpr int TILE = tile_bytes<STORE>(F);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* sDe = reinterpret_cast<double*>(smem_raw + kWarps * TILE);
+    double* sDo = sDe + a.NH * ME;
+    for (int i = threadIdx.x; i < a.NH * ME; i += kThreads) sDe[i] = a.De[i];
+    for (int i = threadIdx.x; i < a.NH * MO; i += kThreads) sDo[i] = a.Do[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* tile_ptr = smem_raw + warp * TILE;
+    const uint32_t tile_s = smem_u32(tile_ptr);
+    const bool do_fine = (a.fine != nullptr) || ERR;
+
+    double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
+    if (a.bc2 != nullptr) {
+        bcl = a.bc2[0]; bcr = a.bc2[1];
+        x_first = a.nodes[0]; x_last = a.nodes[a.E];
+        invL = 1.0 / (x_last - x_first);
+    }
+    double acc_sq = 0.0, acc_mx = 0.0;
+    int nfail = 0;
+    bool store_pending = false;
+
+    const long long ntiles = (a.E + 31) >> 5;
+    for (long long tile = (long long)blockIdx.x * kWarps + warp; tile < ntiles;
+         tile += (long long)gridDim.x * kWarps) {
+        const long long e_raw = tile * 32 + lane;
+        const bool valid = e_raw < a.E;
+        const long long e = valid ? e_raw : a.E - 1;
+        const double xl = __ldg(a.nodes + e), xr = __ldg(a.nodes + e + 1);
+        double ul = __ldg(a.u + e), ur = __ldg(a.u + e + 1);
+        if (a.bc2 != nullptr) {
+            ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
+            ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;
+        }
+        const double h = xr - xl;
+        const double h2 = h * h;
+        const double isig = 0.25 * h2;            // 1 / sigma, sigma = (2/h)^2
+        const double tau = (h2 * h2) * a.c_tau;   // 1 / (gamma sigma^2)
+        const double abar = 0.5 * (ul + ur), bbar = 0.5 * (ur - ul);
+
+        // ---- right-hand sides: re = tau abar 1 - isig De^T f_even, ro = tau bbar 1 - isig Do^T f_odd
+        double re[ME], ro[MO > 0 ? MO : 1];
+#pragma unroll
+        for (int i = 0; i < ME; ++i) re[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < MO; ++i) ro[i] = 0.0;
+        double S = 0.0, C = 0.0;   // sin / cos of k pi x_c
+        if (a.forcing == HFL_FORCING_SINE || ERR) sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
+        double sclE, sclO;
+        if (a.forcing == HFL_FORCING_SINE) {
+            double sb, cb;
+            sincospi(a.k_freq * h * a.cN, &sb, &cb);       // base angle k pi (h/2) / (N-1)
+            const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
+            double s = (a.N & 1) ? 0.0 : sb, c = (a.N & 1) ? 1.0 : cb;
+            for (int j = 0; j < a.NH; ++j) {
+#pragma unroll
+                for (int i = 0; i < ME; ++i) re[i] = fma(sDe[j * ME + i], c, re[i]);
+#pragma unroll
+                for (int i = 0; i < MO; ++i) ro[i] = fma(sDo[j * MO + i], s, ro[i]);
+                rotate(s, c, s2, c2);
+            }
+            sclE = -isig * a.kk * S;
+            sclO = -isig * a.kk * C;
+        } else {
+            const int jp0 = a.N >> 1, jm0 = (a.N - 1) >> 1;   // first right / left sample of pair 0
+            for (int j = 0; j < a.NH; ++j) {
+                const double fp = __ldg(a.f + (long long)(jp0 + j) * a.E + e);
+                const double fm = __ldg(a.f + (long long)(jm0 - j) * a.E + e);
+                const double fe = 0.5 * (fp + fm), fo = 0.5 * (fp - fm);
+#pragma unroll
+                for (int i = 0; i < ME; ++i) re[i] = fma(sDe[j * ME + i], fe, re[i]);
+#pragma unroll
+                for (int i = 0; i < MO; ++i) ro[i] = fma(sDo[j * MO + i], fo, ro[i]);
+            }
+            sclE = -isig;
+            sclO = -isig;
+        }
+        const double ta = tau * abar, tb = tau * bbar;
+#pragma unroll
+        for (int i = 0; i < ME; ++i) re[i] = fma(sclE, re[i], ta);
+#pragma unroll
+        for (int i = 0; i < MO; ++i) ro[i] = fma(sclO, ro[i], tb);
+
+        // ---- per-element matrices tau (I + 1 1^T) + G and their LDL^T solves
+        double Ae[ME * (ME + 1) / 2], Ao[MO > 0 ? MO * (MO + 1) / 2 : 1];
+        const double tau2 = tau + tau;
+#pragma unroll
+        for (int i = 0; i < ME; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+                Ae[i * (i + 1) / 2 + j] = t.Ge[i * (i + 1) / 2 + j] + (i == j ? tau2 : tau);
+#pragma unroll
+        for (int i = 0; i < MO; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+                Ao[i * (i + 1) / 2 + j] = t.Go[i * (i + 1) / 2 + j] + (i == j ? tau2 : tau);
+        bool ok = ldl_solve<ME>(Ae, re);
+        if (MO > 0) ok = ldl_solve<MO>(Ao, ro) && ok;
+        if (!ok) {   // P:171-176: fall back to the linear interpolant of the nodal values
+#pragma unroll
+            for (int i = 0; i < ME; ++i) re[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < MO; ++i) ro[i] = 0.0;
+            if (valid) ++nfail;
+        }
+        double w0 = abar, w1 = bbar;
+#pragma unroll
+        for (int i = 0; i < ME; ++i) w0 -= re[i];
+#pragma unroll
+        for (int i = 0; i < MO; ++i) w1 -= ro[i];
+
+        if (valid && a.status != nullptr) a.status[e] = ok ? 0 : 1;
+        if (valid && a.coef != nullptr) {
+            double* cp = a.coef + e * M;
+            cp[0] = w0;
+            cp[1] = w1;
+#pragma unroll
+            for (int i = 0; i < ME; ++i) cp[2 + 2 * i] = re[i];
+#pragma unroll
+            for (int i = 0; i < MO; ++i) cp[3 + 2 * i] = ro[i];
+        }
+
+        // ---- fine grid: u(+-xi_i) = Ee +- Oo; rows go to shared memory (or straight to global)
+        if (FH > 0 && do_fine) {
+            double sf = 0.0, cf = 1.0, s2f = 0.0, c2f = 1.0, sq = 0.0;
+            if (ERR) {
+                sincospi(a.k_freq * h * a.cF, &sf, &cf);   // base angle k pi (h/2) / (F-1); F even
+                s2f = 2.0 * sf * cf;
+                c2f = fma(-2.0 * sf, sf, 1.0);
+            }
+            const bool st = (a.fine != nullptr);
+            if (STORE == STORE_TMA && st && store_pending) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                store_pending = false;
+            }
+            const uint32_t row_tma = tile_s + lane * 128, sw = (uint32_t)(lane & 7) << 4;
+            const uint32_t row_sm = tile_s + lane * ((F + 2) * 8);
+            double2* row_g = reinterpret_cast<double2*>(a.fine + e * F);
+#pragma unroll
+            for (int i = 0; i < FH; i += 2) {
+                double up[2], um[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double Ee = w0, Oo = w1 * t.fineO[i + q][0];
+#pragma unroll
+                    for (int k = 0; k < ME; ++k) Ee = fma(re[k], t.fineE[i + q][k], Ee);
+#pragma unroll
+                    for (int k = 0; k < MO; ++k) Oo = fma(ro[k], t.fineO[i + q][1 + k], Oo);
+                    up[q] = Ee + Oo;
+                    um[q] = Ee - Oo;
+                    if (ERR) {
+                        const double xe = S * cf, xo = C * sf;
+                        const double ep = up[q] - (xe + xo), em = um[q] - (xe - xo);
+                        const double wgt = (i + q == FH - 1) ? 0.5 : 1.0;
+                        sq = fma(wgt, fma(ep, ep, em * em), sq);
+                        acc_mx = fmax(acc_mx, fmax(fabs(ep), fabs(em)));
+                        rotate(sf, cf, s2f, c2f);
+                    }
+                }
+                if (st) {
+                    const int pp = (FH + i) >> 1;        // chunk holding points FH+i, FH+i+1
+                    const int pm = (FH - 2 - i) >> 1;    // chunk holding points FH-2-i, FH-1-i
+                    if (STORE == STORE_DIRECT) {
+                        if (valid) {
+                            row_g[pp] = make_double2(up[0], up[1]);
+                            row_g[pm] = make_double2(um[1], um[0]);
+                        }
+                    } else if (STORE == STORE_SMEM) {
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pp * 16), "d"(up[0]), "d"(up[1]) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pm * 16), "d"(um[1]), "d"(um[0]) : "memory");
+                    } else {
+                        const uint32_t ap = row_tma + (pp >> 3) * 4096 + ((((uint32_t)pp & 7) << 4) ^ sw);
+                        const uint32_t am = row_tma + (pm >> 3) * 4096 + ((((uint32_t)pm & 7) << 4) ^ sw);
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ap), "d"(up[0]), "d"(up[1]) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(am), "d"(um[1]), "d"(um[0]) : "memory");
+                    }
+                }
+            }
+            if (ERR && valid) acc_sq = fma(sq, h * (2.0 * a.cF), acc_sq);
+            if (st && STORE == STORE_SMEM) {
+                __syncwarp();
+                double2* g = reinterpret_cast<double2*>(a.fine + tile * 32 * F);
+#pragma unroll 4
+                for (int it = 0; it < FH; ++it) {
+                    const int idx = it * 32 + lane;       // 16-byte unit inside the 32 x F tile
+                    constexpr int FHD = FH > 0 ? FH : 1;
+                    const int r = idx / FHD, p = idx - r * FHD;
+                    if (tile * 32 + r < a.E) {
+                        double2 v;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(tile_s + r * ((F + 2) * 8) + p * 16));
+                        g[idx] = v;
+                    }
+                }
+                __syncwarp();
+            }
+            if (st && STORE == STORE_TMA) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int b = 0; b < F / 16; ++b) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                reinterpret_cast<uint64_t>(&tmap)),
+                            "r"(b * 16), "r"((int)(tile * 32)), "r"(tile_s + b * 4096)
+                            : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                store_pending = true;
+            }
+        }
+    }
+    if (STORE == STORE_TMA && store_pending) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    if (a.err3 != nullptr) {
+        const double wsq = warp_sum(acc_sq), wmx = warp_max(acc_mx);
+        const double wf = warp_sum((double)nfail);
+        if (lane == 0) {
+            if (ERR) {
+                atomicAdd(a.err3 + 0, wsq);
+                atomic_max_nonneg(a.err3 + 1, wmx);
+            }
+            if (wf != 0.0) atomicAdd(a.err3 + 2, wf);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernel: any M <= HFL_MAX_M, any N, any F (odd counts included).  Same algorithm with
+// run-time loop bounds (per-thread work arrays live in local memory); used for shapes the
+// specialised kernel is not instantiated for.  Stores go straight to global memory.
+struct GenericTables {
+    const double* De; const double* Do; const double* Ge; const double* Go;
+    const double* fineE; const double* fineO;
+    int M, ME, MO, FH;
+};
+
+__device__ inline bool ldl_solve_rt(int n, double* A, double* b, double* dinv) {
+    bool ok = true;
+    for (int j = 0; j < n; ++j) {
+        const double piv = A[j * (j + 1) / 2 + j];
+        ok = ok && (piv > 0.0);
+        const double r = 1.0 / piv;
+        dinv[j] = r;
+        for (int i = j + 1; i < n; ++i) {
+            const double l = A[i * (i + 1) / 2 + j] * r;
+            for (int k = j + 1; k <= i; ++k) A[i * (i + 1) / 2 + k] -= l * A[k * (k + 1) / 2 + j];
+        }
+        for (int i = j + 1; i < n; ++i) A[i * (i + 1) / 2 + j] *= r;
+    }
+    for (int i = 1; i < n; ++i)
+        for (int j = 0; j < i; ++j) b[i] -= A[i * (i + 1) / 2 + j] * b[j];
+    for (int i = 0; i < n; ++i) b[i] *= dinv[i];
+    for (int j = n - 2; j >= 0; --j)
+        for (int i = j + 1; i < n; ++i) b[j] -= A[i * (i + 1) / 2 + j] * b[i];
+    return ok;
+}
+
+__global__ void __launch_bounds__(128)
+primal_generic_kernel(const PrimalArgs a, const GenericTables t, const bool want_err) {
+    constexpr int MX = HFL_MAX_M / 2;          // max block size (15 at M = 32)
+    const int ME = t.ME, MO = t.MO, M = t.M, F = a.F, FH = t.FH, N = a.N;
+    double acc_sq = 0.0, acc_mx = 0.0;
+    int nfail = 0;
+    double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
+    if (a.bc2 != nullptr) {
+        bcl = a.bc2[0]; bcr = a.bc2[1];
+        x_first = a.nodes[0]; x_last = a.nodes[a.E];
+        invL = 1.0 / (x_last - x_first);
+    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a.E;
+         e += (long long)gridDim.x * blockDim.x) {
+        const double xl = a.nodes[e], xr = a.nodes[e + 1];
+        double ul = a.u[e], ur = a.u[e + 1];
+        if (a.bc2 != nullptr) {
+            ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
+            ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;
+        }
+        const double h = xr - xl, h2 = h * h, isig = 0.25 * h2, tau = (h2 * h2) * a.c_tau;
+        const double abar = 0.5 * (ul + ur), bbar = 0.5 * (ur - ul);
+        double re[MX], ro[MX], dinv[MX];
+        double Ae[MX * (MX + 1) / 2], Ao[MX * (MX + 1) / 2];
+        for (int i = 0; i < ME; ++i) re[i] = 0.0;
+        for (int i = 0; i < MO; ++i) ro[i] = 0.0;
+        double S = 0.0, C = 0.0;
+        if (a.forcing == HFL_FORCING_SINE || want_err) sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
+        double sclE, sclO;
+        if (a.forcing == HFL_FORCING_SINE) {
+            double sb, cb;
+            sincospi(a.k_freq * h * a.cN, &sb, &cb);
+            const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
+            double s = (N & 1) ? 0.0 : sb, c = (N & 1) ? 1.0 : cb;
+            for (int j = 0; j < a.NH; ++j) {
+                for (int i = 0; i < ME; ++i) re[i] = fma(t.De[j * ME + i], c, re[i]);
+                for (int i = 0; i < MO; ++i) ro[i] = fma(t.Do[j * MO + i], s, ro[i]);
+                rotate(s, c, s2, c2);
+            }
+            sclE = -isig * a.kk * S;
+            sclO = -isig * a.kk * C;
+        } else {
+            const int jp0 = N >> 1, jm0 = (N - 1) >> 1;
+            for (int j = 0; j < a.NH; ++j) {
+                const double fp = a.f[(long long)(jp0 + j) * a.E + e];
+                const double fm = a.f[(long long)(jm0 - j) * a.E + e];
+                const double fe = 0.5 * (fp + fm), fo = 0.5 * (fp - fm);
+                for (int i = 0; i < ME; ++i) re[i] = fma(t.De[j * ME + i], fe, re[i]);
+                for (int i = 0; i < MO; ++i) ro[i] = fma(t.Do[j * MO + i], fo, ro[i]);
+            }
+            sclE = -isig;
+            sclO = -isig;
+        }
+        for (int i = 0; i < ME; ++i) re[i] = fma(sclE, re[i], tau * abar);
+        for (int i = 0; i < MO; ++i) ro[i] = fma(sclO, ro[i], tau * bbar);
+        for (int i = 0; i < ME; ++i)
+            for (int j = 0; j <= i; ++j) Ae[i * (i + 1) / 2 + j] = t.Ge[i * (i + 1) / 2 + j] + (i == j ? 2.0 * tau : tau);
+        for (int i = 0; i < MO; ++i)
+            for (int j = 0; j <= i; ++j) Ao[i * (i + 1) / 2 + j] = t.Go[i * (i + 1) / 2 + j] + (i == j ? 2.0 * tau : tau);
+        bool ok = ldl_solve_rt(ME, Ae, re, dinv);
+        if (MO > 0) ok = ldl_solve_rt(MO, Ao, ro, dinv) && ok;
+        if (!ok) {
+            for (int i = 0; i < ME; ++i) re[i] = 0.0;
+            for (int i = 0; i < MO; ++i) ro[i] = 0.0;
+            ++nfail;
+        }
+        double w0 = abar, w1 = bbar;
+        for (int i = 0; i < ME; ++i) w0 -= re[i];
+        for (int i = 0; i < MO; ++i) w1 -= ro[i];
+        if (a.status != nullptr) a.status[e] = ok ? 0 : 1;
+        if (a.coef != nullptr) {
+            double* cp = a.coef + e * M;
+            cp[0] = w0; cp[1] = w1;
+            for (int i = 0; i < ME; ++i) cp[2 + 2 * i] = re[i];
+            for (int i = 0; i < MO; ++i) cp[3 + 2 * i] = ro[i];
+        }
+        if (F > 0 && (a.fine != nullptr || want_err)) {
+            double sf = 0.0, cf = 1.0, s2f = 0.0, c2f = 1.0, sq = 0.0;
+            if (want_err) {
+                double sb, cb;
+                sincospi(a.k_freq * h * a.cF, &sb, &cb);
+                s2f = 2.0 * sb * cb; c2f = fma(-2.0 * sb, sb, 1.0);
+                if (!(F & 1)) { sf = sb; cf = cb; }
+            }
+            const int ip0 = F >> 1, im0 = (F - 1) >> 1;
+            for (int i = 0; i < FH; ++i) {
+                double Ee = w0, Oo = w1 * t.fineO[i * (MO + 1)];
+                for (int k = 0; k < ME; ++k) Ee = fma(re[k], t.fineE[i * ME + k], Ee);
+                for (int k = 0; k < MO; ++k) Oo = fma(ro[k], t.fineO[i * (MO + 1) + 1 + k], Oo);
+                const double up = Ee + Oo, um = Ee - Oo;
+                if (a.fine != nullptr) {
+                    a.fine[e * F + ip0 + i] = up;
+                    a.fine[e * F + im0 - i] = um;
+                }
+                if (want_err) {
+                    const double xe = S * cf, xo = C * sf;
+                    const double ep = up - (xe + xo), em = um - (xe - xo);
+                    const bool self = (F & 1) && i == 0;
+                    const double wgt = (i == FH - 1) ? 0.5 : 1.0;
+                    sq += self ? wgt * ep * ep : wgt * (ep * ep + em * em);
+                    acc_mx = fmax(acc_mx, fmax(fabs(ep), fabs(em)));
+                    rotate(sf, cf, s2f, c2f);
+                }
+            }
+            if (want_err) acc_sq = fma(sq, h * (2.0 * a.cF), acc_sq);
+        }
+    }
+    if (a.err3 != nullptr) {
+        const double wsq = warp_sum(acc_sq), wmx = warp_max(acc_mx), wf = warp_sum((double)nfail);
+        if ((threadIdx.x & 31) == 0) {
+            if (want_err) {
+                atomicAdd(a.err3 + 0, wsq);
+                atomic_max_nonneg(a.err3 + 1, wmx);
+            }
+            if (wf != 0.0) atomicAdd(a.err3 + 2, wf);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+// [E][F] doubles, box = 32 rows x 16 doubles (128 B inner extent, 128-byte swizzle)
+static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int F) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return HFL_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)E};
+    cuuint64_t strides[1] = {(cuuint64_t)F * sizeof(double)};
+    cuuint32_t box[2] = {16, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_fine, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return HFL_ERR_CUDA; }
+    return HFL_OK;
+}
+
+template <int M, int FH, bool ERR, int STORE>
+static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t stream) {
+    constexpr int ME = n_even(M), MO = n_odd(M), F = 2 * FH;
+    PrimalTables<M, FH> t;
+    memset(&t, 0, sizeof(t));
+    for (int i = 0; i < ME * (ME + 1) / 2; ++i) t.Ge[i] = plan->Ge[i];
+    for (int i = 0; i < MO * (MO + 1) / 2; ++i) t.Go[i] = plan->Go[i];
+    for (int i = 0; i < FH; ++i) {
+        for (int k = 0; k < ME; ++k) t.fineE[i][k] = plan->fineE[(size_t)i * ME + k];
+        for (int k = 0; k < MO + 1; ++k) t.fineO[i][k] = plan->fineO[(size_t)i * (MO + 1) + k];
+    }
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (STORE == STORE_TMA && a.fine != nullptr) {
+        int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F);
+        if (rc != HFL_OK) return rc;
+    }
+    auto kern = primal_kernel<M, FH, ERR, STORE>;
+    const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) + (size_t)a.NH * (ME + MO) * sizeof(double);
+    static thread_local const void* configured = nullptr;
+    static thread_local size_t configured_smem = 0;
+    if (configured != (const void*)kern || configured_smem < smem) {
+        HFL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = (const void*)kern;
+        configured_smem = smem;
+    }
+    int per_sm = 0;
+    HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long ntiles = (a.E + 31) / 32;
+    long long grid = (ntiles + kWarps - 1) / kWarps;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (grid > cap) grid = cap;
+    kern<<<(unsigned)grid, kThreads, smem, stream>>>(a, t, tmap);
+    count_launch();
+    HFL_CUDA_CHECK(cudaGetLastError());
+    return HFL_OK;
+}
+
+template <int M, int FH, bool ERR>
+static int dispatch_store(const hfl_plan* plan, const PrimalArgs& a, int store, cudaStream_t s) {
+    switch (store) {
+        case STORE_DIRECT: return launch_fast<M, FH, ERR, STORE_DIRECT>(plan, a, s);
+        case STORE_SMEM: return launch_fast<M, FH, ERR, STORE_SMEM>(plan, a, s);
+        default: return launch_fast<M, FH, ERR, STORE_TMA>(plan, a, s);
+    }
+}
+
+template <int M, int FH>
+static int dispatch_err(const hfl_plan* plan, const PrimalArgs& a, bool err, int store, cudaStream_t s) {
+    return err ? dispatch_store<M, FH, true>(plan, a, store, s) : dispatch_store<M, FH, false>(plan, a, store, s);
+}
+
+template <int FH>
+static int dispatch_M(const hfl_plan* plan, const PrimalArgs& a, bool err, int store, cudaStream_t s) {
+    switch (plan->M) {
+#define HFL_CASE(m)                                                                        \
+    case m:                                                                                \
+        if constexpr (FH == 0) return launch_fast<m, 0, false, STORE_DIRECT>(plan, a, s);  \
+        else return dispatch_err<m, FH>(plan, a, err, store, s);
+        HFL_CASE(3) HFL_CASE(4) HFL_CASE(5) HFL_CASE(6) HFL_CASE(7) HFL_CASE(8) HFL_CASE(9) HFL_CASE(10)
+        HFL_CASE(11) HFL_CASE(12) HFL_CASE(13) HFL_CASE(14)
+#undef HFL_CASE
+        default: return -1;
+    }
+}
+
+}  // namespace hfl
+
+using namespace hfl;
+
+extern "C" int hfl_lssvr_primal_batch(const hfl_plan_t* plan, int64_t E, const double* d_nodes, const double* d_u,
+                                      int forcing_kind, double k_freq, const double* d_f_samples,
+                                      const double* d_bc2, double* d_coef, double* d_fine, int32_t* d_status,
+                                      double* d_err3, void* stream) {
+    HFL_REQUIRE(plan != nullptr, "hfl_lssvr_primal_batch: plan is NULL");
+    HFL_REQUIRE(E >= 0, "hfl_lssvr_primal_batch: E < 0");
+    if (E == 0) return HFL_OK;
+    HFL_REQUIRE(d_nodes != nullptr && d_u != nullptr, "hfl_lssvr_primal_batch: d_nodes / d_u is NULL");
+    HFL_REQUIRE(forcing_kind == HFL_FORCING_SINE || forcing_kind == HFL_FORCING_SAMPLES,
+                "hfl_lssvr_primal_batch: unknown forcing_kind %d", forcing_kind);
+    HFL_REQUIRE(forcing_kind != HFL_FORCING_SAMPLES || d_f_samples != nullptr,
+                "hfl_lssvr_primal_batch: HFL_FORCING_SAMPLES needs d_f_samples");
+    HFL_REQUIRE(d_fine == nullptr || plan->F >= 2, "hfl_lssvr_primal_batch: d_fine given but the plan has F = 0");
+    HFL_REQUIRE(E < (1LL << 31) - 64, "hfl_lssvr_primal_batch: E too large for one call");
+    const bool want_err = (d_err3 != nullptr) && plan->F >= 2;
+    const double pi = 3.14159265358979323846;
+    PrimalArgs a;
+    a.E = E; a.nodes = d_nodes; a.u = d_u; a.f = d_f_samples; a.bc2 = d_bc2;
+    a.coef = d_coef; a.fine = d_fine; a.status = d_status; a.err3 = d_err3;
+    a.De = plan->d_tables + plan->off_De; a.Do = plan->d_tables + plan->off_Do;
+    a.N = plan->N; a.NH = plan->NH; a.F = plan->F; a.forcing = forcing_kind;
+    a.k_freq = k_freq; a.kk = (k_freq * pi) * (k_freq * pi);
+    a.c_tau = 1.0 / (16.0 * plan->gamma);
+    a.cN = 0.5 / (double)(plan->N - 1);
+    a.cF = plan->F >= 2 ? 0.5 / (double)(plan->F - 1) : 0.0;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    int store = get_option_store();
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(d_fine) & 15) == 0;
+    int rc = -1;
+    if (plan->F == 32 && aligned16) {
+        if (store == 0) store = STORE_TMA;
+        rc = dispatch_M<16>(plan, a, want_err, store, s);
+    } else if (plan->F == 0) {
+        rc = dispatch_M<0>(plan, a, false, STORE_DIRECT, s);
+    }
+    if (rc >= 0) return rc;
+
+    GenericTables t;
+    t.De = plan->d_tables + plan->off_De; t.Do = plan->d_tables + plan->off_Do;
+    t.Ge = plan->d_tables + plan->off_Ge; t.Go = plan->d_tables + plan->off_Go;
+    t.fineE = plan->d_tables + plan->off_fineE; t.fineO = plan->d_tables + plan->off_fineO;
+    t.M = plan->M; t.ME = plan->me; t.MO = plan->mo; t.FH = plan->FH;
+    long long blocks = (E + 127) / 128;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    primal_generic_kernel<<<(unsigned)blocks, 128, 0, s>>>(a, t, want_err);
+    count_launch();
+    HFL_CUDA_CHECK(cudaGetLastError());
+    return HFL_OK;
+}

@@ -1,0 +1,77 @@
+"""Multi-GPU host logic: contiguous element ranges, one process per GPU.
+
+Elements are independent given the nodal values, so K2-K5 shard with no exchange.  The coarse solve
+needs ONE exchange (SPIKE): every rank solves its own range with zero Dirichlet data at both ends,
+the ranks all-gather four doubles each ({x_first, x_last, r_left, r_right}), every rank solves the
+(G-1)-unknown interface system redundantly, and the correction - a linear function on the range - is
+applied on the fly by the element kernel (d_bc2) or by hfl_fem_apply_bc.  Error norms end with one
+all-reduce(sum) and one all-reduce(max).  All messages are a few doubles: latency-bound.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, batch
+
+
+def partition(E_global, world, rank):
+    """Contiguous element range [e0, e1) of `rank`; sizes differ by at most one."""
+    if not 0 <= rank < world:
+        raise ValueError('rank %d outside [0, %d)' % (rank, world))
+    base, rem = divmod(int(E_global), int(world))
+    e0 = rank * base + min(rank, rem)
+    return e0, e0 + base + (1 if rank < rem else 0)
+
+
+def local_nodes_linspace(a, b, E_global, world, rank, device='cuda'):
+    """Nodes of this rank's elements from the global numpy.linspace(a, b, E_global + 1)."""
+    e0, e1 = partition(E_global, world, rank)
+    return batch.mesh_linspace(a, b, E_global + 1, e0, e1 - e0 + 1, device=device)
+
+
+def _device_local_solve(nodes, k_freq, coarse_solver, out=None):
+    return batch.fem_p1_solve(nodes, k_freq=k_freq, u_left=0.0, u_right=0.0, coarse_solver=coarse_solver,
+                              out=out, want_reaction=True)
+
+
+def fem_p1_solve_distributed(nodes_local, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='assembled',
+                             group=None, local_solve=None, device_interface=True, out=None):
+    """SPIKE coarse solve.  Returns (y_local, bc2): the local zero-Dirichlet solve and the two
+    interface values {U_rank, U_rank+1} as a 2-vector on the same device as `nodes_local`;
+    u_local = y_local + linear correction (see hfl_fem_apply_bc).
+
+    `local_solve(nodes, k_freq, coarse_solver, out) -> (y, iface4)` defaults to the CUDA kernels; the
+    CPU tests inject a stand-in to exercise the exchange logic over gloo.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    solve = local_solve or _device_local_solve
+    y, mine = solve(nodes_local, k_freq, coarse_solver, out)
+    if world > 1:
+        gathered = torch.empty(4 * world, dtype=torch.float64, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    else:
+        gathered = mine
+    if mine.is_cuda and device_interface:
+        bc2 = torch.empty(2, dtype=torch.float64, device=mine.device)
+        _lib.check(_lib.load().hfl_spike_interface_solve_device(
+            world, batch._ptr(gathered), float(u_left), float(u_right), rank, batch._ptr(bc2), batch._stream()),
+            'hfl_spike_interface_solve_device')
+    else:
+        iface = batch.spike_interface_solve(gathered.cpu().tolist(), u_left, u_right)
+        bc2 = torch.tensor([iface[rank], iface[rank + 1]], dtype=torch.float64, device=mine.device)
+    return y, bc2
+
+
+def reduce_error(err3, group=None):
+    """Global (L2, max, failed) from per-rank accumulators: all-reduce(sum) on [0] and [2], all-reduce(max) on [1]."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        s = err3[[0, 2]].clone()
+        m = err3[1:2].clone()
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        vals = [s[0].item(), m[0].item(), s[1].item()]
+    else:
+        vals = err3.tolist()
+    return math.sqrt(vals[0]), vals[1], int(vals[2])

@@ -1,0 +1,144 @@
+/*
+ * hfl.h - C ABI of libhfl.so: the hybrid FEM + LSSVR hot path on NVIDIA B200 (sm_100a), FP64.
+ *
+ * The reference (maryambabaei/hybrid-FEM-LSSVR) has no FFI: its call surface is Python
+ * (P: = 1D-Possion/Hybrid-FEM-LSSVR.py, D: = 1D-Possion/Hybrid-FEM-LSSVR-Dual.py).  Each entry
+ * point below names the reference code it replaces.  All pointers named d_* are DEVICE pointers;
+ * everything is stream-ordered on `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ * stream); no entry point synchronises the device or allocates device memory behind the caller's
+ * back except hfl_plan_create (a few KB of tables).  Every function returns HFL_OK or an error code
+ * and records a message readable through hfl_last_error().  There is no CPU fallback anywhere.
+ *
+ * Conventions: E elements, n = E + 1 nodes, M Legendre coefficients (degree M - 1), N equispaced
+ * collocation points per element (end points included; the reference hard-codes 12 at P:40),
+ * F equispaced fine points per element (end points included).
+ */
+#ifndef HFL_H
+#define HFL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFL_OK 0
+#define HFL_ERR_ARG 1          /* bad argument (message says which) */
+#define HFL_ERR_CUDA 2         /* a CUDA call failed (message carries cudaGetErrorString) */
+#define HFL_ERR_UNSUPPORTED 3  /* valid request outside what this build covers */
+
+#define HFL_MAX_M 32           /* largest number of Legendre coefficients */
+#define HFL_MAX_N 256          /* largest number of collocation points */
+#define HFL_MAX_F 256          /* largest number of fine points per element */
+
+/* forcing_kind */
+#define HFL_FORCING_SINE 0     /* f(x) = (k pi)^2 sin(k pi x) evaluated on the device; k = 1 is poisson_rhs, P:11-12 */
+#define HFL_FORCING_SAMPLES 1  /* f given as samples d_f[j * E + e] = f(x_e + j h_e / (N - 1)), j < N (any rhs_func, P:20/P:45) */
+
+/* coarse_solver */
+#define HFL_COARSE_ASSEMBLED_PCR 0  /* the reference's assembled tridiagonal system, partition + parallel cyclic reduction */
+#define HFL_COARSE_FLUX_SCAN 1      /* same equations in first-order (flux) form by two prefix sums; better conditioned */
+
+typedef struct hfl_plan hfl_plan_t;
+
+const char* hfl_version(void);
+const char* hfl_last_error(void);          /* thread-local message of the last failing call */
+int hfl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- plans: element-independent tables (Legendre second derivatives at the collocation points,
+ * Gram blocks, fine-grid basis values), built on the host in extended precision and kept on the
+ * device.  Replaces the per-call `Legendre(w, domain)` / `.deriv(2)` object churn of P:43-62. */
+int hfl_plan_create(hfl_plan_t** plan, int M, int N, int F, double gamma);
+int hfl_plan_destroy(hfl_plan_t* plan);
+
+/* ---- mesh: d_out[i] = numpy.linspace(a, b, n_global)[i0 + i], i < n_local, bit for bit
+ * (P:120 `np.linspace(global_domain[0], global_domain[1], num_fem_nodes)`). */
+int hfl_mesh_linspace(double a, double b, int64_t n_global, int64_t i0, int64_t n_local,
+                      double* d_out, void* stream);
+
+/* ---- K1: coarse P1 FEM nodal solve, replaces FEMLSSVRPrimalSolver.solve_fem (P:117-145).
+ * Stiffness and the 2-point-Gauss load of -u'' = (k pi)^2 sin(k pi x) are formed on the fly from
+ * d_nodes[n]; u(d_nodes[0]) = u_left and u(d_nodes[n-1]) = u_right (both 0 in the reference, P:137).
+ * d_iface4 (optional, 4 doubles): {x_first, x_last, r_left, r_right}, the record the multi-GPU
+ * interface system needs from this range: r_left = load_0 + k_0 (u_1 - u_0), r_right = load_{n-1} +
+ * k_{n-2} (u_{n-2} - u_{n-1}) are the end-node residuals.
+ * Workspace: hfl_fem_p1_workspace_bytes(n) bytes, 256-byte aligned. */
+size_t hfl_fem_p1_workspace_bytes(int64_t n_nodes);
+int hfl_fem_p1_solve(int64_t n_nodes, const double* d_nodes, double k_freq,
+                     double u_left, double u_right, int coarse_solver,
+                     double* d_u, double* d_iface4,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Interface (SPIKE) system of a mesh split into G contiguous ranges, one per GPU.  Host function.
+ * gathered[4 * r + {0,1,2,3}] = {x_first, x_last, r_left, r_right} of rank r (its local solve had
+ * zero Dirichlet data at both ends).  Writes the G + 1 interface values (iface[0] = u_left,
+ * iface[G] = u_right); rank r then adds the linear correction with bc = {iface[r], iface[r+1]}. */
+int hfl_spike_interface_solve(int G, const double* gathered, double u_left, double u_right,
+                              double* iface);
+
+/* Same solve on the device (G <= 64), stream-ordered: d_gathered[4 G] as above (e.g. straight out of
+ * an NCCL all-gather); writes d_bc2 = {iface[rank], iface[rank + 1]} for hfl_fem_apply_bc / d_bc2. */
+int hfl_spike_interface_solve_device(int G, const double* d_gathered, double u_left, double u_right,
+                                     int rank, double* d_bc2, void* stream);
+
+/* d_u[i] += bc_left * (x_last - x_i) / L + bc_right * (x_i - x_first) / L  (discrete-harmonic
+ * correction of a local solve; the element kernels can apply it on the fly through d_bc2). */
+int hfl_fem_apply_bc(int64_t n_nodes, const double* d_nodes, double* d_u,
+                     double bc_left, double bc_right, void* stream);
+
+/* ---- K2 + K3 (+ K5): batched per-element primal LSSVR solve, replaces the loop of
+ * solve_lssvr_subproblems (P:147-176) over lssvr_primal (P:20-105) and, through d_fine, the
+ * structured part of evaluate_solution (P:184-211).
+ *   d_nodes[E+1], d_u[E+1]  nodal abscissae and FEM values (element e uses entries e, e+1)
+ *   d_bc2        optional {bc_left, bc_right}: nodal values are corrected as in hfl_fem_apply_bc
+ *   d_coef       optional out, [E][M] Legendre coefficients (P:98 `res.x[:M]`)
+ *   d_fine       optional out, [E][F] u at linspace(x_e, x_{e+1}, F)
+ *   d_status     optional out, [E]: 0 ok, 1 = factorisation broke down and the element fell back
+ *                to the linear interpolant of its two nodal values (P:171-176)
+ *   d_err3       optional in/out accumulators vs sin(k pi x) on the fine grid:
+ *                [0] += sum_e h_e/(F-1) * trapezoid_i err^2, [1] = max(., max|err|), [2] += failed elements
+ */
+int hfl_lssvr_primal_batch(const hfl_plan_t* plan, int64_t E,
+                           const double* d_nodes, const double* d_u,
+                           int forcing_kind, double k_freq, const double* d_f_samples,
+                           const double* d_bc2,
+                           double* d_coef, double* d_fine, int32_t* d_status, double* d_err3,
+                           void* stream);
+
+/* ---- K4: batched per-element dual LSSVR solve ((N+2) x (N+2) kernel system
+ * [[A A^T + I/gamma, A B^T], [B A^T, B B^T]] [alpha; beta] = [f; g], w = A^T alpha + B^T beta).
+ * The reference ships no dual code (D: is a copy of P:); arguments as hfl_lssvr_primal_batch. */
+int hfl_lssvr_dual_batch(const hfl_plan_t* plan, int64_t E,
+                         const double* d_nodes, const double* d_u,
+                         int forcing_kind, double k_freq, const double* d_f_samples,
+                         const double* d_bc2,
+                         double* d_coef, double* d_fine, int32_t* d_status, double* d_err3,
+                         void* stream);
+
+/* ---- K3 unstructured: replaces FEMLSSVRPrimalSolver.evaluate_solution (P:184-211).
+ * For each query x: first element j with nodes[j] <= x <= nodes[j+1] (a shared node goes to the
+ * LEFT element), element 0 / E-1 outside the mesh; value = numpy legval(off + scl x, coef[j]). */
+int hfl_evaluate_points(int64_t E, const double* d_nodes, int M, const double* d_coef,
+                        int64_t P, const double* d_x, double* d_out, void* stream);
+
+/* ---- K5: error norms against sin(k pi x).
+ * hfl_error_fine: same accumulators as d_err3 above from a stored fine grid [E][F].
+ * hfl_error_nodal: [0] += sum_i (u_i - sin)^2 * (x_{i+1} - x_{i-1}) / 2, [1] = max|err|. */
+int hfl_error_fine(int64_t E, int F, const double* d_nodes, const double* d_fine, double k_freq,
+                   double* d_err3, void* stream);
+int hfl_error_nodal(int64_t n_nodes, const double* d_nodes, const double* d_u, double k_freq,
+                    double* d_err3, void* stream);
+
+/* ---- tuning / introspection (bench and tests) */
+int hfl_set_option(const char* key, int value);   /* "primal_store": 0 auto, 1 direct, 2 smem, 3 tma */
+int hfl_get_option(const char* key, int* value);
+int64_t hfl_launch_count(void);                    /* kernels launched by this library so far */
+/* FP64 FMA throughput probe: launches `blocks` CTAs of 256 threads, 16 independent DFMA chains of
+ * length `iters` each; *flops receives the flop count so the caller can time it with CUDA events. */
+int hfl_fp64_probe(int blocks, int iters, double* d_out, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFL_H */

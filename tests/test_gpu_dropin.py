@@ -1,0 +1,76 @@
+"""The reference's call surface (P:20-22, P:107-211) served by the GPU library: same entry points,
+host numpy in and out, compared with what the reference itself produced (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from hybrid_fem_lssvr_b200 import FEMLSSVRPrimalSolver, batch, lssvr_primal, poisson_rhs
+from oracle import fem_p1, kkt
+from gpu_util import dev
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shipped_main_program(golden_config1):
+    """P:214-225: 25 nodes, M = 8, gamma = 1e4, 201 test points."""
+    g = golden_config1
+    solver = FEMLSSVRPrimalSolver(25, lssvr_M=8, lssvr_gamma=1e4, global_domain=(-1, 1))
+    solver.solve()
+    assert np.array_equal(solver.fem_nodes, np.array(g['nodes']))
+    assert np.max(np.abs(solver.fem_values - np.array(g['fem_values']))) <= 1e-13
+    assert len(solver.lssvr_functions) == 24
+    for i in (0, 5, 23):
+        fn = solver.lssvr_functions[i]
+        assert np.max(np.abs(fn.coef - np.array(g['coef'][i]))) <= 1e-10
+        assert list(fn.domain) == [g['nodes'][i], g['nodes'][i + 1]]
+        assert abs(fn(g['nodes'][i]) - (0.0 if i == 0 else g['fem_values'][i])) <= 1e-12   # callable like Legendre
+    xs = np.array(g['x_points'])
+    vals = solver.evaluate_solution(xs)
+    assert vals.shape == xs.shape
+    assert np.max(np.abs(vals - np.array(g['values']))) <= 1e-10     # reference evaluate_solution output
+    computed = solver.evaluate_solution(np.linspace(-1, 1, 201))
+    assert abs(np.max(np.abs(computed - np.sin(np.pi * np.linspace(-1, 1, 201)))) - 3.274e-06) <= 2e-9
+
+
+def test_evaluate_points_bit_exact_with_numpy_legval(golden_config1):
+    """Same coefficients in -> the device legval reproduces Legendre.__call__ bit for bit."""
+    g = golden_config1
+    xs = np.array(g['x_points'])
+    out = batch.evaluate_points(dev(g['nodes']), dev(np.array(g['coef'])), dev(xs)).cpu().numpy()
+    assert np.array_equal(out, np.array(g['values']))
+    rng = np.random.default_rng(0)
+    nodes = np.sort(np.concatenate([[-1.0, 1.0], rng.uniform(-1, 1, 500)]))
+    coef = rng.normal(size=(501, 11))
+    xq = np.concatenate([rng.uniform(-1.2, 1.2, 5000), nodes])
+    out = batch.evaluate_points(dev(nodes), dev(coef), dev(xq)).cpu().numpy()
+    assert np.array_equal(out, kkt.evaluate_solution(nodes, coef, xq))
+
+
+def test_lssvr_primal_signature_and_golden(golden_elements):
+    for c in golden_elements['cases'][:8]:
+        k = c['k_freq']
+        out = lssvr_primal(lambda x: (k * np.pi) ** 2 * np.sin(k * np.pi * x), [c['xmin'], c['xmax']], c['u_xmin'],
+                           c['u_xmax'], c['M'], c['gamma'])
+        assert isinstance(out, np.polynomial.Legendre) and list(out.domain) == [c['xmin'], c['xmax']]
+        runs = np.array(c['coef_runs'])
+        spread = max(np.max(np.abs(runs[i] - runs[j])) for i in range(3) for j in range(i))
+        assert np.min(np.max(np.abs(runs - out.coef), axis=1)) <= max(1e-10 * max(1.0, np.max(np.abs(out.coef))), 3 * spread)
+    # boundary flags (P:68-79): the FEM value is ignored at the global boundary
+    a = lssvr_primal(poisson_rhs, [-1.0, -0.9], 0.123, -0.3, 8, 1e4, is_left_boundary=True)
+    b = lssvr_primal(poisson_rhs, [-1.0, -0.9], 0.0, -0.3, 8, 1e4)
+    assert np.array_equal(a.coef, b.coef)
+    c_ = lssvr_primal(poisson_rhs, [-0.95, -0.9], 0.123, -0.3, 8, 1e4, is_left_boundary=True)   # not at the boundary
+    assert abs(c_(-0.95) - 0.123) <= 1e-12
+
+
+def test_custom_rhs_and_flux_solver():
+    """A host callable as rhs_func (P:20) goes through sampled forcing; 'flux' coarse solver agrees."""
+    s1 = FEMLSSVRPrimalSolver(41, lssvr_M=9, lssvr_gamma=1e4)
+    s1.solve()
+    s2 = FEMLSSVRPrimalSolver(41, lssvr_M=9, lssvr_gamma=1e4, rhs_func=lambda x: np.pi ** 2 * np.sin(np.pi * x),
+                              coarse_solver='flux')
+    s2.solve()
+    xs = np.linspace(-1, 1, 333)
+    assert np.max(np.abs(s1.evaluate_solution(xs) - s2.evaluate_solution(xs))) <= 1e-10
+    ref = fem_p1.solve_fem_p1(np.linspace(-1, 1, 41))
+    assert np.max(np.abs(s1.fem_values - ref)) <= 1e-12

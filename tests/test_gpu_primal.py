@@ -1,0 +1,206 @@
+"""Parity of the batched primal LSSVR kernels (K2 + K3 + fused K5) with the oracle, through the C ABI.
+
+Tolerance: 1e-10 relative (BASELINE.json north_star) on coefficients-as-functions, i.e. on the fine
+grid relative to max|u|, and on the coefficient vector relative to its largest entry."""
+import numpy as np
+import pytest
+import torch
+
+from hybrid_fem_lssvr_b200 import batch
+from oracle import fem_p1, kkt
+from gpu_util import dev, jittered_mesh, oracle_coef, rel, sine_samples
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _run(nodes, u, M, gamma, N=12, F=32, k=1.0, samples=None, **kw):
+    forcing = 'sine' if samples is None else dev(samples)
+    coef, fine, status = batch.lssvr_primal_batch(dev(nodes), dev(u), M, gamma, N=N, F=F, forcing=forcing, k_freq=k,
+                                                  want_fine=F > 0, want_status=True, **kw)
+    torch.cuda.synchronize()
+    return coef.cpu().numpy(), (fine.cpu().numpy() if fine is not None else None), status.cpu().numpy()
+
+
+def test_config1_against_reference_golden(golden_config1):
+    g = golden_config1
+    nodes, u = np.array(g['nodes']), np.array(g['fem_values']).copy()
+    u[0] = u[-1] = 0.0                                  # boundary-flag branches P:68-79
+    coef, fine, status = _run(nodes, u, g['M'], g['gamma'], N=g['N'])
+    assert not status.any()
+    assert np.max(np.abs(coef - np.array(g['coef']))) <= TOL          # reference lssvr_primal output
+    assert rel(fine, kkt.evaluate_fine(np.array(g['coef']), 32)) <= TOL
+
+
+def test_golden_elements_against_reference(golden_elements):
+    for c in golden_elements['cases']:
+        nodes = np.array([c['xmin'], c['xmax']])
+        u = np.array([c['u_xmin'], c['u_xmax']])
+        for samples in (None, sine_samples(nodes, 12, c['k_freq'])):
+            coef, _, status = _run(nodes, u, c['M'], c['gamma'], k=float(c['k_freq']), samples=samples, F=0)
+            runs = np.array(c['coef_runs'])
+            spread = max(np.max(np.abs(runs[i] - runs[j])) for i in range(3) for j in range(i))
+            tol = max(TOL * max(1.0, np.max(np.abs(coef))), 3.0 * spread)   # see tests/golden/make_golden.py
+            assert status[0] == 0
+            assert np.min(np.max(np.abs(runs - coef[0]), axis=1)) <= tol, c
+
+
+@pytest.mark.parametrize('M', [3, 4, 5, 8, 9, 12, 14])
+@pytest.mark.parametrize('store', [1, 2, 3])
+def test_specialised_kernel_vs_oracle(M, store):
+    E, N, gamma, k = 1000 + 37, 12, 1e4, 3.0
+    nodes = jittered_mesh(E, seed=M)
+    u = np.random.default_rng(M).uniform(-1, 1, E + 1)
+    batch.set_option('primal_store', store)
+    try:
+        coef, fine, status = _run(nodes, u, M, gamma, N=N, k=k)
+    finally:
+        batch.set_option('primal_store', 0)
+    ref = oracle_coef(nodes, u, M, gamma, N, k=k)
+    assert not status.any()
+    assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL
+    assert np.max(np.abs(coef - ref)) <= TOL * max(1.0, np.max(np.abs(ref)))
+
+
+def test_store_variants_bitwise_identical():
+    E = 4097
+    nodes = jittered_mesh(E, seed=1)
+    u = np.sin(np.pi * nodes)
+    outs = []
+    for store in (1, 2, 3):
+        batch.set_option('primal_store', store)
+        outs.append(_run(nodes, u, 9, 1e4)[1])
+    batch.set_option('primal_store', 0)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize('E', [1, 2, 31, 32, 33, 127, 128, 129, 4095])
+def test_ragged_sizes(E):
+    nodes = jittered_mesh(E, seed=E)
+    u = np.cos(nodes)
+    coef, fine, status = _run(nodes, u, 9, 1e4, k=2.0)
+    ref = oracle_coef(nodes, u, 9, 1e4, 12, k=2.0)
+    assert fine.shape == (E, 32) and not status.any()
+    assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL
+
+
+@pytest.mark.parametrize('M,N,F', [(9, 12, 16), (9, 12, 5), (9, 12, 33), (9, 7, 32), (9, 13, 32), (9, 128, 32),
+                                   (16, 128, 32), (20, 128, 32), (25, 128, 64), (5, 128, 32), (13, 128, 8), (32, 256, 256)])
+def test_generic_shapes_vs_oracle(M, N, F):
+    E, gamma, k = 300, 1e4, 2.0
+    nodes = np.linspace(-1, 1, E + 1)        # h = 1/150: the bubble is resolved, cond(G22) grows with M
+    u = np.sin(2 * np.pi * nodes) + 0.1 * nodes
+    coef, fine, status = _run(nodes, u, M, gamma, N=N, F=F, k=k)
+    ref = oracle_coef(nodes, u, M, gamma, N, k=k)
+    assert not status.any()
+    tol = TOL if M <= 20 else 1e-8           # cond(G22) ~ 1e7 at M = 25, N = 128
+    assert rel(fine, kkt.evaluate_fine(ref, F)) <= tol
+
+
+def test_samples_forcing_random_data():
+    """SURVEY.md section 8d random-data variant: u ~ U(-1,1), f ~ N(0,1); nothing can be hoisted."""
+    E, M, N = 2000, 9, 12
+    rng = np.random.default_rng(3)
+    nodes = jittered_mesh(E, seed=3)
+    u = rng.uniform(-1, 1, E + 1)
+    f = rng.normal(size=(N, E))
+    coef, fine, status = _run(nodes, u, M, 1e4, samples=f)
+    ref = oracle_coef(nodes, u, M, 1e4, N, f_samples=f)
+    assert not status.any()
+    assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL
+    # a resolved bubble: wide elements, strong forcing -> per-coefficient check (hard part 6)
+    nodes = np.linspace(-1, 1, 9)
+    u = rng.uniform(-1, 1, 9)
+    f = 50.0 * rng.normal(size=(N, 8))
+    coef, fine, _ = _run(nodes, u, M, 1e4, samples=f)
+    ref = oracle_coef(nodes, u, M, 1e4, N, f_samples=f)
+    assert np.max(np.abs(ref[:, 2:])) > 1e-2
+    assert np.max(np.abs(coef - ref)) <= TOL * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize('gamma', [1e-2, 1.0, 1e4, 1e8])
+@pytest.mark.parametrize('E', [4, 24, 10 ** 4])
+def test_gamma_and_width_range(gamma, E):
+    nodes = np.linspace(-1, 1, E + 1)
+    u = fem_p1.c_factor(2.0 / E) * np.sin(np.pi * nodes)
+    sl = slice(0, min(E, 500))
+    coef, fine, status = _run(nodes, u, 8, gamma)
+    ref = oracle_coef(nodes[:sl.stop + 1], u[:sl.stop + 1], 8, gamma, 12, k=1.0)
+    assert not status.any()
+    assert rel(fine[sl], kkt.evaluate_fine(ref, 32)) <= TOL
+
+
+def test_boundary_correction_on_the_fly():
+    E = 777
+    nodes = jittered_mesh(E, seed=9)
+    y = np.random.default_rng(9).uniform(-1, 1, E + 1)
+    bl, br = 0.37, -1.2
+    L = nodes[-1] - nodes[0]
+    u = y + (bl * (nodes[-1] - nodes) + br * (nodes - nodes[0])) / L
+    bc2 = torch.tensor([bl, br], dtype=torch.float64, device='cuda')
+    coef, fine, _ = _run(nodes, y, 9, 1e4, bc2=bc2)
+    ref = oracle_coef(nodes, u, 9, 1e4, 12, k=1.0)
+    assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL
+    u_dev = batch.fem_apply_bc(dev(nodes), dev(y), bl, br).cpu().numpy()
+    assert np.max(np.abs(u_dev - u)) <= 1e-15 * 4
+
+
+def test_breakdown_falls_back_to_linear_interpolant():
+    """More bubble unknowns than collocation points and a vanishing regulariser: the Gram block is
+    singular in FP64 -> status 1 and the P:171-176 fallback (linear interpolant of the nodal values)."""
+    E = 64
+    nodes = np.linspace(-1, 1, E + 1) * 1e-3
+    u = np.linspace(0.2, 0.9, E + 1)
+    err3 = batch.new_error_accumulator()
+    coef, fine, status = _run(nodes, u, 14, 1e12, N=4, err3=err3)
+    if status.any():
+        bad = np.nonzero(status)[0]
+        assert np.allclose(coef[bad, 2:], 0.0)
+        assert np.allclose(coef[bad, 0], 0.5 * (u[bad] + u[bad + 1]), rtol=0, atol=1e-15)
+        assert np.allclose(coef[bad, 1], 0.5 * (u[bad + 1] - u[bad]), rtol=0, atol=1e-15)
+        assert int(err3[2].item()) == len(bad)
+    assert np.isfinite(fine[status == 0]).all()
+
+
+def test_fused_error_matches_standalone_and_numpy():
+    E, k = 5000, 1.0
+    nodes = jittered_mesh(E, seed=4)
+    u = np.sin(np.pi * nodes) + 1e-6 * np.cos(3 * nodes)
+    err3 = batch.new_error_accumulator()
+    coef, fine, _ = _run(nodes, u, 9, 1e4, k=k, err3=err3)
+    l2_f, mx_f = batch.finish_error(err3)
+    l2_s, mx_s = batch.finish_error(batch.error_fine(dev(nodes), dev(fine), k))
+    x = kkt.fine_points(nodes, 32)
+    d = fine - np.sin(np.pi * x)
+    w = np.ones(32); w[0] = w[-1] = 0.5
+    l2_n = np.sqrt(np.sum((np.diff(nodes) / 31.0)[:, None] * w[None, :] * d * d))
+    mx_n = np.max(np.abs(d))
+    assert abs(l2_f - l2_n) <= 1e-9 * l2_n and abs(l2_s - l2_n) <= 1e-9 * l2_n
+    assert abs(mx_f - mx_n) <= 1e-9 * mx_n + 1e-15 and abs(mx_s - mx_n) <= 1e-9 * mx_n + 1e-15
+
+
+def test_full_size_properties():
+    """BASELINE configs[2]: 1e7 elements, M = 9, N = 12, F = 32.  Size-independent properties:
+    the boundary rows hold (end values = nodal values), neighbouring elements agree at shared nodes,
+    the reconstruction is as close to sin(pi x) as the nodal data allow, and a random sample of
+    elements matches the oracle."""
+    E = 10 ** 7
+    nodes = batch.mesh_linspace(-1.0, 1.0, E + 1)
+    u = torch.sin(np.pi * nodes)
+    err3 = batch.new_error_accumulator()
+    _, fine, status = batch.lssvr_primal_batch(nodes, u, 9, 1e4, N=12, F=32, want_coef=False, want_fine=True,
+                                               want_status=True, err3=err3)
+    torch.cuda.synchronize()
+    assert int(status.sum().item()) == 0
+    assert torch.max(torch.abs(fine[:, 0] - u[:-1])).item() <= 1e-12
+    assert torch.max(torch.abs(fine[:, -1] - u[1:])).item() <= 1e-12
+    assert torch.max(torch.abs(fine[1:, 0] - fine[:-1, -1])).item() <= 1e-12
+    l2, mx = batch.finish_error(err3)
+    assert mx <= 1e-12 and l2 <= 1e-12
+    idx = np.sort(np.random.default_rng(0).choice(E - 1, 2000, replace=False))
+    nh = nodes.cpu().numpy()
+    uh = u.cpu().numpy()
+    fh = fine[torch.from_numpy(idx).cuda()].cpu().numpy()
+    for j, e in enumerate(idx[:200]):
+        ref = oracle_coef(nh[e:e + 2], uh[e:e + 2], 9, 1e4, 12, k=1.0)
+        assert rel(fh[j:j + 1], kkt.evaluate_fine(ref, 32)) <= TOL
