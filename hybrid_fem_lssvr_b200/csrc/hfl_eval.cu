@@ -3,9 +3,10 @@
 
 namespace hfl {
 
-// numpy.polynomial.legendre.legval (legendre.py:895-910), operation for operation and without
-// fused multiply-adds, so the value matches Legendre.__call__ of the reference (P:193) bit for bit
-// given the same coefficients.
+// numpy.polynomial.legendre.legval as of numpy 2.3 (the reference pins no numpy version, README.md:34-36;
+// 2.3.5 is what generated tests/golden): Clenshaw with the ratios (nd-1)/nd and (2nd-1)/nd formed first,
+// operation for operation and without fused multiply-adds, so the value matches Legendre.__call__ of the
+// reference (P:193) bit for bit given the same coefficients.
 __device__ __forceinline__ double legval_numpy(double x, const double* __restrict__ c, int M) {
     if (M == 1) return __dadd_rn(c[0], __dmul_rn(0.0, x));
     if (M == 2) return __dadd_rn(c[0], __dmul_rn(c[1], x));
@@ -14,8 +15,8 @@ __device__ __forceinline__ double legval_numpy(double x, const double* __restric
     for (int i = 3; i <= M; ++i) {
         const double tmp = c0;
         nd = nd - 1;
-        c0 = __dsub_rn(c[M - i], __ddiv_rn(__dmul_rn(c1, (double)(nd - 1)), (double)nd));
-        c1 = __dadd_rn(tmp, __ddiv_rn(__dmul_rn(__dmul_rn(c1, x), (double)(2 * nd - 1)), (double)nd));
+        c0 = __dsub_rn(c[M - i], __dmul_rn(c1, __ddiv_rn((double)(nd - 1), (double)nd)));
+        c1 = __dadd_rn(tmp, __dmul_rn(__dmul_rn(c1, x), __ddiv_rn((double)(2 * nd - 1), (double)nd)));
     }
     return __dadd_rn(c0, __dmul_rn(c1, x));
 }

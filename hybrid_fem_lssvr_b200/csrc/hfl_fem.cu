@@ -22,9 +22,9 @@ namespace hfl {
 // x = y - u_head v - u_next w.   out = {y1, v1, w1, ys, vs, ws}.
 template <class Rows>
 __device__ __forceinline__ void chunk_reduce(const Rows& rows, int m0, int S, double (&out)[6]) {
-    if (S < 2) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) out[i] = 0.0;
+    if (S < 2) {   // no interior: neighbouring heads couple directly (x_first = u_next, x_last = u_head)
+        out[0] = 0.0; out[1] = 0.0; out[2] = -1.0;
+        out[3] = 0.0; out[4] = -1.0; out[5] = 0.0;
         return;
     }
     double l, d, r, b;
@@ -32,26 +32,26 @@ __device__ __forceinline__ void chunk_reduce(const Rows& rows, int m0, int S, do
     double dp = d, bp = b, vp = l, rp = r;
     for (int i = 2; i < S; ++i) {
         rows.get(m0 + i, l, d, r, b);
-        const double m = l / dp;
+        const double m = l * fast_rcp(dp);
         dp = d - m * rp;
         bp = b - m * bp;
         vp = -m * vp;
         rp = r;
     }
-    double inv = 1.0 / dp;
+    double inv = fast_rcp(dp);
     out[3] = bp * inv; out[4] = vp * inv; out[5] = rp * inv;
     rows.get(m0 + S - 1, l, d, r, b);
     dp = d; bp = b;
     double wp = r, lp = l;
     for (int i = S - 2; i >= 1; --i) {
         rows.get(m0 + i, l, d, r, b);
-        const double m = r / dp;
+        const double m = r * fast_rcp(dp);
         dp = d - m * lp;
         bp = b - m * bp;
         wp = -m * wp;
         lp = l;
     }
-    inv = 1.0 / dp;
+    inv = fast_rcp(dp);
     out[0] = bp * inv; out[1] = lp * inv; out[2] = wp * inv;
 }
 
@@ -78,14 +78,14 @@ __device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last
             const int im = t - delta, ip = t + delta;
             double dn = d, ln = 0.0, rn = 0.0;
             if (im >= first) {
-                const double al = -l / bufr[1 * T + im];
+                const double al = -l * fast_rcp(bufr[1 * T + im]);
                 dn = fma(al, bufr[2 * T + im], dn);
                 ln = al * bufr[0 * T + im];
 #pragma unroll
                 for (int q = 0; q < NR; ++q) rhs[q] = fma(al, bufr[(3 + q) * T + im], rhs[q]);
             }
             if (ip <= last) {
-                const double be = -r / bufr[1 * T + ip];
+                const double be = -r * fast_rcp(bufr[1 * T + ip]);
                 dn = fma(be, bufr[0 * T + ip], dn);
                 rn = be * bufr[2 * T + ip];
 #pragma unroll
@@ -99,7 +99,7 @@ __device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last
         __syncthreads();
         cur ^= 1;
     }
-    const double inv = 1.0 / d;
+    const double inv = fast_rcp(d);
 #pragma unroll
     for (int q = 0; q < NR; ++q) x[q] = rhs[q] * inv;
 }
@@ -132,7 +132,8 @@ __device__ __forceinline__ void head_equation(double lp, double dp, double rp, d
 }
 
 // Level 0, pass 1: one record per tile = {l, d, r, b of the tile head, y1, v1, w1, ys, vs, ws of the tile interior}.
-__global__ void __launch_bounds__(FT) fem_reduce_kernel(const FemArgs a, double* __restrict__ rec) {
+__global__ void __launch_bounds__(FT) fem_reduce_kernel(const FemArgs a, double* __restrict__ rec,
+                                                        double* __restrict__ yvw) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
@@ -156,6 +157,10 @@ __global__ void __launch_bounds__(FT) fem_reduce_kernel(const FemArgs a, double*
         if (t == FT - 1) { rhs[2] = r; r = 0.0; }
     }
     pcr_solve<3, FT>(sm + SM_PCR, t, 1, FT - 1, l, d, r, rhs, x);
+    {   // chunk-head partial solutions, read back by the back-substitution pass
+        double* o = yvw + (size_t)blockIdx.x * 3 * FT;
+        o[t] = x[0]; o[FT + t] = x[1]; o[2 * FT + t] = x[2];
+    }
     // x = {Y, V, W} of head t.  The tile's first interior node belongs to chunk 0 (it needs head 1's
     // solution), its last interior node to chunk T-1.  ex[0 .. 3 FT) is dead by now (pcr_solve synchronised).
     if (t == 1) { ex[0] = x[0]; ex[1] = x[1]; ex[2] = x[2]; }
@@ -233,12 +238,13 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
         rows.get(m0 + 1, lo, di, ro, bo);
         bo -= lo * ua;
         if (S == 2) bo -= ro * ub;
-        double cp = ro / di, bpv = bo / di;
+        double inv0 = fast_rcp(di);
+        double cp = ro * inv0, bpv = bo * inv0;
         if (m0 + 1 < cnt) { tc[m0 + 1] = cp; tb[m0 + 1] = bpv; }
         for (int i = 2; i < S; ++i) {
             rows.get(m0 + i, lo, di, ro, bo);
             if (i == S - 1) bo -= ro * ub;
-            const double den = 1.0 / (di - lo * cp);
+            const double den = fast_rcp(di - lo * cp);
             cp = ro * den;
             bpv = (bo - lo * bpv) * den;
             if (m0 + i < cnt) { tc[m0 + i] = cp; tb[m0 + i] = bpv; }
@@ -256,37 +262,24 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
     }
 }
 
-// Level 0, pass 2: tile head values known -> chunk heads by PCR -> chunk interiors by Thomas -> u.
+// Level 0, pass 2: tile head values known -> chunk heads from the stored partial solutions
+// (U_t = Y_t - u_P V_t - u_Q W_t) -> chunk interiors by Thomas -> u.
 __global__ void __launch_bounds__(FT) fem_backsub_kernel(const FemArgs a, const double* __restrict__ utop, int ntile,
-                                                         double* __restrict__ u) {
+                                                         const double* __restrict__ yvw, double* __restrict__ u) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
     load_tile_elements(a, P, sm);
-    __syncthreads();
-    MeshRows rows{sm + SM_K, sm + SM_LS, sm + SM_RS, P, a.n, a.uL, a.uR};
     const double uP = utop[blockIdx.x];
     const double uQ = ((int)blockIdx.x + 1 < ntile) ? utop[blockIdx.x + 1] : 0.0;
-    double six[6];
-    chunk_reduce(rows, t * FS, FS, six);
-    double lp, dp, rp, bp;
-    rows.get(t * FS, lp, dp, rp, bp);
-    double* ex = sm + SM_EX;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) ex[i * FT + t] = six[i];
-    __syncthreads();
-    double l = 0.0, d = 1.0, r = 0.0, rhs[1] = {0.0}, x[1];
-    if (t >= 1) {
-        head_equation(lp, dp, rp, bp, ex[3 * FT + t - 1], ex[4 * FT + t - 1], ex[5 * FT + t - 1], six, l, d, r, rhs[0]);
-        if (t == 1) { rhs[0] -= l * uP; l = 0.0; }
-        if (t == FT - 1) { rhs[0] -= r * uQ; r = 0.0; }
+    double* uh = sm + SM_EX;    // FT head values (+1 for the next tile's head)
+    {
+        const double* o = yvw + (size_t)blockIdx.x * 3 * FT;
+        uh[t] = (t == 0) ? uP : (o[t] - uP * o[FT + t] - uQ * o[2 * FT + t]);
+        if (t == 0) uh[FT] = uQ;
     }
-    pcr_solve<1, FT>(sm + SM_PCR, t, 1, FT - 1, l, d, r, rhs, x);
-    double* uh = ex;    // FT head values (+1 for the next tile's head)
     __syncthreads();
-    uh[t] = (t == 0) ? uP : x[0];
-    if (t == 0) uh[FT] = uQ;
-    __syncthreads();
+    MeshRows rows{sm + SM_K, sm + SM_LS, sm + SM_RS, P, a.n, a.uL, a.uR};
     const double ua = uh[t], ub = uh[t + 1];
     // Thomas on the chunk interior, compile-time length FS - 1
     double cpv[FS], bpv[FS], xs[FS];
@@ -294,13 +287,13 @@ __global__ void __launch_bounds__(FT) fem_backsub_kernel(const FemArgs a, const 
         double lo, di, ro, bo;
         rows.get(t * FS + 1, lo, di, ro, bo);
         bo -= lo * ua;
-        double inv = 1.0 / di;
+        double inv = fast_rcp(di);
         cpv[1] = ro * inv; bpv[1] = bo * inv;
 #pragma unroll
         for (int i = 2; i < FS; ++i) {
             rows.get(t * FS + i, lo, di, ro, bo);
             if (i == FS - 1) bo -= ro * ub;
-            inv = 1.0 / (di - lo * cpv[i - 1]);
+            inv = fast_rcp(di - lo * cpv[i - 1]);
             cpv[i] = ro * inv;
             bpv[i] = (bo - lo * bpv[i - 1]) * inv;
         }
@@ -381,7 +374,7 @@ static inline long long fem_ntile(long long n) { return (n + FTS - 1) / FTS; }
 extern "C" size_t hfl_fem_p1_workspace_bytes(int64_t n_nodes) {
     if (n_nodes < 2) return 256;
     const long long nt = fem_ntile(n_nodes);
-    return (size_t)(REC + 1 + 6) * (size_t)nt * sizeof(double) + 256;
+    return (size_t)(REC + 1 + 6 + 3 * FT) * (size_t)nt * sizeof(double) + 256;
 }
 
 int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes, cudaStream_t s);   // hfl_flux.cu
@@ -399,7 +392,7 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
     cudaStream_t s = (cudaStream_t)stream;
     const double pi = 3.14159265358979323846;
     FemArgs a;
-    a.n = n; a.nodes = d_nodes; a.kpi = k_freq * pi; a.kp2 = a.kpi * a.kpi; a.uL = u_left; a.uR = u_right;
+    a.n = n; a.nodes = d_nodes; a.k = k_freq; a.kpi = k_freq * pi; a.kp2 = a.kpi * a.kpi; a.uL = u_left; a.uR = u_right;
     a.gx0 = 0.5 * (-0.5773502691896257) + 0.5;   // 0.5 * leggauss(2) + 0.5
     a.gx1 = 0.5 * (0.5773502691896257) + 0.5;
     if (coarse_solver == HFL_COARSE_FLUX_SCAN) {
@@ -415,6 +408,7 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
         double* rec = reinterpret_cast<double*>(d_ws);
         double* utop = rec + (size_t)REC * nt;
         double* wsrows = utop + nt;
+        double* yvw = wsrows + 6 * (size_t)nt;
         const size_t smem0 = (size_t)SM_TOTAL * sizeof(double);
         static thread_local bool configured = false;
         if (!configured) {
@@ -424,10 +418,10 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
                                                 (int)(14 * TOPT * sizeof(double))));
             configured = true;
         }
-        fem_reduce_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, rec);
+        fem_reduce_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
         const int S = (int)((nt + TOPT - 1) / TOPT);
         fem_top_kernel<<<1, TOPT, 14 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
-        fem_backsub_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, d_u);
+        fem_backsub_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
         count_launch(3);
         HFL_CUDA_CHECK(cudaGetLastError());
     }

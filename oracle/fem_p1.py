@@ -99,4 +99,5 @@ def c_factor(h, k_freq=1.0):
     t = k_freq * np.pi * h
     x1 = 0.5 - 0.5 / np.sqrt(3.0)
     x2 = 0.5 + 0.5 / np.sqrt(3.0)
-    return t * t * (x2 * np.cos(t * x1) + x1 * np.cos(t * x2)) / (2.0 - 2.0 * np.cos(t))
+    s = np.sin(0.5 * t)
+    return t * t * (x2 * np.cos(t * x1) + x1 * np.cos(t * x2)) / (4.0 * s * s)   # 2 - 2 cos t without cancellation
