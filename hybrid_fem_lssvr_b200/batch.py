@@ -165,6 +165,38 @@ def lssvr_dual_batch(nodes, u, M, gamma, N=12, F=0, forcing='sine', k_freq=1.0, 
                           want_fine, want_status, err3, coef_out, fine_out)
 
 
+def lssvr_dual_multi(nodes, u, k_freqs, M, gamma, N=12, F=0, forcing='sine', bc2=None, want_coef=True,
+                     want_fine=False, want_status=False, err3=None):
+    """K4 with R right-hand sides per element sharing one factorisation (BASELINE configs[4]).
+
+    u [R, E+1], k_freqs [R] (CUDA tensor), forcing 'sine' or samples [R, N, E]; returns
+    (coef [R, E, M] | None, fine [R, E, F] | None, status [E] | None); err3, if given, is [R, 3].
+    """
+    _require_cuda_f64(nodes, 'nodes')
+    E = nodes.numel() - 1
+    _require_cuda_f64(u, 'u')
+    R = u.shape[0]
+    if u.shape != (R, E + 1):
+        raise ValueError('u must be [R, E + 1]')
+    _require_cuda_f64(k_freqs, 'k_freqs', R)
+    dev = nodes.device
+    plan = get_plan(M, N, F if (want_fine or err3 is not None) else 0, gamma)
+    if isinstance(forcing, torch.Tensor):
+        _require_cuda_f64(forcing, 'forcing samples', R * N * E)
+        kind, fs = _lib.FORCING_SAMPLES, forcing
+    else:
+        kind, fs = _lib.FORCING_SINE, None
+    coef = torch.empty((R, E, M), dtype=torch.float64, device=dev) if want_coef else None
+    fine = torch.empty((R, E, F), dtype=torch.float64, device=dev) if want_fine else None
+    status = torch.empty(E, dtype=torch.int32, device=dev) if want_status else None
+    if err3 is not None:
+        _require_cuda_f64(err3, 'err3', 3 * R)
+    _lib.check(_lib.load().hfl_lssvr_dual_multi(plan.handle, E, R, _ptr(nodes), _ptr(u), kind, _ptr(k_freqs), _ptr(fs),
+                                                _ptr(bc2), _ptr(coef), _ptr(fine), _ptr(status), _ptr(err3), _stream()),
+               'hfl_lssvr_dual_multi')
+    return coef, fine, status
+
+
 def evaluate_points(nodes, coef, x):
     """K3 unstructured: evaluate_solution's element search + legval on the device (P:184-211)."""
     _require_cuda_f64(nodes, 'nodes')

@@ -143,6 +143,29 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
         for (int k = 0; k < M; ++k) p->V[(size_t)i * M + k] = (double)P[k];
     }
 
+    {   // dual tables: Ct = [-D; B] and K0 = Ct Ct^T accumulated in extended precision
+        const int n = N + 2;
+        std::vector<long double> CtL((size_t)n * M);
+        for (int j = 0; j < N; ++j) {
+            long double x = -1.0L + 2.0L * (long double)j / (long double)(N - 1);
+            legendre012(M, x, P.data(), d1.data(), d2.data());
+            for (int k = 0; k < M; ++k) CtL[(size_t)j * M + k] = -d2[k];
+        }
+        for (int k = 0; k < M; ++k) {
+            CtL[(size_t)N * M + k] = (k % 2 == 0) ? 1.0L : -1.0L;
+            CtL[(size_t)(N + 1) * M + k] = 1.0L;
+        }
+        p->Ct.resize((size_t)n * M);
+        for (size_t i = 0; i < p->Ct.size(); ++i) p->Ct[i] = (double)CtL[i];
+        p->K0.resize((size_t)n * n);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                long double s = 0.0L;
+                for (int k = 0; k < M; ++k) s += CtL[(size_t)i * M + k] * CtL[(size_t)j * M + k];
+                p->K0[(size_t)i * n + j] = (double)s;
+            }
+    }
+
     // one device block, each table 16-double (128 B) aligned
     std::vector<double> blk;
     auto push = [&](const std::vector<double>& v) {
@@ -153,6 +176,7 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
     };
     p->off_De = push(p->De); p->off_Do = push(p->Do); p->off_Ge = push(p->Ge); p->off_Go = push(p->Go);
     p->off_fineE = push(p->fineE); p->off_fineO = push(p->fineO); p->off_D2 = push(p->D2); p->off_V = push(p->V);
+    p->off_Ct = push(p->Ct); p->off_K0 = push(p->K0);
     p->n_tables = blk.size();
     cudaError_t e = cudaMalloc((void**)&p->d_tables, blk.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tables, blk.data(), blk.size() * sizeof(double), cudaMemcpyHostToDevice);

@@ -56,7 +56,9 @@ struct hfl_plan {
     // Full tables (dual path, generic kernels)
     std::vector<double> D2;     // [N][M]  P_k''(xi_j)
     std::vector<double> V;      // [F][M]  P_k(xi_i)
+    std::vector<double> Ct;     // [N+2][M] rows -P_k''(xi_j) (j < N), then (-1)^k, then 1: the scaled [A; B]
+    std::vector<double> K0;     // [N+2][N+2] Ct Ct^T (dual kernel matrix without the tau I block)
     // Device block holding all of the above back to back
     double* d_tables = nullptr;
-    size_t off_De, off_Do, off_Ge, off_Go, off_fineE, off_fineO, off_D2, off_V, n_tables;
+    size_t off_De, off_Do, off_Ge, off_Go, off_fineE, off_fineO, off_D2, off_V, off_Ct, off_K0, n_tables;
 };

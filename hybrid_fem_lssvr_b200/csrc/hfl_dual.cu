@@ -1,13 +1,323 @@
-// K4: batched per-element dual LSSVR solve (placeholder until the pivoted factorisation lands).
+// K4: batched per-element DUAL LSSVR solve.
+//
+// The reference ships no dual code (D: is a copy of P:).  The dual of the QP of
+// P:47-81 (Lagrangian stationarity w = A^T alpha + B^T beta, e = alpha / gamma) is the (N+2) x (N+2) system
+//     [[A A^T + I/gamma, A B^T], [B A^T, B B^T]] [alpha; beta] = [f; g],      A = -sigma D, sigma = (2/h)^2.
+// Scaled by diag(1/sigma, 1) on both sides it reads
+//     (K0 + tau J) z = [f / sigma; g],   K0 = Ct Ct^T, Ct = [-D; B], J = diag(I_N, 0), tau = h^4 / (16 gamma),
+//     w = Ct^T z
+// so the element enters through tau, 1/sigma and the data only.  K0 has rank <= M < N + 2: once
+// tau < eps |K0| the matrix is numerically singular (plain Cholesky returns NaN).  It is
+// factorised PER ELEMENT by a diagonally pivoted (rank-revealing) Cholesky that stops when the largest
+// remaining diagonal entry falls below 2^-10 eps max_diag; the basic solution (zeros outside the pivot
+// set) gives the same w as the primal to ~1e-13 wherever the dual formula itself is well conditioned.
+//
+// One TEAM per element: a warp when N + 2 <= 32 (4 elements per CTA), a 256-thread CTA otherwise.  The
+// matrix lives in shared memory and is addressed through a permutation (no physical row swaps); the
+// factorisation is right-looking with the trailing update spread over the team.  Right-hand sides (R
+// forcing frequencies per element, BASELINE configs[4]) share the factorisation: thread r solves RHS r
+// with broadcast reads of L, then the whole team evaluates the R x F fine values.
 #include "hfl_device.cuh"
 
+namespace hfl {
+
+struct DualArgs {
+    long long E;
+    int R;                  // right-hand sides per element
+    const double* nodes;    // [E+1]
+    const double* u;        // [R][E+1]
+    const double* f;        // samples [R][N][E] or NULL
+    const double* kf;       // [R] forcing frequencies (device) or NULL -> k_scalar
+    double k_scalar;
+    const double* bc2;      // optional {bc_left, bc_right}
+    double* coef;           // optional [R][E][M]
+    double* fine;           // optional [R][E][F]
+    int* status;            // optional [E]
+    double* err3;           // optional [R][3]
+    const double* K0;       // [n][n]
+    const double* Ct;       // [n][M]
+    const double* V;        // [F][M]
+    int M, N, F, n, ld;
+    int forcing;
+    double c_tau;           // 1 / (16 gamma)
+    bool want_err;
+};
+
+template <int TS>
+__device__ __forceinline__ void team_sync() {
+    if (TS == 32) __syncwarp(); else __syncthreads();
+}
+
+// (value, index) arg-max over the team; result valid in every thread.  red: 2 * (TS / 32) doubles of smem.
+template <int TS>
+__device__ __forceinline__ void team_argmax(double& v, int& idx, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if (TS > 32) {
+        const int w = threadIdx.x >> 5, nw = TS / 32;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { red[w] = v; red[nw + w] = (double)idx; }
+        __syncthreads();
+        v = red[0]; idx = (int)red[nw];
+        for (int q = 1; q < nw; ++q) {
+            const double ov = red[q];
+            const int oi = (int)red[nw + q];
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+    }
+}
+
+constexpr int DUAL_NMAX = 160 + 2;     // largest system this kernel holds in shared memory
+
+template <int TS>
+__global__ void __launch_bounds__(TS == 32 ? 128 : TS) dual_kernel(const DualArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TEAMS = (TS == 32) ? 4 : 1;
+    const int n = a.n, ld = a.ld, M = a.M, N = a.N, F = a.F, R = a.R;
+    const int team = (TS == 32) ? (threadIdx.x >> 5) : 0;
+    const int t = (TS == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    // per-team shared memory: A [n][ld] | invl [n] | wbuf [R][M] | eacc [2R] | red [16] | perm [n] (int) | misc
+    const size_t team_doubles = (size_t)n * ld + n + (size_t)R * M + 2 * (size_t)R + 16;
+    const size_t team_bytes = ((team_doubles * 8 + (size_t)n * 4 + 16) + 15) / 16 * 16;
+    unsigned char* base = smem_raw + team * team_bytes;
+    double* A = reinterpret_cast<double*>(base);
+    double* invl = A + (size_t)n * ld;
+    double* wbuf = invl + n;
+    double* eacc = wbuf + (size_t)R * M;      // per right-hand side: sum of weighted squares, max (as bits)
+    double* red = eacc + 2 * (size_t)R;
+    int* perm = reinterpret_cast<int*>(red + 16);
+    int* misc = perm + n;            // [0] = rank
+
+    double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
+    if (a.bc2 != nullptr) {
+        bcl = a.bc2[0]; bcr = a.bc2[1];
+        x_first = a.nodes[0]; x_last = a.nodes[a.E];
+        invL = 1.0 / (x_last - x_first);
+    }
+    const double eps_tol = 2.220446049250313e-16 * (1.0 / 1024.0);
+    for (int i = t; i < 2 * R; i += TS) eacc[i] = 0.0;
+    int nfail = 0;
+
+    for (long long e = (long long)blockIdx.x * TEAMS + team; e < a.E; e += (long long)gridDim.x * TEAMS) {
+        const double xl = a.nodes[e], xr = a.nodes[e + 1];
+        const double h = xr - xl, h2 = h * h;
+        const double isig = 0.25 * h2, tau = (h2 * h2) * a.c_tau;
+
+        // ---- A = K0 + tau J
+        for (int idx = t; idx < n * n; idx += TS) {
+            const int i = idx / n, j = idx - i * n;
+            double v = a.K0[idx];
+            if (i == j && i < N) v += tau;
+            A[i * ld + j] = v;
+        }
+        for (int i = t; i < n; i += TS) perm[i] = i;
+        team_sync<TS>();
+
+        // ---- diagonally pivoted Cholesky with truncation (right-looking, permutation-addressed)
+        double dmax0 = 0.0;
+        int rank = 0;
+        for (int k = 0; k < n; ++k) {
+            double v = -1.0;
+            int pos = 0x7fffffff;
+            for (int i = k + t; i < n; i += TS) {
+                const int pi = perm[i];
+                const double d = A[pi * ld + pi];
+                if (d > v) { v = d; pos = i; }
+            }
+            team_argmax<TS>(v, pos, red);
+            if (k == 0) dmax0 = v;
+            if (!(v > eps_tol * dmax0)) break;
+            if (t == 0) {
+                const int tmp = perm[k]; perm[k] = perm[pos]; perm[pos] = tmp;
+            }
+            team_sync<TS>();
+            const int pk = perm[k];
+            const double il = rsqrt(v);
+            if (t == 0) invl[k] = il;
+            for (int i = k + 1 + t; i < n; i += TS) A[perm[i] * ld + pk] *= il;     // L_ik
+            team_sync<TS>();
+            const int m = n - k - 1;
+            for (int idx = t; idx < m * m; idx += TS) {
+                const int ii = idx / m, jj = idx - ii * m;
+                const int pi = perm[k + 1 + ii], pj = perm[k + 1 + jj];
+                A[pi * ld + pj] = fma(-A[pi * ld + pk], A[pj * ld + pk], A[pi * ld + pj]);
+            }
+            team_sync<TS>();
+            rank = k + 1;
+        }
+        if (t == 0 && a.status != nullptr) a.status[e] = (rank >= 2) ? 0 : 1;
+
+        // ---- solves: thread r handles right-hand side r
+        for (int r0 = 0; r0 < R; r0 += TS) {
+            const int r = r0 + t;
+            if (r < R) {
+                const double kf = a.kf ? a.kf[r] : a.k_scalar;
+                const double kk = (kf * 3.14159265358979323846) * (kf * 3.14159265358979323846);
+                double ul = a.u[(long long)r * (a.E + 1) + e], ur = a.u[(long long)r * (a.E + 1) + e + 1];
+                if (a.bc2 != nullptr) {
+                    ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
+                    ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;
+                }
+                double y[DUAL_NMAX];
+                const double hstep = h / (double)(N - 1);
+                for (int k = 0; k < rank; ++k) {
+                    const int pk = perm[k];
+                    double b;
+                    if (pk < N) {
+                        const double fv = (a.forcing == HFL_FORCING_SINE)
+                                              ? kk * sinpi(kf * fma((double)pk, hstep, xl))
+                                              : a.f[((long long)r * N + pk) * a.E + e];
+                        b = fv * isig;
+                    } else {
+                        b = (pk == N) ? ul : ur;
+                    }
+                    for (int j = 0; j < k; ++j) b = fma(-A[pk * ld + perm[j]], y[j], b);
+                    y[k] = b * invl[k];
+                }
+                for (int k = rank - 1; k >= 0; --k) {
+                    double b = y[k];
+                    const int pk = perm[k];
+                    for (int j = k + 1; j < rank; ++j) b = fma(-A[perm[j] * ld + pk], y[j], b);
+                    y[k] = b * invl[k];
+                }
+                double* w = wbuf + (size_t)r * M;
+                if (rank >= 2) {
+                    for (int mm = 0; mm < M; ++mm) {
+                        double s = 0.0;
+                        for (int k = 0; k < rank; ++k) s = fma(a.Ct[perm[k] * M + mm], y[k], s);
+                        w[mm] = s;
+                    }
+                } else {   // P:171-176 fallback: linear interpolant of the nodal values
+                    for (int mm = 0; mm < M; ++mm) w[mm] = 0.0;
+                    w[0] = 0.5 * (ul + ur);
+                    w[1] = 0.5 * (ur - ul);
+                }
+                if (a.coef != nullptr) {
+                    double* cp = a.coef + ((long long)r * a.E + e) * M;
+                    for (int mm = 0; mm < M; ++mm) cp[mm] = w[mm];
+                }
+            }
+            team_sync<TS>();
+            // ---- fine grid (and error norms) for the right-hand sides of this batch
+            if (F > 0 && (a.fine != nullptr || a.want_err)) {
+                const int rb = min(TS, R - r0);
+                const double xc = 0.5 * (xl + xr);
+                for (int idx = t; idx < rb * F; idx += TS) {
+                    const int rr = idx / F, i = idx - rr * F;
+                    const double* w = wbuf + (size_t)(r0 + rr) * M;
+                    double s = 0.0;
+                    for (int mm = M - 1; mm >= 0; --mm) s = fma(w[mm], a.V[i * M + mm], s);
+                    if (a.fine != nullptr) a.fine[((long long)(r0 + rr) * a.E + e) * F + i] = s;
+                    if (a.want_err) {
+                        const double kf = a.kf ? a.kf[r0 + rr] : a.k_scalar;
+                        const double xi = (double)(2 * i - (F - 1)) / (double)(F - 1);
+                        const double d = s - sinpi(kf * fma(0.5 * h, xi, xc));
+                        const double wq = ((i == 0 || i == F - 1) ? 0.5 : 1.0) * h / (double)(F - 1);
+                        atomicAdd(eacc + 2 * (r0 + rr), wq * d * d);
+                        atomic_max_nonneg(eacc + 2 * (r0 + rr) + 1, fabs(d));
+                    }
+                }
+            }
+            team_sync<TS>();
+        }
+        if (rank < 2) ++nfail;
+    }
+    if (a.err3 != nullptr) {
+        team_sync<TS>();
+        for (int r = t; r < R; r += TS) {
+            if (a.want_err) {
+                atomicAdd(a.err3 + 3 * r, eacc[2 * r]);
+                atomic_max_nonneg(a.err3 + 3 * r + 1, eacc[2 * r + 1]);
+            }
+            if (nfail) atomicAdd(a.err3 + 3 * r + 2, (double)nfail);
+        }
+    }
+}
+
+static int launch_dual(const hfl_plan* plan, long long E, int R, const double* d_nodes, const double* d_u,
+                       int forcing_kind, const double* d_kf, double k_scalar, const double* d_f, const double* d_bc2,
+                       double* d_coef, double* d_fine, int* d_status, double* d_err3, cudaStream_t s) {
+    DualArgs a;
+    a.E = E; a.R = R; a.nodes = d_nodes; a.u = d_u; a.f = d_f; a.kf = d_kf; a.k_scalar = k_scalar; a.bc2 = d_bc2;
+    a.coef = d_coef; a.fine = d_fine; a.status = d_status; a.err3 = d_err3;
+    a.K0 = plan->d_tables + plan->off_K0; a.Ct = plan->d_tables + plan->off_Ct; a.V = plan->d_tables + plan->off_V;
+    a.M = plan->M; a.N = plan->N; a.F = plan->F; a.n = plan->N + 2; a.ld = a.n | 1;
+    a.forcing = forcing_kind; a.c_tau = 1.0 / (16.0 * plan->gamma);
+    a.want_err = (d_err3 != nullptr) && plan->F >= 2;
+    const int n = a.n;
+    const size_t team_doubles = (size_t)n * a.ld + n + (size_t)R * a.M + 2 * (size_t)R + 16;
+    const size_t team_bytes = ((team_doubles * 8 + (size_t)n * 4 + 16) + 15) / 16 * 16;
+    int dev = 0, max_smem = 0;
+    HFL_CUDA_CHECK(cudaGetDevice(&dev));
+    HFL_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (n <= 32 && 4 * team_bytes <= (size_t)max_smem) {
+        const size_t smem = 4 * team_bytes;
+        HFL_CUDA_CHECK(cudaFuncSetAttribute(dual_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dual_kernel<32>, 128, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (E + 3) / 4;
+        const long long cap = (long long)sm_count() * per_sm;
+        if (grid > cap) grid = cap;
+        dual_kernel<32><<<(unsigned)grid, 128, smem, s>>>(a);
+    } else {
+        if (team_bytes > (size_t)max_smem) {
+            set_error("hfl_lssvr_dual: N=%d, R=%d, M=%d need %zu bytes of shared memory per element (limit %d)",
+                      plan->N, R, plan->M, team_bytes, max_smem);
+            return HFL_ERR_UNSUPPORTED;
+        }
+        HFL_CUDA_CHECK(cudaFuncSetAttribute(dual_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_bytes));
+        int per_sm = 0;
+        HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dual_kernel<256>, 256, team_bytes));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = E;
+        const long long cap = (long long)sm_count() * per_sm;
+        if (grid > cap) grid = cap;
+        dual_kernel<256><<<(unsigned)grid, 256, team_bytes, s>>>(a);
+    }
+    count_launch();
+    HFL_CUDA_CHECK(cudaGetLastError());
+    return HFL_OK;
+}
+
+}  // namespace hfl
+
 using namespace hfl;
+
+static int dual_check(const hfl_plan_t* plan, int64_t E, int R, const double* d_nodes, const double* d_u,
+                      int forcing_kind, const double* d_f, double* d_fine) {
+    HFL_REQUIRE(plan != nullptr, "hfl_lssvr_dual: plan is NULL");
+    HFL_REQUIRE(E >= 0 && R >= 1, "hfl_lssvr_dual: E < 0 or R < 1");
+    HFL_REQUIRE(E == 0 || (d_nodes != nullptr && d_u != nullptr), "hfl_lssvr_dual: d_nodes / d_u is NULL");
+    HFL_REQUIRE(forcing_kind == HFL_FORCING_SINE || forcing_kind == HFL_FORCING_SAMPLES,
+                "hfl_lssvr_dual: unknown forcing_kind %d", forcing_kind);
+    HFL_REQUIRE(forcing_kind != HFL_FORCING_SAMPLES || d_f != nullptr, "hfl_lssvr_dual: HFL_FORCING_SAMPLES needs d_f_samples");
+    HFL_REQUIRE(d_fine == nullptr || plan->F >= 2, "hfl_lssvr_dual: d_fine given but the plan has F = 0");
+    HFL_REQUIRE(plan->N + 2 <= DUAL_NMAX, "hfl_lssvr_dual: N=%d exceeds the dual limit of %d collocation points", plan->N,
+                DUAL_NMAX - 2);
+    return HFL_OK;
+}
 
 extern "C" int hfl_lssvr_dual_batch(const hfl_plan_t* plan, int64_t E, const double* d_nodes, const double* d_u,
                                     int forcing_kind, double k_freq, const double* d_f_samples, const double* d_bc2,
                                     double* d_coef, double* d_fine, int32_t* d_status, double* d_err3, void* stream) {
-    (void)plan; (void)E; (void)d_nodes; (void)d_u; (void)forcing_kind; (void)k_freq; (void)d_f_samples; (void)d_bc2;
-    (void)d_coef; (void)d_fine; (void)d_status; (void)d_err3; (void)stream;
-    set_error("hfl_lssvr_dual_batch: not implemented in this build");
-    return HFL_ERR_UNSUPPORTED;
+    int rc = dual_check(plan, E, 1, d_nodes, d_u, forcing_kind, d_f_samples, d_fine);
+    if (rc != HFL_OK || E == 0) return rc;
+    return launch_dual(plan, E, 1, d_nodes, d_u, forcing_kind, nullptr, k_freq, d_f_samples, d_bc2, d_coef, d_fine,
+                       d_status, d_err3, (cudaStream_t)stream);
+}
+
+extern "C" int hfl_lssvr_dual_multi(const hfl_plan_t* plan, int64_t E, int R, const double* d_nodes, const double* d_u,
+                                    int forcing_kind, const double* d_k_freq, const double* d_f_samples,
+                                    const double* d_bc2, double* d_coef, double* d_fine, int32_t* d_status,
+                                    double* d_err3, void* stream) {
+    int rc = dual_check(plan, E, R, d_nodes, d_u, forcing_kind, d_f_samples, d_fine);
+    if (rc != HFL_OK || E == 0) return rc;
+    HFL_REQUIRE(forcing_kind != HFL_FORCING_SINE || d_k_freq != nullptr, "hfl_lssvr_dual_multi: d_k_freq is NULL");
+    return launch_dual(plan, E, R, d_nodes, d_u, forcing_kind, d_k_freq, 1.0, d_f_samples, d_bc2, d_coef, d_fine,
+                       d_status, d_err3, (cudaStream_t)stream);
 }

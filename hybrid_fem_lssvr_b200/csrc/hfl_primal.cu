@@ -61,8 +61,11 @@ __host__ __device__ constexpr int tile_bytes(int F) {
     return STORE == STORE_TMA ? (F / 16) * 4096 : (STORE == STORE_SMEM ? 32 * (F + 2) * 8 : 0);
 }
 
+// CTAs per SM the register budget is sized for: small systems fit 128 registers (4 CTAs = 16 warps)
+__host__ __device__ constexpr int min_ctas(int M, bool err) { return (M <= 10 && !err) ? 4 : 3; }
+
 template <int M, int FH, bool ERR, int STORE>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, min_ctas(M, ERR))
 primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
               const __grid_constant__ CUtensorMap tmap) {
     constexpr int ME = n_even(M), MO = n_odd(M);
@@ -91,13 +94,27 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
     bool store_pending = false;
 
     const long long ntiles = (a.E + 31) >> 5;
-    for (long long tile = (long long)blockIdx.x * kWarps + warp; tile < ntiles;
-         tile += (long long)gridDim.x * kWarps) {
+    const long long tile_step = (long long)gridDim.x * kWarps;
+    long long tile = (long long)blockIdx.x * kWarps + warp;
+    // nodal data of the next tile are fetched while the current one computes (hides the DRAM latency
+    // that 3-4 warps per scheduler cannot)
+    double nxl = 0.0, nxr = 0.0, nul = 0.0, nur = 0.0;
+    if (tile < ntiles) {
+        const long long e0 = min(tile * 32 + lane, a.E - 1);
+        nxl = __ldg(a.nodes + e0); nxr = __ldg(a.nodes + e0 + 1);
+        nul = __ldg(a.u + e0); nur = __ldg(a.u + e0 + 1);
+    }
+    for (; tile < ntiles; tile += tile_step) {
         const long long e_raw = tile * 32 + lane;
         const bool valid = e_raw < a.E;
         const long long e = valid ? e_raw : a.E - 1;
-        const double xl = __ldg(a.nodes + e), xr = __ldg(a.nodes + e + 1);
-        double ul = __ldg(a.u + e), ur = __ldg(a.u + e + 1);
+        const double xl = nxl, xr = nxr;
+        double ul = nul, ur = nur;
+        if (tile + tile_step < ntiles) {
+            const long long en = min((tile + tile_step) * 32 + lane, a.E - 1);
+            nxl = __ldg(a.nodes + en); nxr = __ldg(a.nodes + en + 1);
+            nul = __ldg(a.u + en); nur = __ldg(a.u + en + 1);
+        }
         if (a.bc2 != nullptr) {
             ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
             ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;

@@ -116,6 +116,16 @@ int hfl_lssvr_dual_batch(const hfl_plan_t* plan, int64_t E,
                          double* d_coef, double* d_fine, int32_t* d_status, double* d_err3,
                          void* stream);
 
+/* Same with R right-hand sides per element sharing one factorisation (BASELINE configs[4]: a batch of
+ * forcing frequencies): d_u [R][E+1], d_k_freq [R] (device), d_f_samples [R][N][E], d_coef [R][E][M],
+ * d_fine [R][E][F], d_status [E], d_err3 [R][3]. */
+int hfl_lssvr_dual_multi(const hfl_plan_t* plan, int64_t E, int R,
+                         const double* d_nodes, const double* d_u,
+                         int forcing_kind, const double* d_k_freq, const double* d_f_samples,
+                         const double* d_bc2,
+                         double* d_coef, double* d_fine, int32_t* d_status, double* d_err3,
+                         void* stream);
+
 /* ---- K3 unstructured: replaces FEMLSSVRPrimalSolver.evaluate_solution (P:184-211).
  * For each query x: first element j with nodes[j] <= x <= nodes[j+1] (a shared node goes to the
  * LEFT element), element 0 / E-1 outside the mesh; value = numpy legval(off + scl x, coef[j]). */

@@ -1,0 +1,97 @@
+"""Parity of the batched dual LSSVR kernel (K4) with the dual oracle and, by strong duality, with the
+primal oracle and the primal kernel.  The reference ships no dual code."""
+import numpy as np
+import pytest
+import torch
+
+from hybrid_fem_lssvr_b200 import batch
+from oracle import dual, fem_p1, kkt
+from gpu_util import dev, jittered_mesh, oracle_coef, rel, sine_samples
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _run_dual(nodes, u, M, gamma, N=12, F=32, k=1.0, samples=None, **kw):
+    forcing = 'sine' if samples is None else dev(samples)
+    coef, fine, status = batch.lssvr_dual_batch(dev(nodes), dev(u), M, gamma, N=N, F=F, forcing=forcing, k_freq=k,
+                                                want_fine=F > 0, want_status=True, **kw)
+    torch.cuda.synchronize()
+    return coef.cpu().numpy(), (fine.cpu().numpy() if fine is not None else None), status.cpu().numpy()
+
+
+def test_config1_dual_equals_reference_primal(golden_config1):
+    """The 'Dual' script is the primal script: its outputs are the golden primal outputs."""
+    g = golden_config1
+    nodes, u = np.array(g['nodes']), np.array(g['fem_values']).copy()
+    u[0] = u[-1] = 0.0
+    coef, fine, status = _run_dual(nodes, u, g['M'], g['gamma'], N=g['N'])
+    assert not status.any()
+    assert rel(fine, kkt.evaluate_fine(np.array(g['coef']), 32)) <= TOL
+
+
+@pytest.mark.parametrize('E', [1, 3, 4, 5, 1000, 10 ** 5])
+def test_small_system_vs_oracles(E):
+    """BASELINE configs[1] shape: M = 9, N = 12 (14 x 14 systems), one warp per element."""
+    M, N, gamma, k = 9, 12, 1e4, 1.0
+    nodes = jittered_mesh(E, seed=E)
+    u = fem_p1.c_factor(2.0 / E) * np.sin(np.pi * nodes) if E > 10 else np.cos(nodes)
+    coef, fine, status = _run_dual(nodes, u, M, gamma, N=N, k=k)
+    assert not status.any()
+    sl = slice(0, min(E, 300))
+    f = sine_samples(nodes[:sl.stop + 1], N, k)
+    ref_p = kkt.lssvr_primal_kkt_batch(nodes[:sl.stop + 1], u[:sl.stop + 1], f.T.copy(), M, gamma)
+    ref_d = dual.lssvr_dual_batch(nodes[:sl.stop + 1], u[:sl.stop + 1], f.T.copy(), M, gamma)
+    assert rel(kkt.evaluate_fine(ref_d, 32), kkt.evaluate_fine(ref_p, 32)) <= 1e-12     # strong duality (oracle check)
+    assert rel(fine[sl], kkt.evaluate_fine(ref_d, 32)) <= TOL
+    assert rel(fine[sl], kkt.evaluate_fine(ref_p, 32)) <= TOL
+
+
+def test_dual_matches_primal_kernel_full_size():
+    """BASELINE configs[1]: 1e6 elements, degree 8.  Property: dual and primal kernels agree everywhere."""
+    E = 10 ** 6
+    nodes = batch.mesh_linspace(-1.0, 1.0, E + 1)
+    u = batch.fem_p1_solve(nodes, coarse_solver='flux')
+    _, fp, _ = batch.lssvr_primal_batch(nodes, u, 9, 1e4, N=12, F=32, want_coef=False, want_fine=True)
+    err3 = batch.new_error_accumulator()
+    _, fd, st = batch.lssvr_dual_batch(nodes, u, 9, 1e4, N=12, F=32, want_coef=False, want_fine=True, want_status=True,
+                                       err3=err3)
+    torch.cuda.synchronize()
+    assert int(st.sum().item()) == 0
+    assert torch.max(torch.abs(fp - fd)).item() <= TOL
+    l2, mx = batch.finish_error(err3)
+    assert mx <= 1e-10
+
+
+@pytest.mark.parametrize('M', [5, 9, 13, 17, 21, 25])
+def test_large_system_multi_rhs(M):
+    """BASELINE configs[4]: N = 128 (130 x 130 systems), R forcing frequencies sharing one factorisation."""
+    E, N, F, gamma, R = 64, 128, 32, 1e4, 8
+    nodes = np.linspace(-1, 1, E + 1) * 0.01 + 0.3          # h = 3.1e-4: k h <= 0.02, resolved for every k
+    ks = np.array([1.0, 2.0, 5.0, 8.0, 16.0, 32.0, 48.0, 64.0])
+    u = np.stack([np.sin(k * np.pi * nodes) for k in ks])
+    err3 = torch.zeros((R, 3), dtype=torch.float64, device='cuda')
+    coef, fine, status = batch.lssvr_dual_multi(dev(nodes), dev(u), dev(ks), M, gamma, N=N, F=F, want_fine=True,
+                                                want_status=True, err3=err3)
+    torch.cuda.synchronize()
+    assert not status.cpu().numpy().any()
+    for r, k in enumerate(ks):
+        ref = oracle_coef(nodes, u[r], M, gamma, N, k=k)
+        assert rel(fine[r].cpu().numpy(), kkt.evaluate_fine(ref, F)) <= TOL, (M, k)
+    e = err3.cpu().numpy()
+    assert np.all(e[:, 1] < 1e-6) and np.all(e[:, 2] == 0)
+
+
+def test_samples_forcing_and_boundary_correction():
+    E, M, N = 500, 9, 12
+    rng = np.random.default_rng(2)
+    nodes = jittered_mesh(E, seed=2)
+    y = rng.uniform(-1, 1, E + 1)
+    f = rng.normal(size=(N, E))
+    bl, br = 0.2, -0.4
+    u = y + (bl * (nodes[-1] - nodes) + br * (nodes - nodes[0])) / (nodes[-1] - nodes[0])
+    bc2 = torch.tensor([bl, br], dtype=torch.float64, device='cuda')
+    coef, fine, status = _run_dual(nodes, y, M, 1e4, samples=f, bc2=bc2)
+    ref = oracle_coef(nodes, u, M, 1e4, N, f_samples=f)
+    assert not status.any()
+    assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from oracle import fem_p1, kkt, kkt_mp, ref_loader
+from oracle import dual, fem_p1, kkt, kkt_mp, ref_loader
 
 
 def _rhs(k):
@@ -107,3 +107,17 @@ def test_reference_function_runs_and_agrees():
     w = kkt.lssvr_primal_kkt(ns['poisson_rhs'], [-0.25, -1 / 6], -0.70, -0.5, 8, 1e4)
     assert np.max(np.abs(out.coef - w)) <= 1e-10
     assert list(out.domain) == [-0.25, -1 / 6]
+
+
+@pytest.mark.parametrize('E,M,N,k', [(24, 8, 12, 1), (1000, 9, 12, 1), (10 ** 6, 9, 12, 1), (10 ** 4, 5, 128, 1),
+                                      (10 ** 4, 13, 128, 64), (10 ** 4, 25, 128, 64)])
+def test_dual_oracle_strong_duality(E, M, N, k):
+    """The dual system gives the primal minimiser (the only oracle a dual implementation can have here)."""
+    h = 2.0 / E
+    x = np.linspace(0.3, 0.3 + h, N)
+    f = _rhs(k)(x)
+    g = np.sin(k * np.pi * np.array([0.3, 0.3 + h]))
+    wd = dual.lssvr_dual(f, 0.3, 0.3 + h, g[0], g[1], M, 1e4)
+    wp = kkt.lssvr_primal_kkt_batch(np.array([0.3, 0.3 + h]), g, f[None, :], M, 1e4)[0]
+    V = np.polynomial.legendre.legvander(np.linspace(-1, 1, 32), M - 1)
+    assert np.max(np.abs(V @ wd - V @ wp)) <= 1e-12 * np.max(np.abs(V @ wp))
