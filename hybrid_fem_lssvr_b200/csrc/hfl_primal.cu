@@ -93,25 +93,27 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
     int nfail = 0;
     bool store_pending = false;
 
-    const long long ntiles = (a.E + 31) >> 5;
-    const long long tile_step = (long long)gridDim.x * kWarps;
-    long long tile = (long long)blockIdx.x * kWarps + warp;
+    // CTA tile = kThreads consecutive elements (one per thread); warp w owns rows 32 w .. 32 w + 31 of it.
+    // The loop bounds depend on blockIdx only, so the CTA-wide barriers of the TMA path are uniform.
+    const long long nct = (a.E + kThreads - 1) / kThreads;
+    long long ct = blockIdx.x;
     // nodal data of the next tile are fetched while the current one computes (hides the DRAM latency
     // that 3-4 warps per scheduler cannot)
     double nxl = 0.0, nxr = 0.0, nul = 0.0, nur = 0.0;
-    if (tile < ntiles) {
-        const long long e0 = min(tile * 32 + lane, a.E - 1);
+    if (ct < nct) {
+        const long long e0 = min(ct * kThreads + threadIdx.x, a.E - 1);
         nxl = __ldg(a.nodes + e0); nxr = __ldg(a.nodes + e0 + 1);
         nul = __ldg(a.u + e0); nur = __ldg(a.u + e0 + 1);
     }
-    for (; tile < ntiles; tile += tile_step) {
-        const long long e_raw = tile * 32 + lane;
+    for (; ct < nct; ct += gridDim.x) {
+        const long long wtile_e0 = ct * kThreads + warp * 32;      // first element of this warp's 32 rows
+        const long long e_raw = wtile_e0 + lane;
         const bool valid = e_raw < a.E;
         const long long e = valid ? e_raw : a.E - 1;
         const double xl = nxl, xr = nxr;
         double ul = nul, ur = nur;
-        if (tile + tile_step < ntiles) {
-            const long long en = min((tile + tile_step) * 32 + lane, a.E - 1);
+        if (ct + gridDim.x < nct) {
+            const long long en = min((ct + gridDim.x) * kThreads + threadIdx.x, a.E - 1);
             nxl = __ldg(a.nodes + en); nxr = __ldg(a.nodes + en + 1);
             nul = __ldg(a.u + en); nur = __ldg(a.u + en + 1);
         }
@@ -217,11 +219,13 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
             }
             const bool st = (a.fine != nullptr);
             if (STORE == STORE_TMA && st && store_pending) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
+                // the CTA buffer is free once the issuing thread has seen its last bulk store read it
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
                 store_pending = false;
             }
-            const uint32_t row_tma = tile_s + lane * 128, sw = (uint32_t)(lane & 7) << 4;
+            // TMA layout: F/16 boxes of [kThreads rows][128 B], row = thread, 16-byte chunks XOR-swizzled by row & 7
+            const uint32_t row_tma = smem_u32(smem_raw) + threadIdx.x * 128, sw = (uint32_t)(lane & 7) << 4;
             const uint32_t row_sm = tile_s + lane * ((F + 2) * 8);
             double2* row_g = reinterpret_cast<double2*>(a.fine + e * F);
 #pragma unroll
@@ -257,8 +261,8 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pp * 16), "d"(up[0]), "d"(up[1]) : "memory");
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pm * 16), "d"(um[1]), "d"(um[0]) : "memory");
                     } else {
-                        const uint32_t ap = row_tma + (pp >> 3) * 4096 + ((((uint32_t)pp & 7) << 4) ^ sw);
-                        const uint32_t am = row_tma + (pm >> 3) * 4096 + ((((uint32_t)pm & 7) << 4) ^ sw);
+                        const uint32_t ap = row_tma + (pp >> 3) * (kThreads * 128) + ((((uint32_t)pp & 7) << 4) ^ sw);
+                        const uint32_t am = row_tma + (pm >> 3) * (kThreads * 128) + ((((uint32_t)pm & 7) << 4) ^ sw);
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ap), "d"(up[0]), "d"(up[1]) : "memory");
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(am), "d"(um[1]), "d"(um[0]) : "memory");
                     }
@@ -267,13 +271,13 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
             if (ERR && valid) acc_sq = fma(sq, h * (2.0 * a.cF), acc_sq);
             if (st && STORE == STORE_SMEM) {
                 __syncwarp();
-                double2* g = reinterpret_cast<double2*>(a.fine + tile * 32 * F);
+                double2* g = reinterpret_cast<double2*>(a.fine + wtile_e0 * F);
 #pragma unroll 4
                 for (int it = 0; it < FH; ++it) {
                     const int idx = it * 32 + lane;       // 16-byte unit inside the 32 x F tile
                     constexpr int FHD = FH > 0 ? FH : 1;
                     const int r = idx / FHD, p = idx - r * FHD;
-                    if (tile * 32 + r < a.E) {
+                    if (wtile_e0 + r < a.E) {
                         double2 v;
                         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(tile_s + r * ((F + 2) * 8) + p * 16));
                         g[idx] = v;
@@ -283,14 +287,16 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
             }
             if (st && STORE == STORE_TMA) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
+                __syncthreads();
+                if (threadIdx.x == 0) {   // one bulk tensor store per box for the whole CTA tile; operands are CTA-uniform
+                    const int row0 = (int)(ct * kThreads);
+                    const uint32_t buf = smem_u32(smem_raw);
 #pragma unroll
                     for (int b = 0; b < F / 16; ++b) {
                         asm volatile(
                             "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
                                 reinterpret_cast<uint64_t>(&tmap)),
-                            "r"(b * 16), "r"((int)(tile * 32)), "r"(tile_s + b * 4096)
+                            "r"(b * 16), "r"(row0), "r"(buf + b * (kThreads * 128))
                             : "memory");
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -300,8 +306,8 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
         }
     }
     if (STORE == STORE_TMA && store_pending) {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncwarp();
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncthreads();
     }
     if (a.err3 != nullptr) {
         const double wsq = warp_sum(acc_sq), wmx = warp_max(acc_mx);
@@ -483,13 +489,13 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [E][F] doubles, box = 32 rows x 16 doubles (128 B inner extent, 128-byte swizzle)
+// [E][F] doubles, box = kThreads rows x 16 doubles (128 B inner extent, 128-byte swizzle)
 static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int F) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return HFL_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)E};
     cuuint64_t strides[1] = {(cuuint64_t)F * sizeof(double)};
-    cuuint32_t box[2] = {16, 32};
+    cuuint32_t box[2] = {16, (cuuint32_t)kThreads};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_fine, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -527,8 +533,7 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
     int per_sm = 0;
     HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    const long long ntiles = (a.E + 31) / 32;
-    long long grid = (ntiles + kWarps - 1) / kWarps;
+    long long grid = (a.E + kThreads - 1) / kThreads;
     const long long cap = (long long)sm_count() * per_sm;
     if (grid > cap) grid = cap;
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(a, t, tmap);
