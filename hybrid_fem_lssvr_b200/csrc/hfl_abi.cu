@@ -10,6 +10,7 @@ namespace hfl {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_opt_store{0};
+static std::atomic<int> g_opt_debug{0};
 static std::atomic<int> g_sm_count{0};
 
 void set_error(const char* fmt, ...) {
@@ -20,6 +21,7 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n); }
 int get_option_store() { return g_opt_store.load(); }
+int get_option_debug() { return g_opt_debug.load(); }
 
 int sm_count() {
     int v = g_sm_count.load();
@@ -72,8 +74,13 @@ extern "C" int hfl_device_info(int* sms, int* major, int* minor) {
 extern "C" int hfl_set_option(const char* key, int value) {
     HFL_REQUIRE(key != nullptr, "hfl_set_option: key is NULL");
     if (strcmp(key, "primal_store") == 0) {
-        HFL_REQUIRE(value >= 0 && value <= 3, "primal_store must be 0..3");
+        HFL_REQUIRE(value >= 0 && value <= 5, "primal_store must be 0..5");
         g_opt_store.store(value);
+        return HFL_OK;
+    }
+    if (strcmp(key, "primal_debug") == 0) {
+        HFL_REQUIRE(value >= 0 && value <= 2, "primal_debug must be 0..2");
+        g_opt_debug.store(value);
         return HFL_OK;
     }
     set_error("hfl_set_option: unknown key '%s'", key);

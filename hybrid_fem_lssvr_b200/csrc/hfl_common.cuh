@@ -13,6 +13,7 @@ namespace hfl {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int get_option_store();
+int get_option_debug();
 int sm_count();
 
 #define HFL_CUDA_CHECK(expr)                                                            \

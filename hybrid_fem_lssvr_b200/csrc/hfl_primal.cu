@@ -35,6 +35,7 @@ struct PrimalArgs {
     const double* Do;      // [NH][MO]
     int N, NH, F;
     int forcing;
+    int debug;             // 0 normal; 1 = skip the TMA issue (compute only); 2 = skip the solve (stores only).  Profiling aid.
     double k_freq;
     double kk;             // (k pi)^2
     double c_tau;          // 1 / (16 gamma)
@@ -51,14 +52,22 @@ struct PrimalTables {
     double fineO[FH > 0 ? FH : 1][MO + 1];
 };
 
-enum { STORE_DIRECT = 1, STORE_SMEM = 2, STORE_TMA = 3 };
+enum { STORE_DIRECT = 1, STORE_SMEM = 2, STORE_TMA = 3, STORE_TMA_ROWS = 4, STORE_COOP = 5 };
+// STORE_TMA: F/16 boxes [kThreads][16] of the [E][F] view (128-byte lines at stride 8F bytes).
+// STORE_TMA_ROWS: one box [kThreads * F/16][16] of the [E * F/16][16] view: a contiguous 8F * kThreads byte write.
+// STORE_COOP (F = 32): the solving thread stages its coefficients (14 doubles) in shared memory; then the warp
+//   evaluates cooperatively, lane = (element parity, fine-point pair): basis values are per-lane registers and
+//   every STG.64 of the warp writes two complete 128-byte lines.  No TMA, no constant-bank operands.
 
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 
+constexpr int kCoopPitch = 14;   // doubles per staged element row: w[0..M), h, S, C (M <= 11); 14 keeps STS.128 conflict-free
+
 template <int STORE>
 __host__ __device__ constexpr int tile_bytes(int F) {
-    return STORE == STORE_TMA ? (F / 16) * 4096 : (STORE == STORE_SMEM ? 32 * (F + 2) * 8 : 0);
+    return (STORE == STORE_TMA || STORE == STORE_TMA_ROWS) ? (F / 16) * 4096
+           : (STORE == STORE_SMEM ? 32 * (F + 2) * 8 : (STORE == STORE_COOP ? 32 * kCoopPitch * 8 : 0));
 }
 
 // CTAs per SM the register budget is sized for: small systems fit 128 registers (4 CTAs = 16 warps)
@@ -82,6 +91,14 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
     unsigned char* tile_ptr = smem_raw + warp * TILE;
     const uint32_t tile_s = smem_u32(tile_ptr);
     const bool do_fine = (a.fine != nullptr) || ERR;
+    // STORE_COOP: basis values of this lane's fine-point pair (lane & 15) live in registers for the whole kernel
+    double ltE[ME], ltO[MO + 1];
+    if (STORE == STORE_COOP) {
+#pragma unroll
+        for (int k = 0; k < ME; ++k) ltE[k] = t.fineE[(FH > 0 ? lane & (FH - 1) : 0)][k];
+#pragma unroll
+        for (int k = 0; k < MO + 1; ++k) ltO[k] = t.fineO[(FH > 0 ? lane & (FH - 1) : 0)][k];
+    }
 
     double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
     if (a.bc2 != nullptr) {
@@ -134,9 +151,10 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
 #pragma unroll
         for (int i = 0; i < MO; ++i) ro[i] = 0.0;
         double S = 0.0, C = 0.0;   // sin / cos of k pi x_c
-        if (a.forcing == HFL_FORCING_SINE || ERR) sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
-        double sclE, sclO;
-        if (a.forcing == HFL_FORCING_SINE) {
+        if ((a.forcing == HFL_FORCING_SINE || ERR) && a.debug != 2) sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
+        double sclE = 0.0, sclO = 0.0;
+        if (a.debug == 2) {
+        } else if (a.forcing == HFL_FORCING_SINE) {
             double sb, cb;
             sincospi(a.k_freq * h * a.cN, &sb, &cb);       // base angle k pi (h/2) / (N-1)
             const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
@@ -183,8 +201,11 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
 #pragma unroll
             for (int j = 0; j <= i; ++j)
                 Ao[i * (i + 1) / 2 + j] = t.Go[i * (i + 1) / 2 + j] + (i == j ? tau2 : tau);
-        bool ok = ldl_solve<ME>(Ae, re);
-        if (MO > 0) ok = ldl_solve<MO>(Ao, ro) && ok;
+        bool ok = true;
+        if (a.debug != 2) {
+            ok = ldl_solve<ME>(Ae, re);
+            if (MO > 0) ok = ldl_solve<MO>(Ao, ro) && ok;
+        }
         if (!ok) {   // P:171-176: fall back to the linear interpolant of the nodal values
 #pragma unroll
             for (int i = 0; i < ME; ++i) re[i] = 0.0;
@@ -209,6 +230,60 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
             for (int i = 0; i < MO; ++i) cp[3 + 2 * i] = ro[i];
         }
 
+        if (STORE == STORE_COOP && FH == 16 && do_fine) {
+            // ---- stage {w, h, S, C}; then lane (hf, i) evaluates points FH + i and FH - 1 - i of element 2 s + hf
+            double* crow = reinterpret_cast<double*>(tile_ptr) + lane * kCoopPitch;
+            crow[0] = w0; crow[1] = w1;
+#pragma unroll
+            for (int i = 0; i < ME; ++i) crow[2 + 2 * i] = re[i];
+#pragma unroll
+            for (int i = 0; i < MO; ++i) crow[3 + 2 * i] = ro[i];
+            crow[M] = h; crow[M + 1] = S; crow[M + 2] = C;
+            __syncwarp();
+            const int hf = lane >> 4, pi = lane & 15;
+            const bool st = (a.fine != nullptr);
+            const double wgt = (pi == FH - 1) ? 0.5 : 1.0;
+            const double xi = ltO[0];
+#pragma unroll 4
+            for (int sidx = 0; sidx < 16; ++sidx) {
+                const double* r = reinterpret_cast<const double*>(tile_ptr) + (2 * sidx + hf) * kCoopPitch;
+                double Ee = r[0], Oo = r[1] * ltO[0];
+#pragma unroll
+                for (int k = 0; k < ME; ++k) Ee = fma(r[2 + 2 * k], ltE[k], Ee);
+#pragma unroll
+                for (int k = 0; k < MO; ++k) Oo = fma(r[3 + 2 * k], ltO[1 + k], Oo);
+                const double up = Ee + Oo, um = Ee - Oo;
+                const long long eo = wtile_e0 + 2 * sidx + hf;
+                const bool ev = eo < a.E;
+                if (st && ev) {
+                    double* g = a.fine + eo * F;
+                    g[FH + pi] = up;
+                    g[FH - 1 - pi] = um;
+                }
+                if (ERR) {
+                    // exact = S cos(phi) +- C sin(phi), phi = k pi (h/2) xi: Taylor for |phi| <= 1/4 (|err| < 1e-14)
+                    const double he = r[M], Se = r[M + 1], Ce = r[M + 2];
+                    const double ph = (1.5707963267948966 * a.k_freq) * he * xi;
+                    double sp, cp;
+                    if (fabs(ph) <= 0.25) {
+                        const double z = ph * ph;
+                        sp = ph * fma(z, fma(z, fma(z, fma(z, 2.7557319223985893e-06, -1.984126984126984e-04),
+                                                  8.333333333333333e-03), -1.6666666666666666e-01), 1.0);
+                        cp = fma(z, fma(z, fma(z, fma(z, fma(z, -2.755731922398589e-07, 2.48015873015873e-05),
+                                                     -1.388888888888889e-03), 4.1666666666666664e-02), -0.5), 1.0);
+                    } else {
+                        sincos(ph, &sp, &cp);
+                    }
+                    const double xe = Se * cp, xo = Ce * sp;
+                    const double ep = up - (xe + xo), em = um - (xe - xo);
+                    if (ev) {
+                        acc_sq = fma(wgt * he * (2.0 * a.cF), fma(ep, ep, em * em), acc_sq);
+                        acc_mx = fmax(acc_mx, fmax(fabs(ep), fabs(em)));
+                    }
+                }
+            }
+            __syncwarp();
+        } else
         // ---- fine grid: u(+-xi_i) = Ee +- Oo; rows go to shared memory (or straight to global)
         if (FH > 0 && do_fine) {
             double sf = 0.0, cf = 1.0, s2f = 0.0, c2f = 1.0, sq = 0.0;
@@ -218,7 +293,7 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
                 c2f = fma(-2.0 * sf, sf, 1.0);
             }
             const bool st = (a.fine != nullptr);
-            if (STORE == STORE_TMA && st && store_pending) {
+            if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && st && store_pending) {
                 // the CTA buffer is free once the issuing thread has seen its last bulk store read it
                 if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncthreads();
@@ -260,6 +335,15 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
                     } else if (STORE == STORE_SMEM) {
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pp * 16), "d"(up[0]), "d"(up[1]) : "memory");
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pm * 16), "d"(um[1]), "d"(um[0]) : "memory");
+                    } else if (STORE == STORE_TMA_ROWS) {
+                        // row of the [E * F/16][16] view = thread * (F/16) + (chunk >> 3); swizzle by that row & 7
+                        constexpr int RPE = F / 16 > 0 ? F / 16 : 1;
+                        const uint32_t base = smem_u32(smem_raw);
+                        const uint32_t rp = threadIdx.x * RPE + (pp >> 3), rm = threadIdx.x * RPE + (pm >> 3);
+                        const uint32_t ap = base + rp * 128 + ((((uint32_t)pp & 7) ^ (rp & 7)) << 4);
+                        const uint32_t am = base + rm * 128 + ((((uint32_t)pm & 7) ^ (rm & 7)) << 4);
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ap), "d"(up[0]), "d"(up[1]) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(am), "d"(um[1]), "d"(um[0]) : "memory");
                     } else {
                         const uint32_t ap = row_tma + (pp >> 3) * (kThreads * 128) + ((((uint32_t)pp & 7) << 4) ^ sw);
                         const uint32_t am = row_tma + (pm >> 3) * (kThreads * 128) + ((((uint32_t)pm & 7) << 4) ^ sw);
@@ -285,10 +369,22 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
                 }
                 __syncwarp();
             }
+            if (st && STORE == STORE_TMA_ROWS) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (threadIdx.x == 0 && a.debug != 1) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&tmap)),
+                                 "r"(0), "r"((int)(ct * kThreads * (F / 16))), "r"(smem_u32(smem_raw))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                store_pending = true;
+            }
             if (st && STORE == STORE_TMA) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();
-                if (threadIdx.x == 0) {   // one bulk tensor store per box for the whole CTA tile; operands are CTA-uniform
+                if (threadIdx.x == 0 && a.debug != 1) {   // one bulk tensor store per box for the whole CTA tile; operands are CTA-uniform
                     const int row0 = (int)(ct * kThreads);
                     const uint32_t buf = smem_u32(smem_raw);
 #pragma unroll
@@ -305,7 +401,7 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
             }
         }
     }
-    if (STORE == STORE_TMA && store_pending) {
+    if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && store_pending) {
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncthreads();
     }
@@ -490,12 +586,17 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [E][F] doubles, box = kThreads rows x 16 doubles (128 B inner extent, 128-byte swizzle)
-static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int F) {
+static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int F, bool rows_view = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return HFL_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)E};
     cuuint64_t strides[1] = {(cuuint64_t)F * sizeof(double)};
     cuuint32_t box[2] = {16, (cuuint32_t)kThreads};
+    if (rows_view) {   // [E * F/16][16]: every row is one 128-byte line, the box is a contiguous block
+        dims[0] = 16; dims[1] = (cuuint64_t)E * (F / 16);
+        strides[0] = 128;
+        box[1] = (cuuint32_t)(kThreads * (F / 16));
+    }
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_fine, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -517,8 +618,8 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
     }
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    if (STORE == STORE_TMA && a.fine != nullptr) {
-        int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F);
+    if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && a.fine != nullptr) {
+        int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F, STORE == STORE_TMA_ROWS);
         if (rc != HFL_OK) return rc;
     }
     auto kern = primal_kernel<M, FH, ERR, STORE>;
@@ -547,6 +648,10 @@ static int dispatch_store(const hfl_plan* plan, const PrimalArgs& a, int store, 
     switch (store) {
         case STORE_DIRECT: return launch_fast<M, FH, ERR, STORE_DIRECT>(plan, a, s);
         case STORE_SMEM: return launch_fast<M, FH, ERR, STORE_SMEM>(plan, a, s);
+        case STORE_TMA_ROWS: return launch_fast<M, FH, ERR, STORE_TMA_ROWS>(plan, a, s);
+        case STORE_COOP:
+            if constexpr (FH == 16 && M + 3 <= kCoopPitch) return launch_fast<M, FH, ERR, STORE_COOP>(plan, a, s);
+            else return launch_fast<M, FH, ERR, STORE_TMA>(plan, a, s);
         default: return launch_fast<M, FH, ERR, STORE_TMA>(plan, a, s);
     }
 }
@@ -594,7 +699,7 @@ extern "C" int hfl_lssvr_primal_batch(const hfl_plan_t* plan, int64_t E, const d
     a.E = E; a.nodes = d_nodes; a.u = d_u; a.f = d_f_samples; a.bc2 = d_bc2;
     a.coef = d_coef; a.fine = d_fine; a.status = d_status; a.err3 = d_err3;
     a.De = plan->d_tables + plan->off_De; a.Do = plan->d_tables + plan->off_Do;
-    a.N = plan->N; a.NH = plan->NH; a.F = plan->F; a.forcing = forcing_kind;
+    a.N = plan->N; a.NH = plan->NH; a.F = plan->F; a.forcing = forcing_kind; a.debug = get_option_debug();
     a.k_freq = k_freq; a.kk = (k_freq * pi) * (k_freq * pi);
     a.c_tau = 1.0 / (16.0 * plan->gamma);
     a.cN = 0.5 / (double)(plan->N - 1);
