@@ -111,11 +111,20 @@ constexpr int SM_EX = 3 * EL_LEN;                      // 6 * FT exchange
 constexpr int SM_PCR = SM_EX + 6 * FT;                 // 2 * 6 * FT
 constexpr int SM_TOTAL = SM_PCR + 2 * 6 * FT;
 
+// Nodes P-1 .. P+FTS are staged first (every thread issues its ~9 loads back to back, so the DRAM latency
+// is paid once per tile instead of once per element), then the element terms are formed from shared memory.
+// xs aliases the PCR buffers (FTS + 2 <= 12 FT doubles), which are not live yet.
 __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P, double* sm) {
+    double* xs = sm + SM_PCR;
+    for (int q = threadIdx.x; q < FTS + 2; q += FT) {
+        const long long g = P - 1 + q;
+        xs[q] = (g >= 0 && g < a.n) ? __ldg(a.nodes + g) : 0.0;
+    }
+    __syncthreads();
     for (int q = threadIdx.x; q <= FTS; q += FT) {
         const long long ge = P - 1 + q;
         double k = 0.0, Ls = 0.0, Rs = 0.0;
-        if (ge >= 0 && ge <= a.n - 2) element_terms(a, ge, k, Ls, Rs);
+        if (ge >= 0 && ge <= a.n - 2) element_terms(a, xs[q], xs[q + 1], k, Ls, Rs);
         sm[SM_K + padi(q)] = k; sm[SM_LS + padi(q)] = Ls; sm[SM_RS + padi(q)] = Rs;
     }
 }
@@ -319,9 +328,9 @@ __global__ void fem_reaction_kernel(const FemArgs a, const double* __restrict__ 
         double k, Ls, Rs;
         out4[0] = a.nodes[0];
         out4[1] = a.nodes[a.n - 1];
-        element_terms(a, 0, k, Ls, Rs);
+        element_terms(a, a.nodes[0], a.nodes[1], k, Ls, Rs);
         out4[2] = Ls + k * (u[1] - u[0]);
-        element_terms(a, a.n - 2, k, Ls, Rs);
+        element_terms(a, a.nodes[a.n - 2], a.nodes[a.n - 1], k, Ls, Rs);
         out4[3] = Rs + k * (u[a.n - 2] - u[a.n - 1]);
     }
 }

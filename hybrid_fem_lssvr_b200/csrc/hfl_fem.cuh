@@ -50,8 +50,7 @@ struct ArrayRows {
 
 // Stiffness entry and load contributions of one element, with the reference's rounding
 // (no fused multiply-adds): P:125-136 through scikit-fem's quadrature loop.
-__device__ __forceinline__ void element_terms(const FemArgs& a, long long ge, double& k, double& Ls, double& Rs) {
-    const double x0 = a.nodes[ge], x1 = a.nodes[ge + 1];
+__device__ __forceinline__ void element_terms(const FemArgs& a, double x0, double x1, double& k, double& Ls, double& Rs) {
     const double h = x1 - x0;
     const double invh = __ddiv_rn(1.0, h);
     const double gg = __dmul_rn(invh, invh);
