@@ -111,20 +111,23 @@ constexpr int SM_EX = 3 * EL_LEN;                      // 6 * FT exchange
 constexpr int SM_PCR = SM_EX + 6 * FT;                 // 2 * 6 * FT
 constexpr int SM_TOTAL = SM_PCR + 2 * 6 * FT;
 
-// Nodes P-1 .. P+FTS are staged first (every thread issues its ~9 loads back to back, so the DRAM latency
-// is paid once per tile instead of once per element), then the element terms are formed from shared memory.
-// xs aliases the PCR buffers (FTS + 2 <= 12 FT doubles), which are not live yet.
+// Element terms of local elements q = t, t + FT, ...; the nodes of the next element are fetched while the
+// current one is being computed (software pipelining: the loads are not behind ~120 dependent instructions).
 __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P, double* sm) {
-    double* xs = sm + SM_PCR;
-    for (int q = threadIdx.x; q < FTS + 2; q += FT) {
-        const long long g = P - 1 + q;
-        xs[q] = (g >= 0 && g < a.n) ? __ldg(a.nodes + g) : 0.0;
-    }
-    __syncthreads();
+    auto fetch = [&](int q, double& x0, double& x1) {
+        const long long ge = P - 1 + q;
+        const bool ok = (q <= FTS) && ge >= 0 && ge <= a.n - 2;
+        x0 = ok ? __ldg(a.nodes + ge) : 0.0;
+        x1 = ok ? __ldg(a.nodes + ge + 1) : 1.0;
+    };
+    double nx0, nx1;
+    fetch(threadIdx.x, nx0, nx1);
     for (int q = threadIdx.x; q <= FTS; q += FT) {
+        const double x0 = nx0, x1 = nx1;
+        fetch(q + FT, nx0, nx1);
         const long long ge = P - 1 + q;
         double k = 0.0, Ls = 0.0, Rs = 0.0;
-        if (ge >= 0 && ge <= a.n - 2) element_terms(a, xs[q], xs[q + 1], k, Ls, Rs);
+        if (ge >= 0 && ge <= a.n - 2) element_terms(a, x0, x1, k, Ls, Rs);
         sm[SM_K + padi(q)] = k; sm[SM_LS + padi(q)] = Ls; sm[SM_RS + padi(q)] = Rs;
     }
 }

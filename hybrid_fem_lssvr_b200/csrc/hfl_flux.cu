@@ -24,16 +24,20 @@ constexpr int EL2 = FTS + 1 + (FTS + 1) / 8 + 8;
 // d = B_e / k_e with B inclusive.  Thread t owns elements P + t*FS .. P + t*FS + FS - 1.
 __device__ __forceinline__ void tile_local(const FemArgs& a, long long P, double* sm, Tri (&inc)[FS], Tri& agg) {
     // element arrays with a one-element halo on the left: local q <-> global element P - 1 + q
-    double* xs = sm + 3 * EL2 + 3 * FT;      // node staging (FTS + 2 doubles), see hfl_fem.cu
-    for (int q = threadIdx.x; q < FTS + 2; q += FT) {
-        const long long g = P - 1 + q;
-        xs[q] = (g >= 0 && g < a.n) ? __ldg(a.nodes + g) : 0.0;
-    }
-    __syncthreads();
+    auto fetch = [&](int q, double& x0, double& x1) {
+        const long long ge = P - 1 + q;
+        const bool ok = (q <= FTS) && ge >= 0 && ge <= a.n - 2;
+        x0 = ok ? __ldg(a.nodes + ge) : 0.0;
+        x1 = ok ? __ldg(a.nodes + ge + 1) : 1.0;
+    };
+    double nx0, nx1;
+    fetch(threadIdx.x, nx0, nx1);
     for (int q = threadIdx.x; q <= FTS; q += FT) {
+        const double x0 = nx0, x1 = nx1;
+        fetch(q + FT, nx0, nx1);                         // next element's nodes, in flight during this one's sines
         const long long ge = P - 1 + q;
         double k = 1.0, Ls = 0.0, Rs = 0.0;
-        if (ge >= 0 && ge <= a.n - 2) element_terms(a, xs[q], xs[q + 1], k, Ls, Rs);
+        if (ge >= 0 && ge <= a.n - 2) element_terms(a, x0, x1, k, Ls, Rs);
         sm[padi(q)] = k; sm[EL2 + padi(q)] = Ls; sm[2 * EL2 + padi(q)] = Rs;
     }
     __syncthreads();
@@ -153,7 +157,7 @@ int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes
         set_error("hfl_fem_p1_solve: workspace too small for the flux scan");
         return HFL_ERR_ARG;
     }
-    const size_t smem = (size_t)(3 * EL2 + 3 * FT + FTS + 2) * sizeof(double);
+    const size_t smem = (size_t)(3 * EL2 + 3 * FT) * sizeof(double);
     static thread_local bool configured = false;
     if (!configured) {
         HFL_CUDA_CHECK(cudaFuncSetAttribute(flux_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
