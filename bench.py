@@ -189,6 +189,7 @@ def run_ours(args):
     err3 = batch.new_error_accumulator(dev)
     nerr = batch.new_error_accumulator(dev)
     results = {}
+    err_all = torch.empty((world, 3), dtype=torch.float64, device=dev)
 
     def step():
         err3.zero_()
@@ -203,7 +204,7 @@ def run_ours(args):
         if args.error == 'separate':
             batch.error_fine(nodes, fine, KFREQ, err3)
         if world > 1 and args.error != 'none':
-            results['err'] = hdist.reduce_error(err3)
+            results['err_gathered'] = hdist.gather_error(err3, out=err_all)     # stream-ordered, no host sync
 
     def barrier():
         if world > 1:
@@ -267,7 +268,7 @@ def run_ours(args):
     if world == 1:
         l2, mx = batch.finish_error(err3) if args.error != 'none' else (None, None)
     else:
-        l2, mx = (results['err'][0], results['err'][1]) if 'err' in results else (None, None)
+        l2, mx = hdist.finish_gathered_error(results['err_gathered'])[:2] if 'err_gathered' in results else (None, None)
     nerr.zero_()
     if world == 1:
         nl2, nmx = batch.finish_error(batch.error_nodal(nodes, u, KFREQ, nerr))

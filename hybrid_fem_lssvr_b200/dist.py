@@ -64,6 +64,23 @@ def fem_p1_solve_distributed(nodes_local, k_freq=1.0, u_left=0.0, u_right=0.0, c
     return y, bc2
 
 
+def gather_error(err3, group=None, out=None):
+    """Stream-ordered half of the error reduction: all-gather of the per-rank accumulators into [G, 3]
+    (no host synchronisation; call finish_gathered_error when the numbers are needed)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return err3.reshape(1, 3)
+    out = torch.empty((world, 3), dtype=torch.float64, device=err3.device) if out is None else out
+    dist.all_gather_into_tensor(out.reshape(-1), err3, group=group)
+    return out
+
+
+def finish_gathered_error(gathered):
+    """(L2, max, failed) from the [G, 3] accumulators: sum, max, sum."""
+    g = gathered.cpu()
+    return math.sqrt(float(g[:, 0].sum())), float(g[:, 1].max()), int(g[:, 2].sum())
+
+
 def reduce_error(err3, group=None):
     """Global (L2, max, failed) from per-rank accumulators: all-reduce(sum) on [0] and [2], all-reduce(max) on [1]."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -88,6 +88,7 @@ def _spike_worker(rank, world, port, E, k_freq, out_dir):
         u = y.numpy() + (bc2[0].item() * (x[-1] - x) + bc2[1].item() * (x - x[0])) / L
         err = torch.tensor([float(rank + 1), float(rank), 1.0 if rank == 1 else 0.0], dtype=torch.float64)
         l2, mx, failed = hdist.reduce_error(err)
+        assert hdist.finish_gathered_error(hdist.gather_error(err)) == (l2, mx, failed)
         np.save(os.path.join(out_dir, 'u%d.npy' % rank), u)
         np.save(os.path.join(out_dir, 'r%d.npy' % rank), np.array([l2, mx, failed]))
     finally:
