@@ -11,6 +11,7 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_opt_store{0};
 static std::atomic<int> g_opt_debug{0};
+static std::atomic<int> g_opt_dual_team{0};
 static std::atomic<int> g_sm_count{0};
 
 void set_error(const char* fmt, ...) {
@@ -22,6 +23,7 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n); }
 int get_option_store() { return g_opt_store.load(); }
 int get_option_debug() { return g_opt_debug.load(); }
+int get_option_dual_team() { return g_opt_dual_team.load(); }
 
 int sm_count() {
     int v = g_sm_count.load();
@@ -76,6 +78,10 @@ extern "C" int hfl_set_option(const char* key, int value) {
     if (strcmp(key, "primal_store") == 0) {
         HFL_REQUIRE(value >= 0 && value <= 5, "primal_store must be 0..5");
         g_opt_store.store(value);
+        return HFL_OK;
+    }
+    if (strcmp(key, "dual_team") == 0) {   // 1 = always use the generic team kernel for the dual form
+        g_opt_dual_team.store(value ? 1 : 0);
         return HFL_OK;
     }
     if (strcmp(key, "primal_debug") == 0) {

@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int get_option_store();
 int get_option_debug();
+int get_option_dual_team();
 int sm_count();
 
 #define HFL_CUDA_CHECK(expr)                                                            \

@@ -238,6 +238,10 @@ __global__ void __launch_bounds__(TS == 32 ? 128 : TS) dual_kernel(const DualArg
     }
 }
 
+int launch_dual_small(const hfl_plan* plan, long long E, const double* d_nodes, const double* d_u, int forcing_kind,
+                      double k_freq, const double* d_f, const double* d_bc2, double* d_coef, double* d_fine,
+                      int* d_status, double* d_err3, cudaStream_t s);   // hfl_dual_small.cu
+
 static int launch_dual(const hfl_plan* plan, long long E, int R, const double* d_nodes, const double* d_u,
                        int forcing_kind, const double* d_kf, double k_scalar, const double* d_f, const double* d_bc2,
                        double* d_coef, double* d_fine, int* d_status, double* d_err3, cudaStream_t s) {
@@ -307,6 +311,11 @@ extern "C" int hfl_lssvr_dual_batch(const hfl_plan_t* plan, int64_t E, const dou
                                     double* d_coef, double* d_fine, int32_t* d_status, double* d_err3, void* stream) {
     int rc = dual_check(plan, E, 1, d_nodes, d_u, forcing_kind, d_f_samples, d_fine);
     if (rc != HFL_OK || E == 0) return rc;
+    if (get_option_dual_team() == 0) {   // parity-split register kernel when the shape is covered
+        rc = launch_dual_small(plan, E, d_nodes, d_u, forcing_kind, k_freq, d_f_samples, d_bc2, d_coef, d_fine, d_status,
+                               d_err3, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     return launch_dual(plan, E, 1, d_nodes, d_u, forcing_kind, nullptr, k_freq, d_f_samples, d_bc2, d_coef, d_fine,
                        d_status, d_err3, (cudaStream_t)stream);
 }

@@ -17,406 +17,9 @@
 //    from one sincospi of the centre and one of the base angle (even part ~ cos, odd part ~ sin).
 //  * fine grid: u(+-xi) = E(xi) +- O(xi) with the basis values as immediate constant-bank operands
 //    (kernel parameter block), rows staged in swizzled shared memory and written by TMA tensor stores.
-#include "hfl_device.cuh"
+#include "hfl_element_kernel.cuh"
 
 namespace hfl {
-
-struct PrimalArgs {
-    long long E;
-    const double* nodes;
-    const double* u;
-    const double* f;       // samples [N][E] or NULL
-    const double* bc2;     // optional {bc_left, bc_right}
-    double* coef;          // optional [E][M]
-    double* fine;          // optional [E][F]
-    int* status;           // optional [E]
-    double* err3;          // optional accumulators
-    const double* De;      // [NH][ME]
-    const double* Do;      // [NH][MO]
-    int N, NH, F;
-    int forcing;
-    int debug;             // 0 normal; 1 = skip the TMA issue (compute only); 2 = skip the solve (stores only).  Profiling aid.
-    double k_freq;
-    double kk;             // (k pi)^2
-    double c_tau;          // 1 / (16 gamma)
-    double cN;             // 0.5 / (N - 1)
-    double cF;             // 0.5 / (F - 1)
-};
-
-template <int M, int FH>
-struct PrimalTables {
-    static constexpr int ME = n_even(M), MO = n_odd(M);
-    double Ge[ME * (ME + 1) / 2];
-    double Go[MO > 0 ? MO * (MO + 1) / 2 : 1];
-    double fineE[FH > 0 ? FH : 1][ME];
-    double fineO[FH > 0 ? FH : 1][MO + 1];
-};
-
-enum { STORE_DIRECT = 1, STORE_SMEM = 2, STORE_TMA = 3, STORE_TMA_ROWS = 4, STORE_COOP = 5 };
-// STORE_TMA: F/16 boxes [kThreads][16] of the [E][F] view (128-byte lines at stride 8F bytes).
-// STORE_TMA_ROWS: one box [kThreads * F/16][16] of the [E * F/16][16] view: a contiguous 8F * kThreads byte write.
-// STORE_COOP (F = 32): the solving thread stages its coefficients (14 doubles) in shared memory; then the warp
-//   evaluates cooperatively, lane = (element parity, fine-point pair): basis values are per-lane registers and
-//   every STG.64 of the warp writes two complete 128-byte lines.  No TMA, no constant-bank operands.
-
-constexpr int kThreads = 128;
-constexpr int kWarps = kThreads / 32;
-
-constexpr int kCoopPitch = 14;   // doubles per staged element row: w[0..M), h, S, C (M <= 11); 14 keeps STS.128 conflict-free
-
-template <int STORE>
-__host__ __device__ constexpr int tile_bytes(int F) {
-    return (STORE == STORE_TMA || STORE == STORE_TMA_ROWS) ? (F / 16) * 4096
-           : (STORE == STORE_SMEM ? 32 * (F + 2) * 8 : (STORE == STORE_COOP ? 32 * kCoopPitch * 8 : 0));
-}
-
-// CTAs per SM the register budget is sized for: small systems fit 128 registers (4 CTAs = 16 warps)
-__host__ __device__ constexpr int min_ctas(int M, bool err) { return (M <= 10 && !err) ? 4 : 3; }
-
-template <int M, int FH, bool ERR, int STORE>
-__global__ void __launch_bounds__(kThreads, min_ctas(M, ERR))
-primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
-              const __grid_constant__ CUtensorMap tmap) {
-    constexpr int ME = n_even(M), MO = n_odd(M);
-    constexpr int F = 2 * FH;
-    constexpr int TILE = tile_bytes<STORE>(F);
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double* sDe = reinterpret_cast<double*>(smem_raw + kWarps * TILE);
-    double* sDo = sDe + a.NH * ME;
-    for (int i = threadIdx.x; i < a.NH * ME; i += kThreads) sDe[i] = a.De[i];
-    for (int i = threadIdx.x; i < a.NH * MO; i += kThreads) sDo[i] = a.Do[i];
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* tile_ptr = smem_raw + warp * TILE;
-    const uint32_t tile_s = smem_u32(tile_ptr);
-    const bool do_fine = (a.fine != nullptr) || ERR;
-    // STORE_COOP: basis values of this lane's fine-point pair (lane & 15) live in registers for the whole kernel
-    double ltE[ME], ltO[MO + 1];
-    if (STORE == STORE_COOP) {
-#pragma unroll
-        for (int k = 0; k < ME; ++k) ltE[k] = t.fineE[(FH > 0 ? lane & (FH - 1) : 0)][k];
-#pragma unroll
-        for (int k = 0; k < MO + 1; ++k) ltO[k] = t.fineO[(FH > 0 ? lane & (FH - 1) : 0)][k];
-    }
-
-    double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
-    if (a.bc2 != nullptr) {
-        bcl = a.bc2[0]; bcr = a.bc2[1];
-        x_first = a.nodes[0]; x_last = a.nodes[a.E];
-        invL = 1.0 / (x_last - x_first);
-    }
-    double acc_sq = 0.0, acc_mx = 0.0;
-    int nfail = 0;
-    bool store_pending = false;
-
-    // CTA tile = kThreads consecutive elements (one per thread); warp w owns rows 32 w .. 32 w + 31 of it.
-    // The loop bounds depend on blockIdx only, so the CTA-wide barriers of the TMA path are uniform.
-    const long long nct = (a.E + kThreads - 1) / kThreads;
-    long long ct = blockIdx.x;
-    // nodal data of the next tile are fetched while the current one computes (hides the DRAM latency
-    // that 3-4 warps per scheduler cannot)
-    double nxl = 0.0, nxr = 0.0, nul = 0.0, nur = 0.0;
-    if (ct < nct) {
-        const long long e0 = min(ct * kThreads + threadIdx.x, a.E - 1);
-        nxl = __ldg(a.nodes + e0); nxr = __ldg(a.nodes + e0 + 1);
-        nul = __ldg(a.u + e0); nur = __ldg(a.u + e0 + 1);
-    }
-    for (; ct < nct; ct += gridDim.x) {
-        const long long wtile_e0 = ct * kThreads + warp * 32;      // first element of this warp's 32 rows
-        const long long e_raw = wtile_e0 + lane;
-        const bool valid = e_raw < a.E;
-        const long long e = valid ? e_raw : a.E - 1;
-        const double xl = nxl, xr = nxr;
-        double ul = nul, ur = nur;
-        if (ct + gridDim.x < nct) {
-            const long long en = min((ct + gridDim.x) * kThreads + threadIdx.x, a.E - 1);
-            nxl = __ldg(a.nodes + en); nxr = __ldg(a.nodes + en + 1);
-            nul = __ldg(a.u + en); nur = __ldg(a.u + en + 1);
-        }
-        if (a.bc2 != nullptr) {
-            ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
-            ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;
-        }
-        const double h = xr - xl;
-        const double h2 = h * h;
-        const double isig = 0.25 * h2;            // 1 / sigma, sigma = (2/h)^2
-        const double tau = (h2 * h2) * a.c_tau;   // 1 / (gamma sigma^2)
-        const double abar = 0.5 * (ul + ur), bbar = 0.5 * (ur - ul);
-
-        // ---- right-hand sides: re = tau abar 1 - isig De^T f_even, ro = tau bbar 1 - isig Do^T f_odd
-        double re[ME], ro[MO > 0 ? MO : 1];
-#pragma unroll
-        for (int i = 0; i < ME; ++i) re[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < MO; ++i) ro[i] = 0.0;
-        double S = 0.0, C = 0.0;   // sin / cos of k pi x_c
-        if ((a.forcing == HFL_FORCING_SINE || ERR) && a.debug != 2) sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
-        double sclE = 0.0, sclO = 0.0;
-        if (a.debug == 2) {
-        } else if (a.forcing == HFL_FORCING_SINE) {
-            double sb, cb;
-            sincospi(a.k_freq * h * a.cN, &sb, &cb);       // base angle k pi (h/2) / (N-1)
-            const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
-            double s = (a.N & 1) ? 0.0 : sb, c = (a.N & 1) ? 1.0 : cb;
-            for (int j = 0; j < a.NH; ++j) {
-#pragma unroll
-                for (int i = 0; i < ME; ++i) re[i] = fma(sDe[j * ME + i], c, re[i]);
-#pragma unroll
-                for (int i = 0; i < MO; ++i) ro[i] = fma(sDo[j * MO + i], s, ro[i]);
-                rotate(s, c, s2, c2);
-            }
-            sclE = -isig * a.kk * S;
-            sclO = -isig * a.kk * C;
-        } else {
-            const int jp0 = a.N >> 1, jm0 = (a.N - 1) >> 1;   // first right / left sample of pair 0
-            for (int j = 0; j < a.NH; ++j) {
-                const double fp = __ldg(a.f + (long long)(jp0 + j) * a.E + e);
-                const double fm = __ldg(a.f + (long long)(jm0 - j) * a.E + e);
-                const double fe = 0.5 * (fp + fm), fo = 0.5 * (fp - fm);
-#pragma unroll
-                for (int i = 0; i < ME; ++i) re[i] = fma(sDe[j * ME + i], fe, re[i]);
-#pragma unroll
-                for (int i = 0; i < MO; ++i) ro[i] = fma(sDo[j * MO + i], fo, ro[i]);
-            }
-            sclE = -isig;
-            sclO = -isig;
-        }
-        const double ta = tau * abar, tb = tau * bbar;
-#pragma unroll
-        for (int i = 0; i < ME; ++i) re[i] = fma(sclE, re[i], ta);
-#pragma unroll
-        for (int i = 0; i < MO; ++i) ro[i] = fma(sclO, ro[i], tb);
-
-        // ---- per-element matrices tau (I + 1 1^T) + G and their LDL^T solves
-        double Ae[ME * (ME + 1) / 2], Ao[MO > 0 ? MO * (MO + 1) / 2 : 1];
-        const double tau2 = tau + tau;
-#pragma unroll
-        for (int i = 0; i < ME; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j)
-                Ae[i * (i + 1) / 2 + j] = t.Ge[i * (i + 1) / 2 + j] + (i == j ? tau2 : tau);
-#pragma unroll
-        for (int i = 0; i < MO; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j)
-                Ao[i * (i + 1) / 2 + j] = t.Go[i * (i + 1) / 2 + j] + (i == j ? tau2 : tau);
-        bool ok = true;
-        if (a.debug != 2) {
-            ok = ldl_solve<ME>(Ae, re);
-            if (MO > 0) ok = ldl_solve<MO>(Ao, ro) && ok;
-        }
-        if (!ok) {   // P:171-176: fall back to the linear interpolant of the nodal values
-#pragma unroll
-            for (int i = 0; i < ME; ++i) re[i] = 0.0;
-#pragma unroll
-            for (int i = 0; i < MO; ++i) ro[i] = 0.0;
-            if (valid) ++nfail;
-        }
-        double w0 = abar, w1 = bbar;
-#pragma unroll
-        for (int i = 0; i < ME; ++i) w0 -= re[i];
-#pragma unroll
-        for (int i = 0; i < MO; ++i) w1 -= ro[i];
-
-        if (valid && a.status != nullptr) a.status[e] = ok ? 0 : 1;
-        if (valid && a.coef != nullptr) {
-            double* cp = a.coef + e * M;
-            cp[0] = w0;
-            cp[1] = w1;
-#pragma unroll
-            for (int i = 0; i < ME; ++i) cp[2 + 2 * i] = re[i];
-#pragma unroll
-            for (int i = 0; i < MO; ++i) cp[3 + 2 * i] = ro[i];
-        }
-
-        if (STORE == STORE_COOP && FH == 16 && do_fine) {
-            // ---- stage {w, h, S, C}; then lane (hf, i) evaluates points FH + i and FH - 1 - i of element 2 s + hf
-            double* crow = reinterpret_cast<double*>(tile_ptr) + lane * kCoopPitch;
-            crow[0] = w0; crow[1] = w1;
-#pragma unroll
-            for (int i = 0; i < ME; ++i) crow[2 + 2 * i] = re[i];
-#pragma unroll
-            for (int i = 0; i < MO; ++i) crow[3 + 2 * i] = ro[i];
-            crow[M] = h; crow[M + 1] = S; crow[M + 2] = C;
-            __syncwarp();
-            const int hf = lane >> 4, pi = lane & 15;
-            const bool st = (a.fine != nullptr);
-            const double wgt = (pi == FH - 1) ? 0.5 : 1.0;
-            const double xi = ltO[0];
-#pragma unroll 4
-            for (int sidx = 0; sidx < 16; ++sidx) {
-                const double* r = reinterpret_cast<const double*>(tile_ptr) + (2 * sidx + hf) * kCoopPitch;
-                double Ee = r[0], Oo = r[1] * ltO[0];
-#pragma unroll
-                for (int k = 0; k < ME; ++k) Ee = fma(r[2 + 2 * k], ltE[k], Ee);
-#pragma unroll
-                for (int k = 0; k < MO; ++k) Oo = fma(r[3 + 2 * k], ltO[1 + k], Oo);
-                const double up = Ee + Oo, um = Ee - Oo;
-                const long long eo = wtile_e0 + 2 * sidx + hf;
-                const bool ev = eo < a.E;
-                if (st && ev) {
-                    double* g = a.fine + eo * F;
-                    g[FH + pi] = up;
-                    g[FH - 1 - pi] = um;
-                }
-                if (ERR) {
-                    // exact = S cos(phi) +- C sin(phi), phi = k pi (h/2) xi: Taylor for |phi| <= 1/4 (|err| < 1e-14)
-                    const double he = r[M], Se = r[M + 1], Ce = r[M + 2];
-                    const double ph = (1.5707963267948966 * a.k_freq) * he * xi;
-                    double sp, cp;
-                    if (fabs(ph) <= 0.25) {
-                        const double z = ph * ph;
-                        sp = ph * fma(z, fma(z, fma(z, fma(z, 2.7557319223985893e-06, -1.984126984126984e-04),
-                                                  8.333333333333333e-03), -1.6666666666666666e-01), 1.0);
-                        cp = fma(z, fma(z, fma(z, fma(z, fma(z, -2.755731922398589e-07, 2.48015873015873e-05),
-                                                     -1.388888888888889e-03), 4.1666666666666664e-02), -0.5), 1.0);
-                    } else {
-                        sincos(ph, &sp, &cp);
-                    }
-                    const double xe = Se * cp, xo = Ce * sp;
-                    const double ep = up - (xe + xo), em = um - (xe - xo);
-                    if (ev) {
-                        acc_sq = fma(wgt * he * (2.0 * a.cF), fma(ep, ep, em * em), acc_sq);
-                        acc_mx = fmax(acc_mx, fmax(fabs(ep), fabs(em)));
-                    }
-                }
-            }
-            __syncwarp();
-        } else
-        // ---- fine grid: u(+-xi_i) = Ee +- Oo; rows go to shared memory (or straight to global)
-        if (FH > 0 && do_fine) {
-            double sf = 0.0, cf = 1.0, s2f = 0.0, c2f = 1.0, sq = 0.0;
-            if (ERR) {
-                sincospi(a.k_freq * h * a.cF, &sf, &cf);   // base angle k pi (h/2) / (F-1); F even
-                s2f = 2.0 * sf * cf;
-                c2f = fma(-2.0 * sf, sf, 1.0);
-            }
-            const bool st = (a.fine != nullptr);
-            if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && st && store_pending) {
-                // the CTA buffer is free once the issuing thread has seen its last bulk store read it
-                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncthreads();
-                store_pending = false;
-            }
-            // TMA layout: F/16 boxes of [kThreads rows][128 B], row = thread, 16-byte chunks XOR-swizzled by row & 7
-            const uint32_t row_tma = smem_u32(smem_raw) + threadIdx.x * 128, sw = (uint32_t)(lane & 7) << 4;
-            const uint32_t row_sm = tile_s + lane * ((F + 2) * 8);
-            double2* row_g = reinterpret_cast<double2*>(a.fine + e * F);
-#pragma unroll
-            for (int i = 0; i < FH; i += 2) {
-                double up[2], um[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    double Ee = w0, Oo = w1 * t.fineO[i + q][0];
-#pragma unroll
-                    for (int k = 0; k < ME; ++k) Ee = fma(re[k], t.fineE[i + q][k], Ee);
-#pragma unroll
-                    for (int k = 0; k < MO; ++k) Oo = fma(ro[k], t.fineO[i + q][1 + k], Oo);
-                    up[q] = Ee + Oo;
-                    um[q] = Ee - Oo;
-                    if (ERR) {
-                        const double xe = S * cf, xo = C * sf;
-                        const double ep = up[q] - (xe + xo), em = um[q] - (xe - xo);
-                        const double wgt = (i + q == FH - 1) ? 0.5 : 1.0;
-                        sq = fma(wgt, fma(ep, ep, em * em), sq);
-                        acc_mx = fmax(acc_mx, fmax(fabs(ep), fabs(em)));
-                        rotate(sf, cf, s2f, c2f);
-                    }
-                }
-                if (st) {
-                    const int pp = (FH + i) >> 1;        // chunk holding points FH+i, FH+i+1
-                    const int pm = (FH - 2 - i) >> 1;    // chunk holding points FH-2-i, FH-1-i
-                    if (STORE == STORE_DIRECT) {
-                        if (valid) {
-                            row_g[pp] = make_double2(up[0], up[1]);
-                            row_g[pm] = make_double2(um[1], um[0]);
-                        }
-                    } else if (STORE == STORE_SMEM) {
-                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pp * 16), "d"(up[0]), "d"(up[1]) : "memory");
-                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row_sm + pm * 16), "d"(um[1]), "d"(um[0]) : "memory");
-                    } else if (STORE == STORE_TMA_ROWS) {
-                        // row of the [E * F/16][16] view = thread * (F/16) + (chunk >> 3); swizzle by that row & 7
-                        constexpr int RPE = F / 16 > 0 ? F / 16 : 1;
-                        const uint32_t base = smem_u32(smem_raw);
-                        const uint32_t rp = threadIdx.x * RPE + (pp >> 3), rm = threadIdx.x * RPE + (pm >> 3);
-                        const uint32_t ap = base + rp * 128 + ((((uint32_t)pp & 7) ^ (rp & 7)) << 4);
-                        const uint32_t am = base + rm * 128 + ((((uint32_t)pm & 7) ^ (rm & 7)) << 4);
-                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ap), "d"(up[0]), "d"(up[1]) : "memory");
-                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(am), "d"(um[1]), "d"(um[0]) : "memory");
-                    } else {
-                        const uint32_t ap = row_tma + (pp >> 3) * (kThreads * 128) + ((((uint32_t)pp & 7) << 4) ^ sw);
-                        const uint32_t am = row_tma + (pm >> 3) * (kThreads * 128) + ((((uint32_t)pm & 7) << 4) ^ sw);
-                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ap), "d"(up[0]), "d"(up[1]) : "memory");
-                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(am), "d"(um[1]), "d"(um[0]) : "memory");
-                    }
-                }
-            }
-            if (ERR && valid) acc_sq = fma(sq, h * (2.0 * a.cF), acc_sq);
-            if (st && STORE == STORE_SMEM) {
-                __syncwarp();
-                double2* g = reinterpret_cast<double2*>(a.fine + wtile_e0 * F);
-#pragma unroll 4
-                for (int it = 0; it < FH; ++it) {
-                    const int idx = it * 32 + lane;       // 16-byte unit inside the 32 x F tile
-                    constexpr int FHD = FH > 0 ? FH : 1;
-                    const int r = idx / FHD, p = idx - r * FHD;
-                    if (wtile_e0 + r < a.E) {
-                        double2 v;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(tile_s + r * ((F + 2) * 8) + p * 16));
-                        g[idx] = v;
-                    }
-                }
-                __syncwarp();
-            }
-            if (st && STORE == STORE_TMA_ROWS) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-                if (threadIdx.x == 0 && a.debug != 1) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                                     reinterpret_cast<uint64_t>(&tmap)),
-                                 "r"(0), "r"((int)(ct * kThreads * (F / 16))), "r"(smem_u32(smem_raw))
-                                 : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                store_pending = true;
-            }
-            if (st && STORE == STORE_TMA) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-                if (threadIdx.x == 0 && a.debug != 1) {   // one bulk tensor store per box for the whole CTA tile; operands are CTA-uniform
-                    const int row0 = (int)(ct * kThreads);
-                    const uint32_t buf = smem_u32(smem_raw);
-#pragma unroll
-                    for (int b = 0; b < F / 16; ++b) {
-                        asm volatile(
-                            "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                                reinterpret_cast<uint64_t>(&tmap)),
-                            "r"(b * 16), "r"(row0), "r"(buf + b * (kThreads * 128))
-                            : "memory");
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                store_pending = true;
-            }
-        }
-    }
-    if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && store_pending) {
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncthreads();
-    }
-    if (a.err3 != nullptr) {
-        const double wsq = warp_sum(acc_sq), wmx = warp_max(acc_mx);
-        const double wf = warp_sum((double)nfail);
-        if (lane == 0) {
-            if (ERR) {
-                atomicAdd(a.err3 + 0, wsq);
-                atomic_max_nonneg(a.err3 + 1, wmx);
-            }
-            if (wf != 0.0) atomicAdd(a.err3 + 2, wf);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Generic kernel: any M <= HFL_MAX_M, any N, any F (odd counts included).  Same algorithm with
@@ -566,81 +169,6 @@ primal_generic_kernel(const PrimalArgs a, const GenericTables t, const bool want
             if (wf != 0.0) atomicAdd(a.err3 + 2, wf);
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-        return nullptr;
-    fn = (EncodeTiledFn)p;
-    return fn;
-}
-
-// [E][F] doubles, box = kThreads rows x 16 doubles (128 B inner extent, 128-byte swizzle)
-static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int F, bool rows_view = false) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return HFL_ERR_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)E};
-    cuuint64_t strides[1] = {(cuuint64_t)F * sizeof(double)};
-    cuuint32_t box[2] = {16, (cuuint32_t)kThreads};
-    if (rows_view) {   // [E * F/16][16]: every row is one 128-byte line, the box is a contiguous block
-        dims[0] = 16; dims[1] = (cuuint64_t)E * (F / 16);
-        strides[0] = 128;
-        box[1] = (cuuint32_t)(kThreads * (F / 16));
-    }
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_fine, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return HFL_ERR_CUDA; }
-    return HFL_OK;
-}
-
-template <int M, int FH, bool ERR, int STORE>
-static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t stream) {
-    constexpr int ME = n_even(M), MO = n_odd(M), F = 2 * FH;
-    PrimalTables<M, FH> t;
-    memset(&t, 0, sizeof(t));
-    for (int i = 0; i < ME * (ME + 1) / 2; ++i) t.Ge[i] = plan->Ge[i];
-    for (int i = 0; i < MO * (MO + 1) / 2; ++i) t.Go[i] = plan->Go[i];
-    for (int i = 0; i < FH; ++i) {
-        for (int k = 0; k < ME; ++k) t.fineE[i][k] = plan->fineE[(size_t)i * ME + k];
-        for (int k = 0; k < MO + 1; ++k) t.fineO[i][k] = plan->fineO[(size_t)i * (MO + 1) + k];
-    }
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && a.fine != nullptr) {
-        int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F, STORE == STORE_TMA_ROWS);
-        if (rc != HFL_OK) return rc;
-    }
-    auto kern = primal_kernel<M, FH, ERR, STORE>;
-    const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) + (size_t)a.NH * (ME + MO) * sizeof(double);
-    static thread_local const void* configured = nullptr;
-    static thread_local size_t configured_smem = 0;
-    if (configured != (const void*)kern || configured_smem < smem) {
-        HFL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = (const void*)kern;
-        configured_smem = smem;
-    }
-    int per_sm = 0;
-    HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (a.E + kThreads - 1) / kThreads;
-    const long long cap = (long long)sm_count() * per_sm;
-    if (grid > cap) grid = cap;
-    kern<<<(unsigned)grid, kThreads, smem, stream>>>(a, t, tmap);
-    count_launch();
-    HFL_CUDA_CHECK(cudaGetLastError());
-    return HFL_OK;
 }
 
 template <int M, int FH, bool ERR>
