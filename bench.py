@@ -92,6 +92,25 @@ def cpu_slsqp_sample(n_elements=8):
     return n_elements / (time.perf_counter() - t0)
 
 
+def run_cpu_baseline_c(sample, steps=1):
+    """The C / OpenMP restatement (oracle/c/hfl_oracle.c): coarse solve + element solves + fine grid + max error
+    on `sample` elements of the benchmark's mesh family, all host threads."""
+    import numpy as np
+    from oracle import c_port
+    c_port.load()
+    cores = c_port.threads()
+    nodes = np.linspace(-1.0, 1.0, min(sample, 20000) + 1)
+    c_port.primal_batch(nodes, c_port.fem_p1(nodes, KFREQ), M, GAMMA, N=NCOL, k_freq=KFREQ, F=F, want_coef=False)
+    times, mx = [], 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        nodes = np.linspace(-1.0, 1.0, sample + 1)
+        u = c_port.fem_p1(nodes, KFREQ)
+        _, _, mx = c_port.primal_batch(nodes, u, M, GAMMA, N=NCOL, k_freq=KFREQ, F=F, want_coef=False, want_fine=True)
+        times.append(time.perf_counter() - t0)
+    return sample / (sum(times) / len(times)), cores, mx, times
+
+
 def run_cpu_baseline(sample, steps=1):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
@@ -263,6 +282,14 @@ def run_ours(args):
     k5_ms = time_kernel(lambda: batch.error_fine(nodes, fine, KFREQ, nerr), max(3, reps // 2))
     peak, peak_src = measured_peaks()
     achieved = BYTES_PER_ELEMENT * E / (k2_ms * 1e-3) / 1e9
+    traffic = None
+    try:    # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            tj = json.load(fh)
+        if E == tj.get('elements'):
+            traffic = tj['primal_kernel_fused_err' if args.error == 'fused' else 'primal_kernel']
+    except Exception:
+        pass
 
     # ---- error norms of the last step (reported, not timed)
     if world == 1:
@@ -274,6 +301,25 @@ def run_ours(args):
         nl2, nmx = batch.finish_error(batch.error_nodal(nodes, u, KFREQ, nerr))
     else:
         nl2 = nmx = None
+
+    # ---- BASELINE configs[1]: dual LSSVR, 1e6 elements, degree 8 (reported beside the headline, not part of the step)
+    dual = None
+    if rank == 0:
+        Ed = 10 ** 6
+        nd = batch.mesh_linspace(-1.0, 1.0, Ed + 1, device=dev)
+        ud = batch.fem_p1_solve(nd, k_freq=KFREQ, coarse_solver='flux')
+        fd = fine[:Ed]
+        derr = batch.new_error_accumulator(dev)
+        dms = time_kernel(lambda: batch.lssvr_dual_batch(nd, ud, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ,
+                                                         want_coef=False, want_fine=True, fine_out=fd), reps)
+        derr.zero_()
+        batch.lssvr_dual_batch(nd, ud, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False,
+                               want_fine=True, fine_out=fd, err3=derr)
+        dl2, dmx = batch.finish_error(derr)
+        dual = {'workload': 'BASELINE configs[1]: dual LSSVR (parity-split 7x7 blocks, pivot-skipping LDL^T), 1e6 elements, '
+                            'M=9, N=12, F=32, flux coarse solve', 'kernel_ms': dms,
+                'element_solves_per_s': Ed / (dms * 1e-3), 'roofline_frac_hbm': BYTES_PER_ELEMENT * Ed / (dms * 1e-3) / 1e9 / measured_peaks()[0],
+                'fine_l2_vs_sin': dl2, 'fine_max_vs_sin': dmx}
 
     # ---- FP64 FMA probe (no FP64 figure in MEASURED_PEAKS.json)
     fp64_tflops = None
@@ -316,15 +362,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        sample = args.cpu_sample or 2_000_000
-        v, cores, cmx, times = run_cpu_baseline(sample)
-        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': '%d elements of the same uniform mesh family (M=9, N=12, F=32): SuperLU coarse solve + '
-                         'vectorised numpy KKT solves + fine grid + max error, %d processes, %.1f s'
-                         % (sample, cores, sum(times))}
-        s = cpu_slsqp_sample()
-        if s is not None:
-            cpu['reference_formulation_slsqp_solves_per_s_per_core'] = s
+        cpu = cpu_baseline_record(args.cpu_sample, steps=2)
 
     if rank == 0:
         line = {
@@ -343,13 +381,14 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'kernel': 'primal_kernel<M=9,FH=16,ERR=%s> (K2+K3%s)'
+                         'traffic': traffic, 'kernel': 'primal_kernel<M=9,FH=16,ERR=%s> (K2+K3%s)'
                          % ('true' if args.error == 'fused' else 'false', '+K5' if args.error == 'fused' else ''),
                          'algorithmic_bytes_per_element': BYTES_PER_ELEMENT, 'kernel_ms': k2_ms, 'peak_source': peak_src},
             'kernels_ms': {'K1_coarse_solve_' + args.coarse: k1_ms, 'K1_coarse_solve_' + k1_other: k1_other_ms, 'K2K3_primal_fine' + ('_K5' if args.error == 'fused' else ''): k2_ms,
                            'K2K3_primal_fine_no_error': k2_plain_ms, 'K5_error_fine_standalone': k5_ms},
             'fp64_fma_probe_tflops': fp64_tflops,
             'errors_vs_sin': {'fine_l2': l2, 'fine_max': mx, 'nodal_l2': nl2, 'nodal_max': nmx},
+            'dual_config1': dual,
             'e2e': e2e,
             'cpu_baseline': cpu,
         }
@@ -358,32 +397,58 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def cpu_baseline_record(sample_arg, steps):
+    """cpu_baseline object: the C / OpenMP port when it builds, else the numpy port; both are restatements
+    (kind "port").  Also times the numpy port and the reference's own SLSQP formulation on small samples."""
+    rec = None
+    try:
+        sample = sample_arg or 4_000_000
+        v, cores, cmx, times = run_cpu_baseline_c(sample, steps=steps)
+        rec = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': '%d elements of the same uniform mesh family (M=9, N=12, F=32) per pass, %d passes: C/OpenMP '
+                         'restatement (oracle/c/hfl_oracle.c) - Thomas coarse solve + per-element Cholesky/Schur KKT solve '
+                         '+ fine grid + max error, %d threads, %.1f s' % (sample, steps, cores, sum(times)),
+               'fine_max_error_vs_sin': cmx}
+    except Exception as ex:      # no C compiler / OpenMP on the box: fall back to the numpy port
+        rec = None
+        note = 'C port unavailable (%s)' % type(ex).__name__
+    sample_np = 400_000 if rec is not None else (sample_arg or 2_000_000)
+    v, cores, cmx, times = run_cpu_baseline(sample_np)
+    if rec is None:
+        rec = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'note': note,
+               'sample': '%d elements: SuperLU coarse solve + vectorised numpy KKT solves + fine grid + max error, %d '
+                         'processes, %.1f s' % (sample_np, cores, sum(times))}
+    else:
+        rec['numpy_port_value'] = v
+        rec['numpy_port_sample'] = '%d elements, SuperLU coarse solve + vectorised numpy KKT, %d processes' % (sample_np, cores)
+    s = cpu_slsqp_sample()
+    if s is not None:
+        rec['reference_formulation_slsqp_solves_per_s_per_core'] = s
+    return rec
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample = args.cpu_sample or 1_000_000
-    run_cpu_baseline(20000)
     t0 = time.perf_counter()
-    v, cores, mx, times = run_cpu_baseline(sample, steps=max(1, args.steps))
-    ms = 1e3 * sum(times) / len(times)
-    desc = ('%d elements per step of the uniform mesh family of BASELINE configs[2] (M=9, N=12, F=32): SuperLU coarse '
-            'solve + vectorised numpy KKT element solves + fine grid + max error' % sample)
+    steps = max(1, args.steps)
+    rec = cpu_baseline_record(args.cpu_sample, steps=steps)
+    v = rec['value']
+    sample = int(rec['sample'].split()[0])
+    ms = 1e3 * sample / v
+    rec['note'] = ('oracle port: restatement of P:20-105 (closed-form KKT) and P:117-145; the reference scripts themselves '
+                   'cannot travel to the GPU box (no scikit-fem) and their SLSQP element solve runs at ~3-15 solves/s/core '
+                   '(BASELINE.md)')
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': max(1, args.steps),
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[2] on the host CPU, bounded sample: ' + desc},
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc,
-                         'note': 'oracle port (closed-form KKT restatement of P:20-105 + restated P:117-145); the reference '
-                                 'scripts themselves cannot travel to the GPU box (no scikit-fem) and their SLSQP element '
-                                 'solve runs at ~3-15 solves/s/core (BASELINE.md)'},
+        'config': {'workload': 'BASELINE configs[2] on the host CPU, bounded sample: ' + rec['sample']},
+        'cpu_baseline': rec,
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'fine_max_error_vs_sin': mx, 'wall_s': time.perf_counter() - t0,
+        'wall_s': time.perf_counter() - t0,
     }
-    s = cpu_slsqp_sample()
-    if s is not None:
-        line['cpu_baseline']['reference_formulation_slsqp_solves_per_s_per_core'] = s
     print(json.dumps(line))
 
 

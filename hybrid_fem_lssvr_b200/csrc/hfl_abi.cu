@@ -85,7 +85,7 @@ extern "C" int hfl_set_option(const char* key, int value) {
         return HFL_OK;
     }
     if (strcmp(key, "primal_debug") == 0) {
-        HFL_REQUIRE(value >= 0 && value <= 2, "primal_debug must be 0..2");
+        HFL_REQUIRE(value >= 0 && value <= 3, "primal_debug must be 0..3");
         g_opt_debug.store(value);
         return HFL_OK;
     }

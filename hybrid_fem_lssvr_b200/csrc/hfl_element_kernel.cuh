@@ -385,8 +385,13 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
                 const bool ev = eo < a.E;
                 if (st && ev) {
                     double* g = a.fine + eo * F;
-                    g[FH + pi] = up;
-                    g[FH - 1 - pi] = um;
+                    if (a.debug == 3) {           // streaming (evict-first) stores, profiling aid
+                        __stcs(g + FH + pi, up);
+                        __stcs(g + FH - 1 - pi, um);
+                    } else {
+                        g[FH + pi] = up;
+                        g[FH - 1 - pi] = um;
+                    }
                 }
                 if (ERR) {
                     // exact = S cos(phi) +- C sin(phi), phi = k pi (h/2) xi: Taylor for |phi| <= 1/4 (|err| < 1e-14)
@@ -402,11 +407,10 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
                     } else {
                         sincos(ph, &sp, &cp);
                     }
-                    const double xe = Se * cp, xo = Ce * sp;
-                    const double ep = up - (xe + xo), em = um - (xe - xo);
+                    const double dE = fma(-Se, cp, Ee), dO = fma(-Ce, sp, Oo);
                     if (ev) {
-                        acc_sq = fma(wgt * he * (2.0 * a.cF), fma(ep, ep, em * em), acc_sq);
-                        acc_mx = fmax(acc_mx, fmax(fabs(ep), fabs(em)));
+                        acc_sq = fma(2.0 * wgt * he * (2.0 * a.cF), fma(dE, dE, dO * dO), acc_sq);
+                        acc_mx = fmax(acc_mx, fabs(dE) + fabs(dO));
                     }
                 }
             }
@@ -444,11 +448,12 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
                     up[q] = Ee + Oo;
                     um[q] = Ee - Oo;
                     if (ERR) {
-                        const double xe = S * cf, xo = C * sf;
-                        const double ep = up[q] - (xe + xo), em = um[q] - (xe - xo);
-                        const double wgt = (i + q == FH - 1) ? 0.5 : 1.0;
-                        sq = fma(wgt, fma(ep, ep, em * em), sq);
-                        acc_mx = fmax(acc_mx, fmax(fabs(ep), fabs(em)));
+                        // errors at +-xi are dE +- dO (dE, dO = even / odd part of u - exact), so
+                        // err+^2 + err-^2 = 2 (dE^2 + dO^2) and max(|err+|, |err-|) = |dE| + |dO|
+                        const double dE = fma(-S, cf, Ee), dO = fma(-C, sf, Oo);
+                        const double wgt2 = (i + q == FH - 1) ? 1.0 : 2.0;
+                        sq = fma(wgt2, fma(dE, dE, dO * dO), sq);
+                        acc_mx = fmax(acc_mx, fabs(dE) + fabs(dO));
                         rotate(sf, cf, s2f, c2f);
                     }
                 }

@@ -12,7 +12,7 @@ def t(fn,n=10):
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)/n
 for store in (3,5):
   batch.set_option('primal_store',store)
-  for dbg in (0,1,2):
+  for dbg in ((0,1,2) if store==3 else (0,1,2,3)):
     batch.set_option('primal_debug',dbg)
     print('store',store,'debug',dbg,'ms',t(lambda: batch.lssvr_primal_batch(nodes,u,9,1e4,N=12,F=32,want_coef=False,want_fine=True,fine_out=fine)))
 batch.set_option('primal_debug',0)

@@ -114,3 +114,19 @@ def test_samples_forcing_and_boundary_correction():
     coef, fine, status = _run_dual(nodes, y, M, 1e4, samples=fs, bc2=bc2)
     ref = oracle_coef(nodes, u, M, 1e4, N, f_samples=fs)
     assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL
+
+
+def test_team_kernel_small_system():
+    """The generic team kernel (warp per element) on the 14 x 14 system, forced through the option switch."""
+    E, M, N = 300, 9, 12
+    nodes = jittered_mesh(E, seed=11)
+    u = np.sin(np.pi * nodes)
+    batch.set_option('dual_team', 1)
+    try:
+        coef, fine, status = _run_dual(nodes, u, M, 1e4, N=N, k=1.0)
+    finally:
+        batch.set_option('dual_team', 0)
+    coef2, fine2, _ = _run_dual(nodes, u, M, 1e4, N=N, k=1.0)
+    ref = oracle_coef(nodes, u, M, 1e4, N, k=1.0)
+    assert not status.any()
+    assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL and rel(fine2, kkt.evaluate_fine(ref, 32)) <= TOL

@@ -121,3 +121,21 @@ def test_dual_oracle_strong_duality(E, M, N, k):
     wp = kkt.lssvr_primal_kkt_batch(np.array([0.3, 0.3 + h]), g, f[None, :], M, 1e4)[0]
     V = np.polynomial.legendre.legvander(np.linspace(-1, 1, 32), M - 1)
     assert np.max(np.abs(V @ wd - V @ wp)) <= 1e-12 * np.max(np.abs(V @ wp))
+
+
+def test_c_port_matches_numpy_oracle():
+    """oracle/c/hfl_oracle.c (the CPU baseline of bench.py) against the numpy restatement."""
+    from oracle import c_port
+    try:
+        c_port.load()
+    except Exception as ex:          # no compiler here: the baseline falls back to the numpy port
+        pytest.skip('C port not buildable: %r' % ex)
+    nodes = np.sort(np.concatenate([[-1.0, 1.0], np.random.default_rng(0).uniform(-1, 1, 499)]))
+    u = fem_p1.solve_fem_p1(nodes, 2.0, solver='banded')
+    assert np.max(np.abs(c_port.fem_p1(nodes, 2.0) - u)) <= 1e-10
+    f = fem_p1.forcing(np.linspace(nodes[:-1], nodes[1:], 12, axis=0), 2.0).T.copy()
+    ref = kkt.lssvr_primal_kkt_batch(nodes, u, f, 9, 1e4)
+    coef, fine, mx = c_port.primal_batch(nodes, u, 9, 1e4, N=12, k_freq=2.0, F=32)
+    fr = kkt.evaluate_fine(ref, 32)
+    assert np.max(np.abs(fine - fr)) <= 1e-10 * np.max(np.abs(fr))
+    assert np.max(np.abs(coef - ref)) <= 1e-10 * np.max(np.abs(ref))
