@@ -104,15 +104,19 @@ __device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last
     for (int q = 0; q < NR; ++q) x[q] = rhs[q] * inv;
 }
 
-// Shared-memory layout of the level-0 kernels (doubles)
-constexpr int EL_LEN = FTS + 1 + (FTS + 1) / 8 + 8;   // padded per-element array
-constexpr int SM_K = 0, SM_LS = EL_LEN, SM_RS = 2 * EL_LEN;
-constexpr int SM_EX = 3 * EL_LEN;                      // 6 * FT exchange
-constexpr int SM_PCR = SM_EX + 6 * FT;                 // 2 * 6 * FT
-constexpr int SM_TOTAL = SM_PCR + 2 * 6 * FT;
+// Shared-memory layout of the level-0 kernels (doubles): two padded arrays (element stiffness, node load);
+// the exchange and PCR buffers of the reduce pass alias them once the chunk sweeps are done.
+constexpr int EL_LEN = FTS + 1 + (FTS + 1) / 8 + 8;   // padded array of FTS + 1 entries
+constexpr int SM_K = 0, SM_B = EL_LEN;
+constexpr int SM_EX = 0;                               // 6 * FT exchange (aliases SM_K, after a barrier)
+constexpr int SM_PCR = 6 * FT;                         // 2 * 6 * FT     (aliases the rest)
+constexpr int SM_UH = 2 * EL_LEN;                      // FT + 1 chunk-head values (back-substitution pass)
+constexpr int SM_TOTAL = 2 * EL_LEN + FT + 8;
+static_assert(6 * FT + 2 * 6 * FT <= 2 * EL_LEN, "PCR buffers must fit in the element arrays they alias");
 
 // Element terms of local elements q = t, t + FT, ...; the nodes of the next element are fetched while the
-// current one is being computed (software pipelining: the loads are not behind ~120 dependent instructions).
+// current one is being computed.  Node loads are accumulated as (0 + L_i) + R_{i-1}: every element first
+// writes its left-node share, then (after a barrier) adds its right-node share.
 __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P, double* sm) {
     auto fetch = [&](int q, double& x0, double& x1) {
         const long long ge = P - 1 + q;
@@ -120,16 +124,32 @@ __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P
         x0 = ok ? __ldg(a.nodes + ge) : 0.0;
         x1 = ok ? __ldg(a.nodes + ge + 1) : 1.0;
     };
+    constexpr int NQ = (FTS + FT) / FT;     // elements per thread (the last one only for thread 0)
+    double rs[NQ];
     double nx0, nx1;
     fetch(threadIdx.x, nx0, nx1);
-    for (int q = threadIdx.x; q <= FTS; q += FT) {
-        const double x0 = nx0, x1 = nx1;
-        fetch(q + FT, nx0, nx1);
-        const long long ge = P - 1 + q;
-        double k = 0.0, Ls = 0.0, Rs = 0.0;
-        if (ge >= 0 && ge <= a.n - 2) element_terms(a, x0, x1, k, Ls, Rs);
-        sm[SM_K + padi(q)] = k; sm[SM_LS + padi(q)] = Ls; sm[SM_RS + padi(q)] = Rs;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+        const int q = threadIdx.x + j * FT;
+        rs[j] = 0.0;
+        if (q <= FTS) {
+            const double x0 = nx0, x1 = nx1;
+            fetch(q + FT, nx0, nx1);
+            const long long ge = P - 1 + q;
+            double k = 0.0, Ls = 0.0, Rs = 0.0;
+            if (ge >= 0 && ge <= a.n - 2) element_terms(a, x0, x1, k, Ls, Rs);
+            sm[SM_K + padi(q)] = k;
+            if (q >= 1) sm[SM_B + padi(q - 1)] = Ls;       // left node of local element q is local node q - 1
+            rs[j] = Rs;
+        }
     }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+        const int q = threadIdx.x + j * FT;
+        if (q < FTS) sm[SM_B + padi(q)] += rs[j];          // right node of local element q is local node q
+    }
+    __syncthreads();
 }
 
 // Reduced equation of chunk head t (1 <= t <= T-1) from its own row, the previous chunk's
@@ -144,18 +164,17 @@ __device__ __forceinline__ void head_equation(double lp, double dp, double rp, d
 }
 
 // Level 0, pass 1: one record per tile = {l, d, r, b of the tile head, y1, v1, w1, ys, vs, ws of the tile interior}.
-__global__ void __launch_bounds__(FT) fem_reduce_kernel(const FemArgs a, double* __restrict__ rec,
-                                                        double* __restrict__ yvw) {
-    extern __shared__ double sm[];
+template <bool SPECIAL>
+__device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __restrict__ rec, double* __restrict__ yvw,
+                                                double* sm) {
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
-    load_tile_elements(a, P, sm);
-    __syncthreads();
-    MeshRows rows{sm + SM_K, sm + SM_LS, sm + SM_RS, P, a.n, a.uL, a.uR};
+    MeshRows<SPECIAL> rows{sm + SM_K, sm + SM_B, P, a.n, a.uL, a.uR};
     double six[6];
     chunk_reduce(rows, t * FS, FS, six);
     double lp, dp, rp, bp;
     rows.get(t * FS, lp, dp, rp, bp);
+    __syncthreads();                 // the element arrays are dead from here: exchange / PCR buffers alias them
     double* ex = sm + SM_EX;
 #pragma unroll
     for (int i = 0; i < 6; ++i) ex[i * FT + t] = six[i];
@@ -190,6 +209,15 @@ __global__ void __launch_bounds__(FT) fem_reduce_kernel(const FemArgs a, double*
         out[8] = -six[4] * x[1];
         out[9] = six[5] - six[4] * x[2];
     }
+}
+
+__global__ void __launch_bounds__(FT, 4) fem_reduce_kernel(const FemArgs a, double* __restrict__ rec,
+                                                           double* __restrict__ yvw) {
+    extern __shared__ double sm[];
+    const long long P = (long long)blockIdx.x * FTS;
+    load_tile_elements(a, P, sm);
+    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true>(a, rec, yvw, sm);
+    else fem_reduce_body<false>(a, rec, yvw, sm);
 }
 
 // Top level: solve the system of tile heads.  One CTA of TOPT threads, chunk of S heads per thread.
@@ -276,22 +304,21 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
 
 // Level 0, pass 2: tile head values known -> chunk heads from the stored partial solutions
 // (U_t = Y_t - u_P V_t - u_Q W_t) -> chunk interiors by Thomas -> u.
-__global__ void __launch_bounds__(FT) fem_backsub_kernel(const FemArgs a, const double* __restrict__ utop, int ntile,
-                                                         const double* __restrict__ yvw, double* __restrict__ u) {
-    extern __shared__ double sm[];
+template <bool SPECIAL>
+__device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double* __restrict__ utop, int ntile,
+                                                 const double* __restrict__ yvw, double* __restrict__ u, double* sm) {
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
-    load_tile_elements(a, P, sm);
     const double uP = utop[blockIdx.x];
     const double uQ = ((int)blockIdx.x + 1 < ntile) ? utop[blockIdx.x + 1] : 0.0;
-    double* uh = sm + SM_EX;    // FT head values (+1 for the next tile's head)
+    double* uh = sm + SM_UH;    // FT head values (+1 for the next tile's head)
     {
         const double* o = yvw + (size_t)blockIdx.x * 3 * FT;
         uh[t] = (t == 0) ? uP : (o[t] - uP * o[FT + t] - uQ * o[2 * FT + t]);
         if (t == 0) uh[FT] = uQ;
     }
     __syncthreads();
-    MeshRows rows{sm + SM_K, sm + SM_LS, sm + SM_RS, P, a.n, a.uL, a.uR};
+    MeshRows<SPECIAL> rows{sm + SM_K, sm + SM_B, P, a.n, a.uL, a.uR};
     const double ua = uh[t], ub = uh[t + 1];
     // Thomas on the chunk interior, compile-time length FS - 1
     double cpv[FS], bpv[FS], xs[FS];
@@ -323,6 +350,15 @@ __global__ void __launch_bounds__(FT) fem_backsub_kernel(const FemArgs a, const 
         const long long g = P + m;
         if (g < a.n) u[g] = stage[padi(m)];
     }
+}
+
+__global__ void __launch_bounds__(FT, 4) fem_backsub_kernel(const FemArgs a, const double* __restrict__ utop, int ntile,
+                                                            const double* __restrict__ yvw, double* __restrict__ u) {
+    extern __shared__ double sm[];
+    const long long P = (long long)blockIdx.x * FTS;
+    load_tile_elements(a, P, sm);
+    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true>(a, utop, ntile, yvw, u, sm);
+    else fem_backsub_body<false>(a, utop, ntile, yvw, u, sm);
 }
 
 // End-node residuals for the multi-GPU interface system (see hfl.h).

@@ -23,19 +23,23 @@ struct FemArgs {
     double gx0, gx1; // Gauss points on [0, 1]
 };
 
-// Rows of the level-0 system from per-element arrays held in shared memory.
-// Local element q <-> global element P - 1 + q;  local node m <-> global node P + m.
+// Rows of the level-0 system from shared memory: k[q] = stiffness entry of local element q (global element
+// P - 1 + q), b[m] = load of local node m (global node P + m).  SPECIAL = the tile contains a Dirichlet node
+// or padding past the mesh (first / last tile only); interior tiles take the branch-free path.
+template <bool SPECIAL>
 struct MeshRows {
-    const double* k; const double* Ls; const double* Rs;
+    const double* k; const double* b;
     long long P, n; double uL, uR;
-    __device__ __forceinline__ void get(int m, double& l, double& d, double& r, double& b) const {
-        const long long g = P + m;
-        if (g >= n) { l = 0.0; d = 1.0; r = 0.0; b = 0.0; return; }
-        if (g == 0) { l = 0.0; d = 1.0; r = 0.0; b = uL; return; }
-        if (g == n - 1) { l = 0.0; d = 1.0; r = 0.0; b = uR; return; }
+    __device__ __forceinline__ void get(int m, double& l, double& d, double& r, double& bo) const {
+        if (SPECIAL) {
+            const long long g = P + m;
+            if (g >= n) { l = 0.0; d = 1.0; r = 0.0; bo = 0.0; return; }
+            if (g == 0) { l = 0.0; d = 1.0; r = 0.0; bo = uL; return; }
+            if (g == n - 1) { l = 0.0; d = 1.0; r = 0.0; bo = uR; return; }
+        }
         const double kl = k[padi(m)], kr = k[padi(m + 1)];
         l = -kl; r = -kr; d = kl + kr;
-        b = Ls[padi(m + 1)] + Rs[padi(m)];
+        bo = b[padi(m)];
     }
 };
 
