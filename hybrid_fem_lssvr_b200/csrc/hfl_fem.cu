@@ -104,54 +104,6 @@ __device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last
     for (int q = 0; q < NR; ++q) x[q] = rhs[q] * inv;
 }
 
-// Shared-memory layout of the level-0 kernels (doubles): two padded arrays (element stiffness, node load);
-// the exchange and PCR buffers of the reduce pass alias them once the chunk sweeps are done.
-constexpr int EL_LEN = FTS + 1 + (FTS + 1) / 8 + 8;   // padded array of FTS + 1 entries
-constexpr int SM_K = 0, SM_B = EL_LEN;
-constexpr int SM_EX = 0;                               // 6 * FT exchange (aliases SM_K, after a barrier)
-constexpr int SM_PCR = 6 * FT;                         // 2 * 6 * FT     (aliases the rest)
-constexpr int SM_UH = 2 * EL_LEN;                      // FT + 1 chunk-head values (back-substitution pass)
-constexpr int SM_TOTAL = 2 * EL_LEN + FT + 8;
-static_assert(6 * FT + 2 * 6 * FT <= 2 * EL_LEN, "PCR buffers must fit in the element arrays they alias");
-
-// Element terms of local elements q = t, t + FT, ...; the nodes of the next element are fetched while the
-// current one is being computed.  Node loads are accumulated as (0 + L_i) + R_{i-1}: every element first
-// writes its left-node share, then (after a barrier) adds its right-node share.
-__device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P, double* sm) {
-    auto fetch = [&](int q, double& x0, double& x1) {
-        const long long ge = P - 1 + q;
-        const bool ok = (q <= FTS) && ge >= 0 && ge <= a.n - 2;
-        x0 = ok ? __ldg(a.nodes + ge) : 0.0;
-        x1 = ok ? __ldg(a.nodes + ge + 1) : 1.0;
-    };
-    constexpr int NQ = (FTS + FT) / FT;     // elements per thread (the last one only for thread 0)
-    double rs[NQ];
-    double nx0, nx1;
-    fetch(threadIdx.x, nx0, nx1);
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-        const int q = threadIdx.x + j * FT;
-        rs[j] = 0.0;
-        if (q <= FTS) {
-            const double x0 = nx0, x1 = nx1;
-            fetch(q + FT, nx0, nx1);
-            const long long ge = P - 1 + q;
-            double k = 0.0, Ls = 0.0, Rs = 0.0;
-            if (ge >= 0 && ge <= a.n - 2) element_terms(a, x0, x1, k, Ls, Rs);
-            sm[SM_K + padi(q)] = k;
-            if (q >= 1) sm[SM_B + padi(q - 1)] = Ls;       // left node of local element q is local node q - 1
-            rs[j] = Rs;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-        const int q = threadIdx.x + j * FT;
-        if (q < FTS) sm[SM_B + padi(q)] += rs[j];          // right node of local element q is local node q
-    }
-    __syncthreads();
-}
-
 // Reduced equation of chunk head t (1 <= t <= T-1) from its own row, the previous chunk's
 // {ys, vs, ws} and its own {y1, v1, w1}.
 __device__ __forceinline__ void head_equation(double lp, double dp, double rp, double bp, double ys_prev,

@@ -18,29 +18,14 @@ __device__ __forceinline__ Tri tri_op(const Tri& x, const Tri& y) {   // x befor
     return Tri{x.b + y.b, x.c + y.c, x.d + y.d + x.b * y.c};
 }
 
-constexpr int EL2 = FTS + 1 + (FTS + 1) / 8 + 8;
+constexpr int FLUX_SCAN = 2 * EL_LEN;          // 3 * FT doubles of scan scratch after the two element arrays
+constexpr int FLUX_SMEM = 2 * EL_LEN + 3 * FT;
 
 // Tile = elements [P, P + FTS).  Element e contributes b_e (load of node e; 0 for e = 0), c = 1/k_e,
-// d = B_e / k_e with B inclusive.  Thread t owns elements P + t*FS .. P + t*FS + FS - 1.
+// d = B_e / k_e with B inclusive.  Thread t owns elements P + t*FS .. P + t*FS + FS - 1.  The element arrays are
+// the ones of hfl_fem.cu (local element q <-> global element P - 1 + q, node load of local node m = q - 1).
 __device__ __forceinline__ void tile_local(const FemArgs& a, long long P, double* sm, Tri (&inc)[FS], Tri& agg) {
-    // element arrays with a one-element halo on the left: local q <-> global element P - 1 + q
-    auto fetch = [&](int q, double& x0, double& x1) {
-        const long long ge = P - 1 + q;
-        const bool ok = (q <= FTS) && ge >= 0 && ge <= a.n - 2;
-        x0 = ok ? __ldg(a.nodes + ge) : 0.0;
-        x1 = ok ? __ldg(a.nodes + ge + 1) : 1.0;
-    };
-    double nx0, nx1;
-    fetch(threadIdx.x, nx0, nx1);
-    for (int q = threadIdx.x; q <= FTS; q += FT) {
-        const double x0 = nx0, x1 = nx1;
-        fetch(q + FT, nx0, nx1);                         // next element's nodes, in flight during this one's sines
-        const long long ge = P - 1 + q;
-        double k = 1.0, Ls = 0.0, Rs = 0.0;
-        if (ge >= 0 && ge <= a.n - 2) element_terms(a, x0, x1, k, Ls, Rs);
-        sm[padi(q)] = k; sm[EL2 + padi(q)] = Ls; sm[2 * EL2 + padi(q)] = Rs;
-    }
-    __syncthreads();
+    load_tile_elements(a, P, sm);
     agg = Tri{0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < FS; ++i) {
@@ -48,8 +33,8 @@ __device__ __forceinline__ void tile_local(const FemArgs& a, long long P, double
         const long long ge = P - 1 + q;
         Tri x{0.0, 0.0, 0.0};
         if (ge <= a.n - 2) {
-            const double b = (ge >= 1) ? sm[EL2 + padi(q)] + sm[2 * EL2 + padi(q - 1)] : 0.0;   // Ls_e + Rs_{e-1}
-            const double c = 1.0 / sm[padi(q)];
+            const double b = (ge >= 1) ? sm[SM_B + padi(q - 1)] : 0.0;      // load of node ge
+            const double c = 1.0 / sm[SM_K + padi(q)];
             x = Tri{b, c, b * c};
         }
         inc[i] = x;
@@ -81,11 +66,11 @@ __device__ __forceinline__ Tri cta_exclusive_scan(Tri v, double* sm, Tri& total)
     return ex;
 }
 
-__global__ void __launch_bounds__(FT) flux_tile_kernel(const FemArgs a, double* __restrict__ agg3) {
+__global__ void __launch_bounds__(FT, 4) flux_tile_kernel(const FemArgs a, double* __restrict__ agg3) {
     extern __shared__ double sm[];
     Tri inc[FS], agg, total;
     tile_local(a, (long long)blockIdx.x * FTS, sm, inc, agg);
-    cta_exclusive_scan<FT>(agg, sm + 3 * EL2, total);
+    cta_exclusive_scan<FT>(agg, sm + FLUX_SCAN, total);
     if (threadIdx.x == 0) {
         agg3[3 * (size_t)blockIdx.x + 0] = total.b;
         agg3[3 * (size_t)blockIdx.x + 1] = total.c;
@@ -115,14 +100,14 @@ __global__ void __launch_bounds__(TOPT) flux_top_kernel(const double* __restrict
     if (t == 0) prefix[3 * (size_t)nt] = (uR - uL + total.d) / total.c;
 }
 
-__global__ void __launch_bounds__(FT) flux_apply_kernel(const FemArgs a, const double* __restrict__ prefix, int nt,
+__global__ void __launch_bounds__(FT, 4) flux_apply_kernel(const FemArgs a, const double* __restrict__ prefix, int nt,
                                                         double* __restrict__ u) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
     Tri inc[FS], agg, total;
     tile_local(a, P, sm, inc, agg);
-    Tri run = cta_exclusive_scan<FT>(agg, sm + 3 * EL2, total);
+    Tri run = cta_exclusive_scan<FT>(agg, sm + FLUX_SCAN, total);
     const Tri base{prefix[3 * (size_t)blockIdx.x], prefix[3 * (size_t)blockIdx.x + 1], prefix[3 * (size_t)blockIdx.x + 2]};
     const double q0 = prefix[3 * (size_t)nt];
     run = tri_op(base, run);
@@ -157,7 +142,7 @@ int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes
         set_error("hfl_fem_p1_solve: workspace too small for the flux scan");
         return HFL_ERR_ARG;
     }
-    const size_t smem = (size_t)(3 * EL2 + 3 * FT) * sizeof(double);
+    const size_t smem = (size_t)FLUX_SMEM * sizeof(double);
     static thread_local bool configured = false;
     if (!configured) {
         HFL_CUDA_CHECK(cudaFuncSetAttribute(flux_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
