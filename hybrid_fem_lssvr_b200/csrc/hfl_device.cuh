@@ -62,6 +62,19 @@ __device__ __forceinline__ bool ldl_solve(double (&A)[n * (n + 1) / 2 > 0 ? n * 
     return ok;
 }
 
+// sin(pi t), cos(pi t) for the per-element BASE angles (k h / (2 (N-1)) and the like), which are tiny on any
+// mesh fine enough to matter for throughput: below 2^-7 a degree-7 / degree-8 Taylor polynomial is exact to
+// rounding (truncation < 1e-19 relative); otherwise the library sincospi.
+__device__ __forceinline__ void sincospi_base(double t, double* s, double* c) {
+    if (fabs(t) < 0.0078125) {
+        const double x = 3.14159265358979323846 * t, z = x * x;
+        *s = x * fma(z, fma(z, fma(z, -1.984126984126984e-04, 8.333333333333333e-03), -1.6666666666666666e-01), 1.0);
+        *c = fma(z, fma(z, fma(z, fma(z, 2.48015873015873e-05, -1.388888888888889e-03), 4.1666666666666664e-02), -0.5), 1.0);
+    } else {
+        sincospi(t, s, c);
+    }
+}
+
 // Rotation of (s, c) = (sin t, cos t) by the angle whose sine / cosine are (s2, c2).
 __device__ __forceinline__ void rotate(double& s, double& c, double s2, double c2) {
     const double sn = fma(s, c2, c * s2);

@@ -201,7 +201,7 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
             if (a.forcing == HFL_FORCING_SINE || ERR) sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
             if (a.forcing == HFL_FORCING_SINE) {
                 double sb, cb;
-                sincospi(a.k_freq * h * a.cN, &sb, &cb);
+                sincospi_base(a.k_freq * h * a.cN, &sb, &cb);
                 const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
                 double s = sb, c = cb;                      // N even
                 const double fE = isig * a.kk * S, fO = isig * a.kk * C;
@@ -283,7 +283,7 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
         if (a.debug == 2) {
         } else if (a.forcing == HFL_FORCING_SINE) {
             double sb, cb;
-            sincospi(a.k_freq * h * a.cN, &sb, &cb);       // base angle k pi (h/2) / (N-1)
+            sincospi_base(a.k_freq * h * a.cN, &sb, &cb);       // base angle k pi (h/2) / (N-1)
             const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
             double s = (a.N & 1) ? 0.0 : sb, c = (a.N & 1) ? 1.0 : cb;
             for (int j = 0; j < a.NH; ++j) {
@@ -420,7 +420,7 @@ primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ Prim
         if (FH > 0 && do_fine) {
             double sf = 0.0, cf = 1.0, s2f = 0.0, c2f = 1.0, sq = 0.0;
             if (ERR) {
-                sincospi(a.k_freq * h * a.cF, &sf, &cf);   // base angle k pi (h/2) / (F-1); F even
+                sincospi_base(a.k_freq * h * a.cF, &sf, &cf);   // base angle k pi (h/2) / (F-1); F even
                 s2f = 2.0 * sf * cf;
                 c2f = fma(-2.0 * sf, sf, 1.0);
             }
