@@ -308,8 +308,7 @@ __global__ void __launch_bounds__(FT, 4) fem_backsub_kernel(const FemArgs a, con
                                                             const double* __restrict__ yvw, double* __restrict__ u) {
     extern __shared__ double sm[];
     const long long P = (long long)blockIdx.x * FTS;
-    if (a.cache_k != nullptr) load_tile_cached(a, P, sm);
-    else load_tile_elements(a, P, sm);
+    load_tile_elements(a, P, sm);   // recomputed: re-reading cached terms (16 B/node) measured slower than 2 sinpi
     if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true>(a, utop, ntile, yvw, u, sm);
     else fem_backsub_body<false>(a, utop, ntile, yvw, u, sm);
 }
@@ -375,7 +374,7 @@ static inline long long fem_ntile(long long n) { return (n + FTS - 1) / FTS; }
 extern "C" size_t hfl_fem_p1_workspace_bytes(int64_t n_nodes) {
     if (n_nodes < 2) return 256;
     const long long nt = fem_ntile(n_nodes);
-    return (size_t)(REC + 1 + 6 + 3 * FT) * (size_t)nt * sizeof(double) + 2 * (size_t)n_nodes * sizeof(double) + 512;
+    return (size_t)(REC + 1 + 6 + 3 * FT) * (size_t)nt * sizeof(double) + 256;
 }
 
 int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes, cudaStream_t s);   // hfl_flux.cu
@@ -396,12 +395,6 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
     a.n = n; a.nodes = d_nodes; a.k = k_freq; a.kpi = k_freq * pi; a.kp2 = a.kpi * a.kpi; a.uL = u_left; a.uR = u_right;
     a.gx0 = 0.5 * (-0.5773502691896257) + 0.5;   // 0.5 * leggauss(2) + 0.5
     a.gx1 = 0.5 * (0.5773502691896257) + 0.5;
-    {   // element-term cache at the end of the workspace (2 n doubles)
-        const size_t small = (size_t)(REC + 1 + 6 + 3 * FT) * (size_t)fem_ntile(n) * sizeof(double);
-        double* c = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + ((small + 255) / 256) * 256);
-        a.cache_k = c;
-        a.cache_b = c + n;
-    }
     if (coarse_solver == HFL_COARSE_FLUX_SCAN) {
         int rc = hfl_fem_flux_scan(a, d_u, d_ws, ws_bytes, s);
         if (rc != HFL_OK) return rc;

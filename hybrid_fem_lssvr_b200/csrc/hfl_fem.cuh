@@ -21,8 +21,6 @@ struct FemArgs {
     double kp2;      // (k pi)^2
     double uL, uR;
     double gx0, gx1; // Gauss points on [0, 1]
-    double* cache_k; // optional [n]: element stiffness entries written by pass 1, read by pass 2
-    double* cache_b; // optional [n]: node loads
 };
 
 // Rows of the level-0 system from shared memory: k[q] = stiffness entry of local element q (global element
@@ -113,24 +111,7 @@ __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
         const int q = threadIdx.x + j * FT;
-        if (q < FTS) {
-            const double bv = sm[SM_B + padi(q)] + rs[j];  // right node of local element q is local node q
-            sm[SM_B + padi(q)] = bv;
-            if (a.cache_b != nullptr && P + q < a.n) {     // pass 2 reloads these instead of recomputing the sines
-                a.cache_b[P + q] = bv;
-                a.cache_k[P + q] = sm[SM_K + padi(q + 1)]; // element P + q
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// Pass 2: the same two arrays from the cache written by pass 1 (coalesced 16 B/node instead of 2 sinpi + 1 division).
-__device__ __forceinline__ void load_tile_cached(const FemArgs& a, long long P, double* sm) {
-    for (int q = threadIdx.x; q <= FTS; q += FT) {
-        const long long ge = P - 1 + q;
-        sm[SM_K + padi(q)] = (ge >= 0 && ge <= a.n - 2) ? __ldg(a.cache_k + ge) : 0.0;
-        if (q < FTS) sm[SM_B + padi(q)] = (P + q < a.n) ? __ldg(a.cache_b + P + q) : 0.0;
+        if (q < FTS) sm[SM_B + padi(q)] += rs[j];          // right node of local element q is local node q
     }
     __syncthreads();
 }

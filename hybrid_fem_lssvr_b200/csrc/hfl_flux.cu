@@ -24,10 +24,8 @@ constexpr int FLUX_SMEM = 2 * EL_LEN + 3 * FT;
 // Tile = elements [P, P + FTS).  Element e contributes b_e (load of node e; 0 for e = 0), c = 1/k_e,
 // d = B_e / k_e with B inclusive.  Thread t owns elements P + t*FS .. P + t*FS + FS - 1.  The element arrays are
 // the ones of hfl_fem.cu (local element q <-> global element P - 1 + q, node load of local node m = q - 1).
-__device__ __forceinline__ void tile_local(const FemArgs& a, long long P, double* sm, Tri (&inc)[FS], Tri& agg,
-                                           bool from_cache) {
-    if (from_cache) load_tile_cached(a, P, sm);
-    else load_tile_elements(a, P, sm);
+__device__ __forceinline__ void tile_local(const FemArgs& a, long long P, double* sm, Tri (&inc)[FS], Tri& agg) {
+    load_tile_elements(a, P, sm);
     agg = Tri{0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < FS; ++i) {
@@ -71,7 +69,7 @@ __device__ __forceinline__ Tri cta_exclusive_scan(Tri v, double* sm, Tri& total)
 __global__ void __launch_bounds__(FT, 4) flux_tile_kernel(const FemArgs a, double* __restrict__ agg3) {
     extern __shared__ double sm[];
     Tri inc[FS], agg, total;
-    tile_local(a, (long long)blockIdx.x * FTS, sm, inc, agg, false);
+    tile_local(a, (long long)blockIdx.x * FTS, sm, inc, agg);
     cta_exclusive_scan<FT>(agg, sm + FLUX_SCAN, total);
     if (threadIdx.x == 0) {
         agg3[3 * (size_t)blockIdx.x + 0] = total.b;
@@ -108,7 +106,7 @@ __global__ void __launch_bounds__(FT, 4) flux_apply_kernel(const FemArgs a, cons
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
     Tri inc[FS], agg, total;
-    tile_local(a, P, sm, inc, agg, a.cache_k != nullptr);
+    tile_local(a, P, sm, inc, agg);
     Tri run = cta_exclusive_scan<FT>(agg, sm + FLUX_SCAN, total);
     const Tri base{prefix[3 * (size_t)blockIdx.x], prefix[3 * (size_t)blockIdx.x + 1], prefix[3 * (size_t)blockIdx.x + 2]};
     const double q0 = prefix[3 * (size_t)nt];

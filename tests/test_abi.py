@@ -49,7 +49,7 @@ def test_version_and_error_paths(lib):
     v = C.c_int(-1)
     assert lib.hfl_get_option(b'primal_store', C.byref(v)) == 0 and v.value == 2
     assert lib.hfl_set_option(b'primal_store', 0) == 0
-    assert lib.hfl_fem_p1_workspace_bytes(10_000_001) >= (17 + 768) * 4883 * 8 + 2 * 10_000_001 * 8
+    assert lib.hfl_fem_p1_workspace_bytes(10_000_001) >= (17 + 768) * 4883 * 8
 
 
 def test_interface_solve_host(lib):
