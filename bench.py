@@ -102,11 +102,13 @@ def run_cpu_baseline_c(sample, steps=1):
     nodes = np.linspace(-1.0, 1.0, min(sample, 20000) + 1)
     c_port.primal_batch(nodes, c_port.fem_p1(nodes, KFREQ), M, GAMMA, N=NCOL, k_freq=KFREQ, F=F, want_coef=False)
     times, mx = [], 0.0
+    fine = np.empty((sample, F))            # output buffer allocated (and its pages touched) once, like the GPU arm
+    fine[:] = 0.0
     for _ in range(steps):
         t0 = time.perf_counter()
         nodes = np.linspace(-1.0, 1.0, sample + 1)
         u = c_port.fem_p1(nodes, KFREQ)
-        _, _, mx = c_port.primal_batch(nodes, u, M, GAMMA, N=NCOL, k_freq=KFREQ, F=F, want_coef=False, want_fine=True)
+        _, _, mx = c_port.primal_batch(nodes, u, M, GAMMA, N=NCOL, k_freq=KFREQ, F=F, want_coef=False, fine_out=fine)
         times.append(time.perf_counter() - t0)
     return sample / (sum(times) / len(times)), cores, mx, times
 
@@ -287,7 +289,7 @@ def run_ours(args):
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             tj = json.load(fh)
         if E == tj.get('elements'):
-            traffic = tj['primal_kernel_fused_err' if args.error == 'fused' else 'primal_kernel']
+            traffic = tj['lssvr_element_kernel_fused_err' if args.error == 'fused' else 'lssvr_element_kernel']
     except Exception:
         pass
 
@@ -362,7 +364,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        cpu = cpu_baseline_record(args.cpu_sample, steps=2)
+        cpu = cpu_baseline_record(args.cpu_sample, steps=6)
 
     if rank == 0:
         line = {
@@ -381,7 +383,7 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'kernel': 'primal_kernel<M=9,FH=16,ERR=%s> (K2+K3%s)'
+                         'traffic': traffic, 'kernel': 'lssvr_element_kernel<M=9,FH=16,ERR=%s> (K2+K3%s)'
                          % ('true' if args.error == 'fused' else 'false', '+K5' if args.error == 'fused' else ''),
                          'algorithmic_bytes_per_element': BYTES_PER_ELEMENT, 'kernel_ms': k2_ms, 'peak_source': peak_src},
             'kernels_ms': {'K1_coarse_solve_' + args.coarse: k1_ms, 'K1_coarse_solve_' + k1_other: k1_other_ms, 'K2K3_primal_fine' + ('_K5' if args.error == 'fused' else ''): k2_ms,
@@ -402,7 +404,7 @@ def cpu_baseline_record(sample_arg, steps):
     (kind "port").  Also times the numpy port and the reference's own SLSQP formulation on small samples."""
     rec = None
     try:
-        sample = sample_arg or 4_000_000
+        sample = sample_arg or 10_000_000      # the whole headline workload; ~1-3 s per pass on a 16+ thread host
         v, cores, cmx, times = run_cpu_baseline_c(sample, steps=steps)
         rec = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                'sample': '%d elements of the same uniform mesh family (M=9, N=12, F=32) per pass, %d passes: C/OpenMP '

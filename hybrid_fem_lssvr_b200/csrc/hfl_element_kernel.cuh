@@ -118,7 +118,7 @@ __device__ __forceinline__ int ldl_solve_skip(double (&A)[n * (n + 1) / 2], doub
 
 template <int M, int FH, bool ERR, int STORE, int NHD = 0>
 __global__ void __launch_bounds__(kThreads, NHD > 0 ? 3 : min_ctas(M, ERR))
-primal_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
+lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
               const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DualSmallTables<M, NHD> dt) {
     constexpr int ME = n_even(M), MO = n_odd(M);
     constexpr int F = 2 * FH;
@@ -607,7 +607,7 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
         int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F, STORE == STORE_TMA_ROWS);
         if (rc != HFL_OK) return rc;
     }
-    auto kern = primal_kernel<M, FH, ERR, STORE, NHD>;
+    auto kern = lssvr_element_kernel<M, FH, ERR, STORE, NHD>;
     DualSmallTables<M, NHD> dt;
     if (dtp) dt = *dtp; else memset(&dt, 0, sizeof(dt));
     const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) +

@@ -39,13 +39,13 @@ def fem_p1(nodes, k_freq=1.0):
     return u
 
 
-def primal_batch(nodes, u, M, gamma, N=12, k_freq=1.0, F=32, want_coef=True, want_fine=True):
+def primal_batch(nodes, u, M, gamma, N=12, k_freq=1.0, F=32, want_coef=True, want_fine=True, fine_out=None):
     """Returns (coef [E, M] | None, fine [E, F] | None, max |u - sin(k pi x)| on the fine grid)."""
     nodes = np.ascontiguousarray(nodes, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
     E = nodes.size - 1
     coef = np.empty((E, M)) if want_coef else None
-    fine = np.empty((E, F)) if want_fine else None
+    fine = fine_out if fine_out is not None else (np.empty((E, F)) if want_fine else None)
     mx = load().oracle_primal_batch(E, nodes, u, M, float(gamma), N, float(k_freq), F,
                                     coef.ctypes.data if coef is not None else None,
                                     fine.ctypes.data if fine is not None else None)
