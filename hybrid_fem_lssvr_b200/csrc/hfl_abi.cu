@@ -80,8 +80,9 @@ extern "C" int hfl_set_option(const char* key, int value) {
         g_opt_store.store(value);
         return HFL_OK;
     }
-    if (strcmp(key, "dual_team") == 0) {   // 1 = always use the generic team kernel for the dual form
-        g_opt_dual_team.store(value ? 1 : 0);
+    if (strcmp(key, "dual_team") == 0) {   // 1 = skip the register kernel; 2 = also skip the parity-split team kernel
+        HFL_REQUIRE(value >= 0 && value <= 2, "dual_team must be 0..2");
+        g_opt_dual_team.store(value);
         return HFL_OK;
     }
     if (strcmp(key, "primal_debug") == 0) {
@@ -179,6 +180,35 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
             }
     }
 
+    if (N % 2 == 0) {   // parity blocks of the dual system
+        const int NHp = N / 2, nh = NHp + 1, MEA = n_even(M) + 1, MOA = n_odd(M) + 1;
+        std::vector<long double> Ce((size_t)nh * MEA), Co((size_t)nh * MOA);
+        for (int j = 0; j < NHp; ++j) {
+            legendre012(M, half_point(N, j), P.data(), d1.data(), d2.data());
+            for (int a = 0; a < MEA; ++a) Ce[(size_t)j * MEA + a] = -d2[2 * a];
+            for (int b = 0; b < MOA; ++b) Co[(size_t)j * MOA + b] = -d2[2 * b + 1];
+        }
+        for (int a = 0; a < MEA; ++a) Ce[(size_t)NHp * MEA + a] = 1.0L;
+        for (int b = 0; b < MOA; ++b) Co[(size_t)NHp * MOA + b] = 1.0L;
+        auto gram = [&](const std::vector<long double>& C, int m, std::vector<double>& K) {
+            K.resize((size_t)nh * nh);
+            for (int i = 0; i < nh; ++i)
+                for (int j = 0; j < nh; ++j) {
+                    long double s = 0.0L;
+                    for (int k = 0; k < m; ++k) s += C[(size_t)i * m + k] * C[(size_t)j * m + k];
+                    K[(size_t)i * nh + j] = (double)s;
+                }
+        };
+        gram(Ce, MEA, p->Kpe);
+        gram(Co, MOA, p->Kpo);
+        p->Cpe.resize(Ce.size());
+        p->Cpo.resize(Co.size());
+        for (size_t i = 0; i < Ce.size(); ++i) p->Cpe[i] = (double)Ce[i];
+        for (size_t i = 0; i < Co.size(); ++i) p->Cpo[i] = (double)Co[i];
+    } else {
+        p->Cpe.assign(1, 0.0); p->Cpo.assign(1, 0.0); p->Kpe.assign(1, 0.0); p->Kpo.assign(1, 0.0);
+    }
+
     // one device block, each table 16-double (128 B) aligned
     std::vector<double> blk;
     auto push = [&](const std::vector<double>& v) {
@@ -190,6 +220,7 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
     p->off_De = push(p->De); p->off_Do = push(p->Do); p->off_Ge = push(p->Ge); p->off_Go = push(p->Go);
     p->off_fineE = push(p->fineE); p->off_fineO = push(p->fineO); p->off_D2 = push(p->D2); p->off_V = push(p->V);
     p->off_Ct = push(p->Ct); p->off_K0 = push(p->K0);
+    p->off_Cpe = push(p->Cpe); p->off_Cpo = push(p->Cpo); p->off_Kpe = push(p->Kpe); p->off_Kpo = push(p->Kpo);
     p->n_tables = blk.size();
     cudaError_t e = cudaMalloc((void**)&p->d_tables, blk.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tables, blk.data(), blk.size() * sizeof(double), cudaMemcpyHostToDevice);

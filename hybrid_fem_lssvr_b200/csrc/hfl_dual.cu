@@ -238,6 +238,207 @@ __global__ void __launch_bounds__(TS == 32 ? 128 : TS) dual_kernel(const DualArg
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Parity-split team kernel (even N): the (N+2) system decouples into an even and an odd block of nh = N/2 + 1
+// unknowns (derivation in hfl_dual_small.cu).  One CTA of 256 threads per element = two teams of 128, team 0
+// factorises the even block, team 1 the odd one, concurrently (named barriers); the R right-hand sides are solved
+// one per thread inside each team; the whole CTA then evaluates the R x F fine values.  Compared with the
+// full-system kernel above: 4x fewer flops per pivot step, half the pivot steps per team, half the shared memory.
+struct DualParityArgs {
+    DualArgs d;
+    const double* Kp[2];    // [nh][nh] per parity
+    const double* Cp[2];    // [nh][MA] per parity
+    int nh, ldh, MA[2];
+};
+
+__device__ __forceinline__ void half_sync(int team) {
+    asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory");
+}
+
+__device__ __forceinline__ void half_argmax(double& v, int& idx, double* red, int team, int t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    half_sync(team);
+    if ((t & 31) == 0) { red[t >> 5] = v; red[4 + (t >> 5)] = (double)idx; }
+    half_sync(team);
+    v = red[0]; idx = (int)red[4];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+        const double ov = red[q];
+        const int oi = (int)red[4 + q];
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+
+__global__ void __launch_bounds__(256) dual_parity_kernel(const DualParityArgs pa) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DualArgs& a = pa.d;
+    const int nh = pa.nh, ld = pa.ldh, M = a.M, N = a.N, NHc = N / 2, F = a.F, R = a.R;
+    const int team = threadIdx.x >> 7, t = threadIdx.x & 127;
+    // shared: per team {A [nh][ld], invl [nh], red [8], perm [nh] int, rank int}; then wbuf [R][M], eacc [2R]
+    const size_t team_doubles = (size_t)nh * ld + nh + 8;
+    const size_t team_bytes = ((team_doubles * 8 + (size_t)(nh + 2) * 4) + 15) / 16 * 16;
+    unsigned char* base = smem_raw + team * team_bytes;
+    double* A = reinterpret_cast<double*>(base);
+    double* invl = A + (size_t)nh * ld;
+    double* red = invl + nh;
+    int* perm = reinterpret_cast<int*>(red + 8);
+    int* rank_s = perm + nh;
+    double* wbuf = reinterpret_cast<double*>(smem_raw + 2 * team_bytes);
+    double* eacc = wbuf + (size_t)R * M;
+    const int* rank_other = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw + (1 - team) * team_bytes) +
+                                                   (size_t)nh * ld + nh + 8) + nh;
+
+    double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
+    if (a.bc2 != nullptr) {
+        bcl = a.bc2[0]; bcr = a.bc2[1];
+        x_first = a.nodes[0]; x_last = a.nodes[a.E];
+        invL = 1.0 / (x_last - x_first);
+    }
+    const double eps_tol = 2.220446049250313e-16 * (1.0 / 1024.0);
+    for (int i = threadIdx.x; i < 2 * R; i += 256) eacc[i] = 0.0;
+    int nfail = 0;
+    const double* Kp = pa.Kp[team];
+    const double* Cp = pa.Cp[team];
+    const int MA = pa.MA[team];
+
+    for (long long e = blockIdx.x; e < a.E; e += gridDim.x) {
+        const double xl = a.nodes[e], xr = a.nodes[e + 1];
+        const double h = xr - xl, h2 = h * h;
+        const double isig = 0.25 * h2, th = 0.5 * (h2 * h2) * a.c_tau;
+        for (int idx = t; idx < nh * nh; idx += 128) {
+            const int i = idx / nh, j = idx - i * nh;
+            double v = Kp[idx];
+            if (i == j && i < NHc) v += th;
+            A[i * ld + j] = v;
+        }
+        for (int i = t; i < nh; i += 128) perm[i] = i;
+        half_sync(team);
+        double dmax0 = 0.0;
+        int rank = 0;
+        for (int k = 0; k < nh; ++k) {
+            double v = -1.0;
+            int pos = 0x7fffffff;
+            for (int i = k + t; i < nh; i += 128) {
+                const int pi = perm[i];
+                const double d = A[pi * ld + pi];
+                if (d > v) { v = d; pos = i; }
+            }
+            half_argmax(v, pos, red, team, t);
+            if (k == 0) dmax0 = v;
+            if (!(v > eps_tol * dmax0)) break;
+            if (t == 0) { const int tmp = perm[k]; perm[k] = perm[pos]; perm[pos] = tmp; }
+            half_sync(team);
+            const int pk = perm[k];
+            const double il = rsqrt(v);
+            if (t == 0) invl[k] = il;
+            for (int i = k + 1 + t; i < nh; i += 128) A[perm[i] * ld + pk] *= il;
+            half_sync(team);
+            const int m = nh - k - 1;
+            for (int idx = t; idx < m * m; idx += 128) {
+                const int ii = idx / m, jj = idx - ii * m;
+                const int pi = perm[k + 1 + ii], pj = perm[k + 1 + jj];
+                A[pi * ld + pj] = fma(-A[pi * ld + pk], A[pj * ld + pk], A[pi * ld + pj]);
+            }
+            half_sync(team);
+            rank = k + 1;
+        }
+        if (t == 0) *rank_s = rank;
+        __syncthreads();
+        const bool ok = rank >= 1 && *rank_other >= 1;
+        if (threadIdx.x == 0 && a.status != nullptr) a.status[e] = ok ? 0 : 1;
+        if (!ok) ++nfail;
+
+        for (int r0 = 0; r0 < R; r0 += 128) {
+            const int r = r0 + t;
+            if (r < R) {
+                const double kf = a.kf ? a.kf[r] : a.k_scalar;
+                const double kk = (kf * 3.14159265358979323846) * (kf * 3.14159265358979323846);
+                double ul = a.u[(long long)r * (a.E + 1) + e], ur = a.u[(long long)r * (a.E + 1) + e + 1];
+                if (a.bc2 != nullptr) {
+                    ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
+                    ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;
+                }
+                const double gpar = team == 0 ? 0.5 * (ul + ur) : 0.5 * (ur - ul);
+                double S = 0.0, C = 0.0;
+                if (a.forcing == HFL_FORCING_SINE) sincospi(kf * (0.5 * (xl + xr)), &S, &C);
+                const double amp = isig * kk * (team == 0 ? S : C);
+                const double tb = kf * h * (0.5 / (double)(N - 1));       // base angle / pi
+                double y[DUAL_NMAX / 2 + 2];
+                for (int k = 0; k < rank; ++k) {
+                    const int pk = perm[k];
+                    double b;
+                    if (pk < NHc) {
+                        if (a.forcing == HFL_FORCING_SINE) {
+                            double sj, cj;
+                            sincospi(tb * (double)(2 * pk + 1), &sj, &cj);
+                            b = amp * (team == 0 ? cj : sj);
+                        } else {
+                            const double fp = a.f[((long long)r * N + NHc + pk) * a.E + e];
+                            const double fm = a.f[((long long)r * N + NHc - 1 - pk) * a.E + e];
+                            b = isig * (team == 0 ? 0.5 * (fp + fm) : 0.5 * (fp - fm));
+                        }
+                    } else {
+                        b = gpar;
+                    }
+                    for (int j = 0; j < k; ++j) b = fma(-A[pk * ld + perm[j]], y[j], b);
+                    y[k] = b * invl[k];
+                }
+                for (int k = rank - 1; k >= 0; --k) {
+                    double b = y[k];
+                    const int pk = perm[k];
+                    for (int j = k + 1; j < rank; ++j) b = fma(-A[perm[j] * ld + pk], y[j], b);
+                    y[k] = b * invl[k];
+                }
+                double* w = wbuf + (size_t)r * M;
+                for (int q = 0; q < MA; ++q) {
+                    double s = 0.0;
+                    for (int k = 0; k < rank; ++k) s = fma(Cp[perm[k] * MA + q], y[k], s);
+                    w[2 * q + team] = ok ? s : (q == 0 ? gpar : 0.0);   // P:171-176 fallback: linear interpolant
+                }
+            }
+            __syncthreads();
+            const int rb = min(128, R - r0);
+            if (a.coef != nullptr)
+                for (int idx = threadIdx.x; idx < rb * M; idx += 256)
+                    a.coef[((long long)(r0 + idx / M) * a.E + e) * M + idx % M] = wbuf[(size_t)(r0 + idx / M) * M + idx % M];
+            if (F > 0 && (a.fine != nullptr || a.want_err)) {
+                const double xc = 0.5 * (xl + xr);
+                for (int idx = threadIdx.x; idx < rb * F; idx += 256) {
+                    const int rr = idx / F, i = idx - rr * F;
+                    const double* w = wbuf + (size_t)(r0 + rr) * M;
+                    double s = 0.0;
+                    for (int mm = M - 1; mm >= 0; --mm) s = fma(w[mm], a.V[i * M + mm], s);
+                    if (a.fine != nullptr) a.fine[((long long)(r0 + rr) * a.E + e) * F + i] = s;
+                    if (a.want_err) {
+                        const double kf = a.kf ? a.kf[r0 + rr] : a.k_scalar;
+                        const double xi = (double)(2 * i - (F - 1)) / (double)(F - 1);
+                        const double d = s - sinpi(kf * fma(0.5 * h, xi, xc));
+                        const double wq = ((i == 0 || i == F - 1) ? 0.5 : 1.0) * h / (double)(F - 1);
+                        atomicAdd(eacc + 2 * (r0 + rr), wq * d * d);
+                        atomic_max_nonneg(eacc + 2 * (r0 + rr) + 1, fabs(d));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (a.err3 != nullptr) {
+        __syncthreads();
+        for (int r = threadIdx.x; r < R; r += 256) {
+            if (a.want_err) {
+                atomicAdd(a.err3 + 3 * r, eacc[2 * r]);
+                atomic_max_nonneg(a.err3 + 3 * r + 1, eacc[2 * r + 1]);
+            }
+            if (nfail) atomicAdd(a.err3 + 3 * r + 2, (double)nfail);
+        }
+    }
+}
+
 int launch_dual_small(const hfl_plan* plan, long long E, const double* d_nodes, const double* d_u, int forcing_kind,
                       double k_freq, const double* d_f, const double* d_bc2, double* d_coef, double* d_fine,
                       int* d_status, double* d_err3, cudaStream_t s);   // hfl_dual_small.cu
@@ -268,6 +469,29 @@ static int launch_dual(const hfl_plan* plan, long long E, int R, const double* d
         const long long cap = (long long)sm_count() * per_sm;
         if (grid > cap) grid = cap;
         dual_kernel<32><<<(unsigned)grid, 128, smem, s>>>(a);
+    } else if (plan->N % 2 == 0 && get_option_dual_team() != 2) {
+        DualParityArgs pa;
+        pa.d = a;
+        pa.nh = plan->N / 2 + 1; pa.ldh = pa.nh | 1;
+        pa.Kp[0] = plan->d_tables + plan->off_Kpe; pa.Kp[1] = plan->d_tables + plan->off_Kpo;
+        pa.Cp[0] = plan->d_tables + plan->off_Cpe; pa.Cp[1] = plan->d_tables + plan->off_Cpo;
+        pa.MA[0] = n_even(plan->M) + 1; pa.MA[1] = n_odd(plan->M) + 1;
+        const size_t td = (size_t)pa.nh * pa.ldh + pa.nh + 8;
+        const size_t tb = ((td * 8 + (size_t)(pa.nh + 2) * 4) + 15) / 16 * 16;
+        const size_t smem = 2 * tb + ((size_t)R * a.M + 2 * (size_t)R) * 8;
+        if (smem > (size_t)max_smem) {
+            set_error("hfl_lssvr_dual: N=%d, R=%d, M=%d need %zu bytes of shared memory per element (limit %d)",
+                      plan->N, R, plan->M, smem, max_smem);
+            return HFL_ERR_UNSUPPORTED;
+        }
+        HFL_CUDA_CHECK(cudaFuncSetAttribute(dual_parity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dual_parity_kernel, 256, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = E;
+        const long long cap = (long long)sm_count() * per_sm;
+        if (grid > cap) grid = cap;
+        dual_parity_kernel<<<(unsigned)grid, 256, smem, s>>>(pa);
     } else {
         if (team_bytes > (size_t)max_smem) {
             set_error("hfl_lssvr_dual: N=%d, R=%d, M=%d need %zu bytes of shared memory per element (limit %d)",

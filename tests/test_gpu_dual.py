@@ -72,17 +72,23 @@ def test_dual_matches_primal_kernel_full_size():
     assert mx <= 1e-10
 
 
-@pytest.mark.parametrize('M', [5, 9, 13, 17, 21, 25])
-def test_large_system_multi_rhs(M):
-    """BASELINE configs[4]: N = 128 (130 x 130 systems), R forcing frequencies sharing one factorisation."""
+@pytest.mark.parametrize('M,team', [(5, 0), (9, 0), (13, 0), (17, 0), (21, 0), (25, 0), (9, 2), (25, 2)])
+def test_large_system_multi_rhs(M, team):
+    """BASELINE configs[4]: N = 128, R forcing frequencies sharing one factorisation.  team = 0: parity-split
+    team kernel (two 65 x 65 blocks); team = 2: full 130 x 130 system kernel."""
     E, N, F, gamma, R = 64, 128, 32, 1e4, 8
+    batch.set_option('dual_team', team)
     nodes = np.linspace(-1, 1, E + 1) * 0.01 + 0.3          # h = 3.1e-4: k h <= 0.02, resolved for every k
     ks = np.array([1.0, 2.0, 5.0, 8.0, 16.0, 32.0, 48.0, 64.0])
     u = np.stack([np.sin(k * np.pi * nodes) for k in ks])
     err3 = torch.zeros((R, 3), dtype=torch.float64, device='cuda')
-    coef, fine, status = batch.lssvr_dual_multi(dev(nodes), dev(u), dev(ks), M, gamma, N=N, F=F, want_fine=True,
-                                                want_status=True, err3=err3)
-    torch.cuda.synchronize()
+    try:
+        coef, fine, status = batch.lssvr_dual_multi(dev(nodes), dev(u), dev(ks), M, gamma, N=N, F=F, want_fine=True,
+                                                    want_status=True, err3=err3)
+        torch.cuda.synchronize()
+    finally:
+        batch.set_option('dual_team', 0)
+    assert rel(kkt.evaluate_fine(coef[3].cpu().numpy(), F), fine[3].cpu().numpy()) <= 1e-13     # coef and fine agree
     assert not status.cpu().numpy().any()
     for r, k in enumerate(ks):
         ref = oracle_coef(nodes, u[r], M, gamma, N, k=k)
