@@ -612,13 +612,7 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
     if (dtp) dt = *dtp; else memset(&dt, 0, sizeof(dt));
     const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) +
                         (NHD > 0 ? (size_t)2 * (NHD + 1) * kThreads : (size_t)a.NH * (ME + MO)) * sizeof(double);
-    static thread_local const void* configured = nullptr;
-    static thread_local size_t configured_smem = 0;
-    if (configured != (const void*)kern || configured_smem < smem) {
-        HFL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = (const void*)kern;
-        configured_smem = smem;
-    }
+    HFL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     if (per_sm < 1) per_sm = 1;

@@ -410,13 +410,11 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
         double* wsrows = utop + nt;
         double* yvw = wsrows + 6 * (size_t)nt;
         const size_t smem0 = (size_t)SM_TOTAL * sizeof(double);
-        static thread_local bool configured = false;
-        if (!configured) {
+        {   // per device and cheap: set on every call (the function attributes do not carry over between devices)
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(14 * TOPT * sizeof(double))));
-            configured = true;
         }
         fem_reduce_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
         const int S = (int)((nt + TOPT - 1) / TOPT);

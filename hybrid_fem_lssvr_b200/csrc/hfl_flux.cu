@@ -143,11 +143,9 @@ int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes
         return HFL_ERR_ARG;
     }
     const size_t smem = (size_t)FLUX_SMEM * sizeof(double);
-    static thread_local bool configured = false;
-    if (!configured) {
+    {
         HFL_CUDA_CHECK(cudaFuncSetAttribute(flux_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HFL_CUDA_CHECK(cudaFuncSetAttribute(flux_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     const int S = (int)((nt + TOPT - 1) / TOPT);
     flux_tile_kernel<<<(unsigned)nt, FT, smem, s>>>(a, agg3);
