@@ -98,6 +98,7 @@ def run_cpu_baseline_c(sample, steps=1):
     import numpy as np
     from oracle import c_port
     c_port.load()
+    c_port.set_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1 for its workers
     cores = c_port.threads()
     nodes = np.linspace(-1.0, 1.0, min(sample, 20000) + 1)
     c_port.primal_batch(nodes, c_port.fem_p1(nodes, KFREQ), M, GAMMA, N=NCOL, k_freq=KFREQ, F=F, want_coef=False)

@@ -35,6 +35,15 @@ int oracle_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline must use all host threads it can. */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* Coarse P1 solve: nodes[n] -> u[n], forcing (k pi)^2 sin(k pi x), u = 0 at both ends. */
 int oracle_fem_p1(long n, const double* nodes, double kf, double* u) {
     const double pi = 3.14159265358979323846, kpi = kf * pi, kp2 = kpi * kpi;

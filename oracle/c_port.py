@@ -19,6 +19,7 @@ def load(build=True):
     lib = C.CDLL(LIB)
     dp = np.ctypeslib.ndpointer(dtype=np.float64, flags='C_CONTIGUOUS')
     lib.oracle_threads.restype = C.c_int
+    lib.oracle_set_threads.argtypes = [C.c_int]
     lib.oracle_fem_p1.restype = C.c_int
     lib.oracle_fem_p1.argtypes = [C.c_long, dp, C.c_double, dp]
     lib.oracle_primal_batch.restype = C.c_double
@@ -30,6 +31,10 @@ def load(build=True):
 
 def threads():
     return int(load().oracle_threads())
+
+
+def set_threads(n):
+    load().oracle_set_threads(int(n))
 
 
 def fem_p1(nodes, k_freq=1.0):
