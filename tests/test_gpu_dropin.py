@@ -74,3 +74,26 @@ def test_custom_rhs_and_flux_solver():
     assert np.max(np.abs(s1.evaluate_solution(xs) - s2.evaluate_solution(xs))) <= 1e-10
     ref = fem_p1.solve_fem_p1(np.linspace(-1, 1, 41))
     assert np.max(np.abs(s1.fem_values - ref)) <= 1e-12
+
+
+def test_dual_form_through_the_class():
+    """The 'Dual' script's entry points (D:100-203 are P:107-211): same class, form='dual'."""
+    xs = np.linspace(-1, 1, 201)
+    a = FEMLSSVRPrimalSolver(25, lssvr_M=8, lssvr_gamma=1e4)
+    a.solve()
+    b = FEMLSSVRPrimalSolver(25, lssvr_M=8, lssvr_gamma=1e4, form='dual')
+    b.solve()
+    assert np.max(np.abs(a.evaluate_solution(xs) - b.evaluate_solution(xs))) <= 1e-10
+    assert not b.element_status.any()
+
+
+def test_empty_and_single_element_batches():
+    nodes = dev(np.array([0.25]))
+    u = dev(np.array([0.5]))
+    coef, fine, status = batch.lssvr_primal_batch(nodes, u, 9, 1e4, N=12, F=32, want_fine=True, want_status=True)
+    assert coef.shape == (0, 9) and fine.shape == (0, 32) and status.shape == (0,)
+    coef, fine, status = batch.lssvr_dual_batch(nodes, u, 9, 1e4, N=12, F=32, want_fine=True, want_status=True)
+    assert coef.shape == (0, 9)
+    s = FEMLSSVRPrimalSolver(2, lssvr_M=5, lssvr_gamma=1e2)      # one element, both ends Dirichlet
+    s.solve()
+    assert len(s.lssvr_functions) == 1 and abs(s.evaluate_solution(np.array([-1.0]))[0]) <= 1e-12
