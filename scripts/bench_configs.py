@@ -65,6 +65,44 @@ def config1():
                           'fine_l2_vs_sin': l2, 'fine_max_vs_sin': mx}))
 
 
+def config2_variants(E=10 ** 7):
+    """the headline shape on a non-uniform mesh and with random data, where nothing could be hoisted
+    across elements even in principle (the kernel never hoists: same launch, same code path)."""
+    M, N, F = 9, 12, 32
+    fine = torch.empty((E, F), dtype=torch.float64, device='cuda')
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    # (a) uniform mesh, device forcing (the bench.py workload)
+    nodes = batch.mesh_linspace(-1.0, 1.0, E + 1)
+    u = torch.sin(np.pi * nodes)
+    ms = t_ms(lambda: batch.lssvr_primal_batch(nodes, u, M, 1e4, N=N, F=F, want_coef=False, want_fine=True, fine_out=fine))
+    print(json.dumps({'config': 2, 'variant': 'uniform mesh, sine forcing on device', 'K2K3_ms': ms,
+                      'element_solves_per_s': E / (ms * 1e-3), 'GBps_algorithmic_272B': 272 * E / (ms * 1e-3) / 1e9}))
+    # (b) jittered mesh: widths (2/E)(1 + 0.5 U(-1,1)), renormalised
+    w = 1.0 + 0.5 * (2.0 * torch.rand(E, dtype=torch.float64, device='cuda', generator=gen) - 1.0)
+    x = torch.cat([torch.zeros(1, dtype=torch.float64, device='cuda'), torch.cumsum(w, 0)])
+    nodes_j = (-1.0 + 2.0 * x / x[-1]).contiguous()
+    u_j = torch.sin(np.pi * nodes_j)
+    ms = t_ms(lambda: batch.lssvr_primal_batch(nodes_j, u_j, M, 1e4, N=N, F=F, want_coef=False, want_fine=True, fine_out=fine))
+    err = batch.new_error_accumulator()
+    batch.lssvr_primal_batch(nodes_j, u_j, M, 1e4, N=N, F=F, want_coef=False, want_fine=True, fine_out=fine, err3=err)
+    l2, mx = batch.finish_error(err)
+    print(json.dumps({'config': 2, 'variant': 'non-uniform (jittered) mesh, sine forcing on device', 'K2K3_ms': ms,
+                      'element_solves_per_s': E / (ms * 1e-3), 'GBps_algorithmic_272B': 272 * E / (ms * 1e-3) / 1e9,
+                      'fine_max_vs_sin': mx}))
+    # (c) random data: u ~ U(-1,1), f ~ N(0,1) streamed as samples [N][E] (+96 B/element)
+    u_r = 2.0 * torch.rand(E + 1, dtype=torch.float64, device='cuda', generator=gen) - 1.0
+    f_r = torch.randn((N, E), dtype=torch.float64, device='cuda', generator=gen)
+    ms = t_ms(lambda: batch.lssvr_primal_batch(nodes_j, u_r, M, 1e4, N=N, F=F, forcing=f_r, want_coef=False, want_fine=True,
+                                               fine_out=fine))
+    idx = torch.arange(0, 200, device='cuda')
+    ref = kkt.evaluate_fine(kkt.lssvr_primal_kkt_batch(nodes_j[:201].cpu().numpy(), u_r[:201].cpu().numpy(),
+                                                        f_r[:, :200].cpu().numpy().T.copy(), M, 1e4), F)
+    worst = float(np.max(np.abs(fine[idx].cpu().numpy() - ref)) / np.max(np.abs(ref)))
+    print(json.dumps({'config': 2, 'variant': 'jittered mesh, random nodal data, random forcing samples', 'K2K3_ms': ms,
+                      'element_solves_per_s': E / (ms * 1e-3), 'GBps_algorithmic_368B': 368 * E / (ms * 1e-3) / 1e9,
+                      'max_rel_diff_vs_oracle_sample': worst}))
+
+
 def config4(E=10 ** 4, R=64):
     nodes = batch.mesh_linspace(-1.0, 1.0, E + 1)
     ks = torch.arange(1, R + 1, dtype=torch.float64, device='cuda')
@@ -92,10 +130,12 @@ def config4(E=10 ** 4, R=64):
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['0', '1', '4']
+    which = sys.argv[1:] or ['0', '1', '2', '4']
     if '0' in which:
         config0()
     if '1' in which:
         config1()
+    if '2' in which:
+        config2_variants()
     if '4' in which:
         config4()
