@@ -44,6 +44,7 @@ SIGNATURES = {
     'hfl_set_option': (_i32, [C.c_char_p, _i32]),
     'hfl_get_option': (_i32, [C.c_char_p, C.POINTER(_i32)]),
     'hfl_launch_count': (_i64, []),
+    'hfl_store_probe': (_i32, [_i32, _i32, _i64, _i32, _i32, _vp, _vp]),
     'hfl_fp64_probe': (_i32, [_i32, _i32, _vp, C.POINTER(_f64), _vp]),
 }
 

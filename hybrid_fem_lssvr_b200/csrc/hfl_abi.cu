@@ -297,3 +297,31 @@ extern "C" int hfl_fp64_probe(int blocks, int iters, double* d_out, double* flop
     if (flops) *flops = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
     return HFL_OK;
 }
+
+// ---- store-path probe (profiling aid): writes n distinct doubles with a configurable launch shape.
+// pattern 0: grid-stride, consecutive threads write consecutive doubles (a plain stream);
+// pattern 1: like the element kernel - each CTA writes contiguous tiles of `tile` doubles (thread t writes a
+//            16-byte chunk per step, warp = 512 contiguous bytes), tiles visited blockIdx + i * gridDim.
+__global__ void store_probe_kernel(long long n, int pattern, int tile, double* __restrict__ out) {
+    if (pattern == 0) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            out[i] = (double)i * 1e-9;
+    } else {
+        const long long ntile = n / tile;
+        for (long long tb = blockIdx.x; tb < ntile; tb += gridDim.x) {
+            double2* o = reinterpret_cast<double2*>(out + tb * tile);
+            for (int j = threadIdx.x; j < tile / 2; j += blockDim.x) {
+                const double v = (double)(tb * tile + 2 * j) * 1e-9;
+                o[j] = make_double2(v, v + 1e-9);
+            }
+        }
+    }
+}
+
+extern "C" int hfl_store_probe(int blocks, int threads, int64_t n, int pattern, int tile, double* d_out, void* stream) {
+    HFL_REQUIRE(blocks > 0 && threads > 0 && n > 0 && d_out != nullptr && tile > 0 && tile % 2 == 0, "hfl_store_probe: bad arguments");
+    store_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(n, pattern, tile, d_out);
+    count_launch();
+    HFL_CUDA_CHECK(cudaGetLastError());
+    return HFL_OK;
+}

@@ -148,6 +148,9 @@ int64_t hfl_launch_count(void);                    /* kernels launched by this l
 /* FP64 FMA throughput probe: launches `blocks` CTAs of 256 threads, 16 independent DFMA chains of
  * length `iters` each; *flops receives the flop count so the caller can time it with CUDA events. */
 int hfl_fp64_probe(int blocks, int iters, double* d_out, double* flops, void* stream);
+/* Store-path probe: n distinct doubles written with a given launch shape; pattern 0 = plain stream, 1 = contiguous
+ * per-CTA tiles of `tile` doubles visited like the element kernel does. */
+int hfl_store_probe(int blocks, int threads, int64_t n, int pattern, int tile, double* d_out, void* stream);
 
 #ifdef __cplusplus
 }

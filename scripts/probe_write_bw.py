@@ -23,3 +23,9 @@ ms = t(lambda: buf.copy_(src))
 print('torch copy_ (read 2.56 + write 2.56 GB)           : %.4f ms  %.0f GB/s' % (ms, 16 * n / ms / 1e6))
 ms = t(lambda: torch.add(src, 1.0, out=buf))
 print('torch add scalar (read + write)                   : %.4f ms  %.0f GB/s' % (ms, 16 * n / ms / 1e6))
+
+for blocks, threads, pattern, tile in ((148 * 16, 256, 0, 2), (148 * 8, 256, 0, 2), (148 * 4, 128, 0, 2), (148 * 4, 128, 1, 4096),
+                                       (148 * 3, 128, 1, 4096), (148 * 8, 128, 1, 4096), (148 * 16, 128, 1, 4096),
+                                       (148 * 4, 256, 1, 4096), (148 * 4, 128, 1, 1024), (148 * 4, 128, 1, 32768)):
+    ms = t(lambda: batch._lib.check(lib.hfl_store_probe(blocks, threads, n, pattern, tile, batch._ptr(buf), batch._stream()), 'probe'))
+    print('store probe blocks=%5d threads=%3d pattern=%d tile=%6d doubles: %.4f ms  %.0f GB/s' % (blocks, threads, pattern, tile, ms, 8 * n / ms / 1e6))
