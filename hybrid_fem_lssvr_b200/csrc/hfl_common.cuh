@@ -15,7 +15,6 @@ void count_launch(int n = 1);
 int get_option_store();
 int get_option_debug();
 int get_option_dual_team();
-int get_option_nbuf();
 int sm_count();
 
 #define HFL_CUDA_CHECK(expr)                                                            \

@@ -20,7 +20,6 @@ struct PrimalArgs {
     const double* Do;      // [NH][MO]
     int N, NH, F;
     int forcing;
-    int nbuf;              // TMA staging buffers per CTA: 2 lets the bulk store of tile i drain during all of tile i+1
     int debug;             // 0 normal; 1 = skip the TMA issue (compute only); 2 = skip the solve (stores only).  Profiling aid.
     double k_freq;
     double kk;             // (k pi)^2
@@ -125,8 +124,7 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
     constexpr int F = 2 * FH;
     constexpr int TILE = tile_bytes<STORE>(F);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int nbuf = (STORE == STORE_TMA) ? a.nbuf : 1;      // TMA staging buffers per CTA (1 or 2)
-    double* sDe = reinterpret_cast<double*>(smem_raw + nbuf * kWarps * TILE);
+    double* sDe = reinterpret_cast<double*>(smem_raw + kWarps * TILE);
     double* sDo = sDe + a.NH * ME;
     if (NHD == 0) {
         for (int i = threadIdx.x; i < a.NH * ME; i += kThreads) sDe[i] = a.De[i];
@@ -157,7 +155,6 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
     double acc_sq = 0.0, acc_mx = 0.0;
     int nfail = 0;
     bool store_pending = false;
-    int it = 0;                                              // tile counter of this CTA (TMA buffer parity)
 
     // CTA tile = kThreads consecutive elements (one per thread); warp w owns rows 32 w .. 32 w + 31 of it.
     // The loop bounds depend on blockIdx only, so the CTA-wide barriers of the TMA path are uniform.
@@ -429,18 +426,13 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
             }
             const bool st = (a.fine != nullptr);
             if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && st && store_pending) {
-                // the staging buffer is free once the issuing thread has seen the bulk store that used it read it
-                // (with two buffers that is the store before last: one group may stay in flight)
-                if (threadIdx.x == 0) {
-                    if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
+                // the CTA buffer is free once the issuing thread has seen its last bulk store read it
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncthreads();
-                store_pending = (nbuf == 2);
+                store_pending = false;
             }
-            const uint32_t buf_off = (STORE == STORE_TMA && nbuf == 2 && (it & 1)) ? (uint32_t)(kWarps * TILE) : 0u;
             // TMA layout: F/16 boxes of [kThreads rows][128 B], row = thread, 16-byte chunks XOR-swizzled by row & 7
-            const uint32_t row_tma = smem_u32(smem_raw) + buf_off + threadIdx.x * 128, sw = (uint32_t)(lane & 7) << 4;
+            const uint32_t row_tma = smem_u32(smem_raw) + threadIdx.x * 128, sw = (uint32_t)(lane & 7) << 4;
             const uint32_t row_sm = tile_s + lane * ((F + 2) * 8);
             double2* row_g = reinterpret_cast<double2*>(a.fine + e * F);
 #pragma unroll
@@ -527,7 +519,7 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
                 __syncthreads();
                 if (threadIdx.x == 0 && a.debug != 1) {   // one bulk tensor store per box for the whole CTA tile; operands are CTA-uniform
                     const int row0 = (int)(ct * kThreads);
-                    const uint32_t buf = smem_u32(smem_raw) + buf_off;
+                    const uint32_t buf = smem_u32(smem_raw);
 #pragma unroll
                     for (int b = 0; b < F / 16; ++b) {
                         asm volatile(
@@ -539,7 +531,6 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 store_pending = true;
-                ++it;
             }
         }
     }
@@ -619,8 +610,7 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
     auto kern = lssvr_element_kernel<M, FH, ERR, STORE, NHD>;
     DualSmallTables<M, NHD> dt;
     if (dtp) dt = *dtp; else memset(&dt, 0, sizeof(dt));
-    const int nbuf = (STORE == STORE_TMA) ? a.nbuf : 1;
-    const size_t smem = (size_t)nbuf * kWarps * tile_bytes<STORE>(F) +
+    const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) +
                         (NHD > 0 ? (size_t)2 * (NHD + 1) * kThreads : (size_t)a.NH * (ME + MO)) * sizeof(double);
     HFL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -227,7 +227,7 @@ extern "C" int hfl_lssvr_primal_batch(const hfl_plan_t* plan, int64_t E, const d
     a.E = E; a.nodes = d_nodes; a.u = d_u; a.f = d_f_samples; a.bc2 = d_bc2;
     a.coef = d_coef; a.fine = d_fine; a.status = d_status; a.err3 = d_err3;
     a.De = plan->d_tables + plan->off_De; a.Do = plan->d_tables + plan->off_Do;
-    a.N = plan->N; a.NH = plan->NH; a.F = plan->F; a.forcing = forcing_kind; a.debug = get_option_debug(); a.nbuf = get_option_nbuf();
+    a.N = plan->N; a.NH = plan->NH; a.F = plan->F; a.forcing = forcing_kind; a.debug = get_option_debug();
     a.k_freq = k_freq; a.kk = (k_freq * pi) * (k_freq * pi);
     a.c_tau = 1.0 / (16.0 * plan->gamma);
     a.cN = 0.5 / (double)(plan->N - 1);

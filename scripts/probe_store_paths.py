@@ -20,10 +20,3 @@ for store in (1, 2, 3, 4, 5):
         row.append(t(lambda: batch.lssvr_primal_batch(nodes, u, 9, 1e4, N=12, F=32, want_coef=False, want_fine=True, fine_out=fine)))
     print('store %d: full %.4f ms, solve off %.4f ms' % (store, row[0], row[1]))
 batch.set_option('primal_debug', 0); batch.set_option('primal_store', 0)
-err3 = batch.new_error_accumulator()
-for nb in (1, 2):
-    batch.set_option('tma_buffers', nb)
-    a = t(lambda: batch.lssvr_primal_batch(nodes, u, 9, 1e4, N=12, F=32, want_coef=False, want_fine=True, fine_out=fine))
-    b = t(lambda: batch.lssvr_primal_batch(nodes, u, 9, 1e4, N=12, F=32, want_coef=False, want_fine=True, fine_out=fine, err3=err3))
-    print('tma_buffers %d: plain %.4f ms, fused error %.4f ms' % (nb, a, b))
-batch.set_option('tma_buffers', 1)
