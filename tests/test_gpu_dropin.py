@@ -97,3 +97,22 @@ def test_empty_and_single_element_batches():
     s = FEMLSSVRPrimalSolver(2, lssvr_M=5, lssvr_gamma=1e2)      # one element, both ends Dirichlet
     s.solve()
     assert len(s.lssvr_functions) == 1 and abs(s.evaluate_solution(np.array([-1.0]))[0]) <= 1e-12
+
+
+def test_host_pipeline_matches_device_path():
+    """The host-buffer pipeline of bench.py's e2e leg (pinned host in, chunked D2H out) against one device-resident launch."""
+    from hybrid_fem_lssvr_b200 import host_api
+    E = 10007
+    pipe = host_api.HostPipeline(E, 9, 1e4, N=12, F=32, chunks=3)
+    nodes_h = pipe.pinned_nodes()
+    nodes_h.copy_(torch.from_numpy(np.linspace(-1.0, 1.0, E + 1)))
+    fine_h, u_h, (l2, mx) = pipe.run(nodes_h)
+    nodes = nodes_h.cuda()
+    u = batch.fem_p1_solve(nodes)
+    err = batch.new_error_accumulator()
+    _, fine, _ = batch.lssvr_primal_batch(nodes, u, 9, 1e4, N=12, F=32, want_coef=False, want_fine=True, err3=err)
+    assert torch.equal(u.cpu(), u_h)
+    assert torch.equal(fine.cpu(), fine_h)
+    l2d, mxd = batch.finish_error(err)
+    assert abs(l2 - l2d) <= 1e-9 * l2d and mx == mxd
+    assert pipe.d2h_bytes == 8 * E * 32 + 8 * (E + 1) + 24 and pipe.h2d_bytes == 8 * (E + 1)
