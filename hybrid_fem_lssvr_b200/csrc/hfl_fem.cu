@@ -19,53 +19,60 @@
 namespace hfl {
 
 // Interior of a chunk (rows m0+1 .. m0+S-1): first / last entries of the three partial solutions
-// x = y - u_head v - u_next w.   out = {y1, v1, w1, ys, vs, ws}.
+// x = y - u_head v - u_next w and the "leaks" e = 1 + v + w, all formed without cancellation.
+// out = {y1, v1, w1, e1, ys, vs, ws, es}.
 template <class Rows>
-__device__ __forceinline__ void chunk_reduce(const Rows& rows, int m0, int S, double (&out)[6]) {
+__device__ __forceinline__ void chunk_reduce(const Rows& rows, int m0, int S, double (&out)[8]) {
     if (S < 2) {   // no interior: neighbouring heads couple directly (x_first = u_next, x_last = u_head)
-        out[0] = 0.0; out[1] = 0.0; out[2] = -1.0;
-        out[3] = 0.0; out[4] = -1.0; out[5] = 0.0;
+        out[0] = 0.0; out[1] = 0.0; out[2] = -1.0; out[3] = 0.0;
+        out[4] = 0.0; out[5] = -1.0; out[6] = 0.0; out[7] = 0.0;
         return;
     }
-    double l, d, r, b;
-    rows.get(m0 + 1, l, d, r, b);
-    double dp = d, bp = b, vp = l, rp = r;
+    double l, sg, r, b;
+    // forward: transformed row i has entries (head: v, i: d, i+1: r); tp = v + d + r is its row sum
+    rows.get(m0 + 1, l, sg, r, b);
+    double tp = sg, vp = l, rp = r, bp = b;
+    double dp = tp - vp - rp;
     for (int i = 2; i < S; ++i) {
-        rows.get(m0 + i, l, d, r, b);
-        const double m = l * fast_rcp(dp);
-        dp = d - m * rp;
-        bp = b - m * bp;
+        rows.get(m0 + i, l, sg, r, b);
+        const double m = l * fast_rcp(dp);        // <= 0
+        tp = fma(-m, tp, sg);
         vp = -m * vp;
+        bp = fma(-m, bp, b);
         rp = r;
+        dp = tp - vp - rp;
     }
     double inv = fast_rcp(dp);
-    out[3] = bp * inv; out[4] = vp * inv; out[5] = rp * inv;
-    rows.get(m0 + S - 1, l, d, r, b);
-    dp = d; bp = b;
+    out[4] = bp * inv; out[5] = vp * inv; out[6] = rp * inv; out[7] = tp * inv;
+    // backward: entries (i-1: l, i: d, next head: w)
+    rows.get(m0 + S - 1, l, sg, r, b);
+    tp = sg; bp = b;
     double wp = r, lp = l;
+    dp = tp - lp - wp;
     for (int i = S - 2; i >= 1; --i) {
-        rows.get(m0 + i, l, d, r, b);
+        rows.get(m0 + i, l, sg, r, b);
         const double m = r * fast_rcp(dp);
-        dp = d - m * lp;
-        bp = b - m * bp;
+        tp = fma(-m, tp, sg);
         wp = -m * wp;
+        bp = fma(-m, bp, b);
         lp = l;
+        dp = tp - lp - wp;
     }
     inv = fast_rcp(dp);
-    out[0] = bp * inv; out[1] = lp * inv; out[2] = wp * inv;
+    out[0] = bp * inv; out[1] = lp * inv; out[2] = wp * inv; out[3] = tp * inv;
 }
 
-// Parallel cyclic reduction over equations first..last (one per thread, index = thread id), NR
-// right-hand sides.  sm holds 2 * (3 + NR) * T doubles.  Every thread of the CTA must call this.
+// Parallel cyclic reduction over equations first..last (one per thread, index = thread id), NR right-hand
+// sides, rows as (l, sigma, r).  sm holds 2 * (3 + NR) * T doubles.  Every thread of the CTA must call this.
 template <int NR, int T>
-__device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last, double l, double d, double r,
+__device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last, double l, double sg, double r,
                                           double (&rhs)[NR], double (&x)[NR]) {
     constexpr int W = 3 + NR;
     int cur = 0;
     const bool active = (t >= first && t <= last);
     {
         double* bufw = sm + cur * W * T;
-        bufw[0 * T + t] = l; bufw[1 * T + t] = d; bufw[2 * T + t] = r;
+        bufw[0 * T + t] = l; bufw[1 * T + t] = sg; bufw[2 * T + t] = r;
 #pragma unroll
         for (int q = 0; q < NR; ++q) bufw[(3 + q) * T + t] = rhs[q];
     }
@@ -76,90 +83,101 @@ __device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last
         double* bufw = sm + (cur ^ 1) * W * T;
         if (active) {
             const int im = t - delta, ip = t + delta;
-            double dn = d, ln = 0.0, rn = 0.0;
+            double sn = sg, ln = 0.0, rn = 0.0;
             if (im >= first) {
-                const double al = -l * fast_rcp(bufr[1 * T + im]);
-                dn = fma(al, bufr[2 * T + im], dn);
-                ln = al * bufr[0 * T + im];
+                const double lm = bufr[0 * T + im], sm_ = bufr[1 * T + im], rm = bufr[2 * T + im];
+                const double al = -l * fast_rcp(sm_ - lm - rm);      // >= 0
+                sn = fma(al, sm_, sn);
+                ln = al * lm;
 #pragma unroll
                 for (int q = 0; q < NR; ++q) rhs[q] = fma(al, bufr[(3 + q) * T + im], rhs[q]);
+            } else {
+                sn -= l;          // no such neighbour: l is 0 here by construction
             }
             if (ip <= last) {
-                const double be = -r * fast_rcp(bufr[1 * T + ip]);
-                dn = fma(be, bufr[0 * T + ip], dn);
-                rn = be * bufr[2 * T + ip];
+                const double lq = bufr[0 * T + ip], sq = bufr[1 * T + ip], rq = bufr[2 * T + ip];
+                const double be = -r * fast_rcp(sq - lq - rq);
+                sn = fma(be, sq, sn);
+                rn = be * rq;
 #pragma unroll
                 for (int q = 0; q < NR; ++q) rhs[q] = fma(be, bufr[(3 + q) * T + ip], rhs[q]);
+            } else {
+                sn -= r;
             }
-            l = ln; d = dn; r = rn;
+            l = ln; sg = sn; r = rn;
         }
-        bufw[0 * T + t] = l; bufw[1 * T + t] = d; bufw[2 * T + t] = r;
+        bufw[0 * T + t] = l; bufw[1 * T + t] = sg; bufw[2 * T + t] = r;
 #pragma unroll
         for (int q = 0; q < NR; ++q) bufw[(3 + q) * T + t] = rhs[q];
         __syncthreads();
         cur ^= 1;
     }
-    const double inv = fast_rcp(d);
+    const double inv = fast_rcp(sg - l - r);
 #pragma unroll
     for (int q = 0; q < NR; ++q) x[q] = rhs[q] * inv;
 }
 
-// Reduced equation of chunk head t (1 <= t <= T-1) from its own row, the previous chunk's
-// {ys, vs, ws} and its own {y1, v1, w1}.
-__device__ __forceinline__ void head_equation(double lp, double dp, double rp, double bp, double ys_prev,
-                                              double vs_prev, double ws_prev, const double (&six)[6], double& l,
-                                              double& d, double& r, double& b) {
-    l = -lp * vs_prev;
-    d = dp - lp * ws_prev - rp * six[1];
-    r = -rp * six[2];
-    b = bp - lp * ys_prev - rp * six[0];
+// Reduced equation of a chunk head from its own row (lp, sp, rp, bp), the previous chunk's {ys, vs, ws, es} and
+// its own {y1, v1, w1, e1}: couplings L, R to the neighbouring heads, row sum S, right-hand side B.
+__device__ __forceinline__ void head_equation(double lp, double sp, double rp, double bp, double ys_prev,
+                                              double vs_prev, double es_prev, const double (&e8)[8], double& L,
+                                              double& S, double& R, double& B) {
+    L = -lp * vs_prev;
+    R = -rp * e8[2];
+    S = fma(-rp, e8[3], fma(-lp, es_prev, sp));
+    B = fma(-rp, e8[0], fma(-lp, ys_prev, bp));
 }
 
-// Level 0, pass 1: one record per tile = {l, d, r, b of the tile head, y1, v1, w1, ys, vs, ws of the tile interior}.
+// Level 0, pass 1: one record per tile = {l, sigma, r, b of the tile head, y1, v1, w1, e1, ys, vs, ws, es of the interior}.
 template <bool SPECIAL>
 __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __restrict__ rec, double* __restrict__ yvw,
                                                 double* sm) {
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
     MeshRows<SPECIAL> rows{sm + SM_K, sm + SM_B, P, a.n, a.uL, a.uR};
-    double six[6];
-    chunk_reduce(rows, t * FS, FS, six);
-    double lp, dp, rp, bp;
-    rows.get(t * FS, lp, dp, rp, bp);
+    double e8[8];
+    chunk_reduce(rows, t * FS, FS, e8);
+    double lp, sp, rp, bp;
+    rows.get(t * FS, lp, sp, rp, bp);
     __syncthreads();                 // the element arrays are dead from here: exchange / PCR buffers alias them
     double* ex = sm + SM_EX;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) ex[i * FT + t] = six[i];
+    ex[0 * FT + t] = e8[4]; ex[1 * FT + t] = e8[5]; ex[2 * FT + t] = e8[7];     // ys, vs, es of this chunk
     __syncthreads();
-    double l = 0.0, d = 1.0, r = 0.0, rhs[3] = {0.0, 0.0, 0.0}, x[3];
+    double l = 0.0, sg = 1.0, r = 0.0, rhs[4] = {0.0, 0.0, 0.0, 0.0}, x[4];
     if (t >= 1) {
-        double b;
-        head_equation(lp, dp, rp, bp, ex[3 * FT + t - 1], ex[4 * FT + t - 1], ex[5 * FT + t - 1], six, l, d, r, b);
-        rhs[0] = b;
-        if (t == 1) { rhs[1] = l; l = 0.0; }
-        if (t == FT - 1) { rhs[2] = r; r = 0.0; }
+        double B;
+        head_equation(lp, sp, rp, bp, ex[0 * FT + t - 1], ex[1 * FT + t - 1], ex[2 * FT + t - 1], e8, l, sg, r, B);
+        rhs[0] = B;
+        rhs[3] = sg;                                       // T (1 + V + W) = full row sums  ->  E = 1 + V + W
+        if (t == 1) { rhs[1] = l; sg -= l; l = 0.0; }      // coupling to the tile head moves to the right-hand side
+        if (t == FT - 1) { rhs[2] = r; sg -= r; r = 0.0; } // ... and the one to the next tile's head
     }
-    pcr_solve<3, FT>(sm + SM_PCR, t, 1, FT - 1, l, d, r, rhs, x);
+    __syncthreads();                 // ex is consumed; the PCR buffers alias it
+    pcr_solve<4, FT>(sm + SM_PCR, t, 1, FT - 1, l, sg, r, rhs, x);
     {   // chunk-head partial solutions, read back by the back-substitution pass
         double* o = yvw + (size_t)blockIdx.x * 3 * FT;
         o[t] = x[0]; o[FT + t] = x[1]; o[2 * FT + t] = x[2];
     }
-    // x = {Y, V, W} of head t.  The tile's first interior node belongs to chunk 0 (it needs head 1's
-    // solution), its last interior node to chunk T-1.  ex[0 .. 3 FT) is dead by now (pcr_solve synchronised).
-    if (t == 1) { ex[0] = x[0]; ex[1] = x[1]; ex[2] = x[2]; }
+    // x = {Y, V, W, E} of head t.  The tile's first interior node belongs to chunk 0 (it needs head 1's
+    // solution), its last interior node to chunk T-1.
+    __syncthreads();
+    double* xb = sm;                 // 4 doubles: head 1's solution for thread 0
+    if (t == 1) { xb[0] = x[0]; xb[1] = x[1]; xb[2] = x[2]; xb[3] = x[3]; }
     __syncthreads();
     double* out = rec + (long long)blockIdx.x * REC;
     if (t == 0) {
-        const double Y1 = ex[0], V1 = ex[1], W1 = ex[2];
-        out[0] = lp; out[1] = dp; out[2] = rp; out[3] = bp;
-        out[4] = six[0] - six[2] * Y1;
-        out[5] = six[1] - six[2] * V1;
-        out[6] = -six[2] * W1;
+        const double Y1 = xb[0], V1 = xb[1], W1 = xb[2], E1 = xb[3];
+        out[0] = lp; out[1] = sp; out[2] = rp; out[3] = bp;
+        out[4] = fma(-e8[2], Y1, e8[0]);
+        out[5] = fma(-e8[2], V1, e8[1]);
+        out[6] = -e8[2] * W1;
+        out[7] = fma(-e8[2], E1, e8[3]);
     }
     if (t == FT - 1) {
-        out[7] = six[3] - six[4] * x[0];
-        out[8] = -six[4] * x[1];
-        out[9] = six[5] - six[4] * x[2];
+        out[8] = fma(-e8[5], x[0], e8[4]);
+        out[9] = -e8[5] * x[1];
+        out[10] = fma(-e8[5], x[2], e8[6]);
+        out[11] = fma(-e8[5], x[3], e8[7]);
     }
 }
 
@@ -172,50 +190,59 @@ __global__ void __launch_bounds__(FT, 4) fem_reduce_kernel(const FemArgs a, doub
     else fem_reduce_body<false>(a, rec, yvw, sm);
 }
 
+// Thomas elimination of a chunk interior between two known head values, in (l, sigma, r) form: s = row sum over
+// the not-yet-eliminated columns, d = s - r.  One forward step; q carries s / d of the previous row.
+__device__ __forceinline__ void thomas_step(double l, double sg, double r, double b, double& q, double& cprev,
+                                            double& bprev) {
+    const double s = fma(-l, q, sg);      // sg - l on the first row (q = 1), sg - l * (s'/d')_{i-1} afterwards
+    const double inv = fast_rcp(s - r);
+    bprev = fma(-l, bprev, b) * inv;
+    cprev = r * inv;
+    q = s * inv;
+}
+
 // Top level: solve the system of tile heads.  One CTA of TOPT threads, chunk of S heads per thread.
-// ws: rows l, d, r, b [4][cnt] followed by Thomas scratch c', b' [2][cnt].
+// ws: rows l, sigma, r, b [4][cnt] followed by Thomas scratch c', b' [2][cnt].
 __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict__ rec, int cnt, int S,
                                                        double* __restrict__ wsrows, double* __restrict__ utop) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
-    double* rl = wsrows; double* rd = wsrows + cnt; double* rr = wsrows + 2 * (size_t)cnt; double* rb = wsrows + 3 * (size_t)cnt;
+    double* rl = wsrows; double* rs = wsrows + cnt; double* rr = wsrows + 2 * (size_t)cnt; double* rb = wsrows + 3 * (size_t)cnt;
     double* tc = wsrows + 4 * (size_t)cnt; double* tb = wsrows + 5 * (size_t)cnt;
     for (int c = t; c < cnt; c += TOPT) {
         const double* rc = rec + (size_t)c * REC;
-        double l = 0.0, d = rc[1], r, b = rc[3];
+        double l = 0.0, sg = rc[1], b = rc[3];
         if (c > 0) {
             const double* rp = rec + (size_t)(c - 1) * REC;
-            l = -rc[0] * rp[8];
-            d -= rc[0] * rp[9];
-            b -= rc[0] * rp[7];
+            l = -rc[0] * rp[9];
+            sg = fma(-rc[0], rp[11], sg);
+            b = fma(-rc[0], rp[8], b);
+        } else {
+            sg -= rc[0];          // no tile to the left (rc[0] is 0 for the Dirichlet head anyway)
         }
-        d -= rc[2] * rc[5];
-        r = -rc[2] * rc[6];
-        b -= rc[2] * rc[4];
-        rl[c] = l; rd[c] = d; rr[c] = r; rb[c] = b;
+        sg = fma(-rc[2], rc[7], sg);
+        const double r = -rc[2] * rc[6];
+        b = fma(-rc[2], rc[4], b);
+        rl[c] = l; rs[c] = sg; rr[c] = r; rb[c] = b;
     }
     __syncthreads();
-    ArrayRows rows{rl, rd, rr, rb, cnt};
-    double six[6];
-    chunk_reduce(rows, t * S, S, six);
-    double lp, dp, rp, bp;
-    rows.get(t * S, lp, dp, rp, bp);
-    double* ex = sm;                 // 6 * TOPT
-    double* pcr = sm + 6 * TOPT;     // 2 * 4 * TOPT
-#pragma unroll
-    for (int i = 0; i < 6; ++i) ex[i * TOPT + t] = six[i];
+    ArrayRows rows{rl, rs, rr, rb, cnt};
+    double e8[8];
+    chunk_reduce(rows, t * S, S, e8);
+    double lp, sp, rp, bp;
+    rows.get(t * S, lp, sp, rp, bp);
+    double* ex = sm;                 // 3 * TOPT
+    double* pcr = sm + 3 * TOPT;     // 2 * 4 * TOPT
+    ex[0 * TOPT + t] = e8[4]; ex[1 * TOPT + t] = e8[5]; ex[2 * TOPT + t] = e8[7];
     __syncthreads();
-    double l = 0.0, d = 1.0, r = 0.0, rhs[1] = {0.0}, x[1];
+    double l = 0.0, sg = 1.0, r = 0.0, rhs[1] = {0.0}, x[1];
     if (t >= 1) {
-        head_equation(lp, dp, rp, bp, ex[3 * TOPT + t - 1], ex[4 * TOPT + t - 1], ex[5 * TOPT + t - 1], six, l, d, r, rhs[0]);
+        head_equation(lp, sp, rp, bp, ex[0 * TOPT + t - 1], ex[1 * TOPT + t - 1], ex[2 * TOPT + t - 1], e8, l, sg, r, rhs[0]);
     } else {
         // head 0 is global node 0 (identity row); its equation still carries the coupling to chunk 0's interior
-        l = 0.0;
-        d = dp - rp * six[1];
-        r = -rp * six[2];
-        rhs[0] = bp - rp * six[0];
+        head_equation(0.0, sp - lp, rp, bp, 0.0, 0.0, 0.0, e8, l, sg, r, rhs[0]);
     }
-    pcr_solve<1, TOPT>(pcr, t, 0, TOPT - 1, l, d, r, rhs, x);
+    pcr_solve<1, TOPT>(pcr, t, 0, TOPT - 1, l, sg, r, rhs, x);
     double* uh = ex;   // head values, reuse
     __syncthreads();
     uh[t] = x[0];
@@ -226,19 +253,11 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
         const double ua = x[0];
         const double ub = (t + 1 < TOPT) ? uh[t + 1] : 0.0;
         // Thomas on rows m0+1 .. m0+S-1 with known neighbours
-        double lo, di, ro, bo;
-        rows.get(m0 + 1, lo, di, ro, bo);
-        bo -= lo * ua;
-        if (S == 2) bo -= ro * ub;
-        double inv0 = fast_rcp(di);
-        double cp = ro * inv0, bpv = bo * inv0;
-        if (m0 + 1 < cnt) { tc[m0 + 1] = cp; tb[m0 + 1] = bpv; }
-        for (int i = 2; i < S; ++i) {
-            rows.get(m0 + i, lo, di, ro, bo);
-            if (i == S - 1) bo -= ro * ub;
-            const double den = fast_rcp(di - lo * cp);
-            cp = ro * den;
-            bpv = (bo - lo * bpv) * den;
+        double lo, so, ro, bo, q = 1.0, cp = 0.0, bpv = ua;     // "previous row" = the known head: x = ua
+        for (int i = 1; i < S; ++i) {
+            rows.get(m0 + i, lo, so, ro, bo);
+            if (i == S - 1) bo = fma(-ro, ub, bo);
+            thomas_step(lo, so, ro, bo, q, cp, bpv);
             if (m0 + i < cnt) { tc[m0 + i] = cp; tb[m0 + i] = bpv; }
         }
         double xv = bpv;
@@ -272,21 +291,16 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
     __syncthreads();
     MeshRows<SPECIAL> rows{sm + SM_K, sm + SM_B, P, a.n, a.uL, a.uR};
     const double ua = uh[t], ub = uh[t + 1];
-    // Thomas on the chunk interior, compile-time length FS - 1
+    // Thomas on the chunk interior, compile-time length FS - 1 (row-sum form, see thomas_step)
     double cpv[FS], bpv[FS], xs[FS];
     {
-        double lo, di, ro, bo;
-        rows.get(t * FS + 1, lo, di, ro, bo);
-        bo -= lo * ua;
-        double inv = fast_rcp(di);
-        cpv[1] = ro * inv; bpv[1] = bo * inv;
+        double lo, so, ro, bo, q = 1.0, cp = 0.0, bv = ua;      // "previous row" = the known head: x = ua
 #pragma unroll
-        for (int i = 2; i < FS; ++i) {
-            rows.get(t * FS + i, lo, di, ro, bo);
-            if (i == FS - 1) bo -= ro * ub;
-            inv = fast_rcp(di - lo * cpv[i - 1]);
-            cpv[i] = ro * inv;
-            bpv[i] = (bo - lo * bpv[i - 1]) * inv;
+        for (int i = 1; i < FS; ++i) {
+            rows.get(t * FS + i, lo, so, ro, bo);
+            if (i == FS - 1) bo = fma(-ro, ub, bo);
+            thomas_step(lo, so, ro, bo, q, cp, bv);
+            cpv[i] = cp; bpv[i] = bv;
         }
         xs[FS - 1] = bpv[FS - 1];
 #pragma unroll
@@ -414,11 +428,11 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)(14 * TOPT * sizeof(double))));
+                                                (int)(11 * TOPT * sizeof(double))));
         }
         fem_reduce_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
         const int S = (int)((nt + TOPT - 1) / TOPT);
-        fem_top_kernel<<<1, TOPT, 14 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
+        fem_top_kernel<<<1, TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
         fem_backsub_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
         count_launch(3);
         HFL_CUDA_CHECK(cudaGetLastError());

@@ -9,7 +9,7 @@ constexpr int FS = 8;             // nodes per thread chunk (head + 7 interior)
 constexpr int FTS = FT * FS;      // nodes per tile
 constexpr int TOPT = 1024;        // threads of the top-level CTA
 constexpr int TOP_MAX_CHUNK = 64; // tile heads per top-level thread
-constexpr int REC = 10;           // doubles per tile record
+constexpr int REC = 12;           // doubles per tile record
 
 __host__ __device__ inline int padi(int i) { return i + (i >> 3); }
 
@@ -23,6 +23,13 @@ struct FemArgs {
     double gx0, gx1; // Gauss points on [0, 1]
 };
 
+// Row representation used by every elimination below: (l, sigma, r, b) with sigma = l + d + r the ROW SUM, the
+// diagonal being recovered as d = sigma - l - r.  For this M-matrix l, r <= 0 and sigma is tiny (exactly the
+// rounding residue of d = fl(k_left + k_right), obtained by an error-free TwoSum), so every diagonal that the
+// eliminations form is a sum of same-signed terms: no cancellation (the GTH idea for M-matrices).  Plain (l, d, r)
+// elimination loses ~cond * eps on this matrix (5e-12 at 1e4 nodes, 1e-10 at 1e5, like LAPACK or SuperLU); this form
+// stays at ~1e-14 of the exact solution of the same rounded system.
+//
 // Rows of the level-0 system from shared memory: k[q] = stiffness entry of local element q (global element
 // P - 1 + q), b[m] = load of local node m (global node P + m).  SPECIAL = the tile contains a Dirichlet node
 // or padding past the mesh (first / last tile only); interior tiles take the branch-free path.
@@ -30,25 +37,29 @@ template <bool SPECIAL>
 struct MeshRows {
     const double* k; const double* b;
     long long P, n; double uL, uR;
-    __device__ __forceinline__ void get(int m, double& l, double& d, double& r, double& bo) const {
+    __device__ __forceinline__ void get(int m, double& l, double& sg, double& r, double& bo) const {
         if (SPECIAL) {
             const long long g = P + m;
-            if (g >= n) { l = 0.0; d = 1.0; r = 0.0; bo = 0.0; return; }
-            if (g == 0) { l = 0.0; d = 1.0; r = 0.0; bo = uL; return; }
-            if (g == n - 1) { l = 0.0; d = 1.0; r = 0.0; bo = uR; return; }
+            if (g >= n) { l = 0.0; sg = 1.0; r = 0.0; bo = 0.0; return; }
+            if (g == 0) { l = 0.0; sg = 1.0; r = 0.0; bo = uL; return; }
+            if (g == n - 1) { l = 0.0; sg = 1.0; r = 0.0; bo = uR; return; }
         }
         const double kl = k[padi(m)], kr = k[padi(m + 1)];
-        l = -kl; r = -kr; d = kl + kr;
+        l = -kl; r = -kr;
+        // d = fl(kl + kr) is the reference's assembled diagonal; kl + kr = d + err exactly (TwoSum), so sigma = -err
+        const double d = __dadd_rn(kl, kr);
+        const double t = __dsub_rn(d, kl);
+        sg = -__dadd_rn(__dsub_rn(kl, __dsub_rn(d, t)), __dsub_rn(kr, t));
         bo = b[padi(m)];
     }
 };
 
-// Rows of the top-level system, stored as four arrays in global memory.
+// Rows of the top-level system, stored as four arrays (l, sigma, r, b) in global memory.
 struct ArrayRows {
-    const double* l; const double* d; const double* r; const double* b; int count;
-    __device__ __forceinline__ void get(int m, double& lo, double& di, double& ro, double& bo) const {
-        if (m >= count) { lo = 0.0; di = 1.0; ro = 0.0; bo = 0.0; return; }
-        lo = l[m]; di = d[m]; ro = r[m]; bo = b[m];
+    const double* l; const double* sg; const double* r; const double* b; int count;
+    __device__ __forceinline__ void get(int m, double& lo, double& so, double& ro, double& bo) const {
+        if (m >= count) { lo = 0.0; so = 1.0; ro = 0.0; bo = 0.0; return; }
+        lo = l[m]; so = sg[m]; ro = r[m]; bo = b[m];
     }
 };
 
@@ -72,11 +83,11 @@ __device__ __forceinline__ void element_terms(const FemArgs& a, double x0, doubl
 // the exchange and PCR buffers of the reduce pass alias them once the chunk sweeps are done.
 constexpr int EL_LEN = FTS + 1 + (FTS + 1) / 8 + 8;   // padded array of FTS + 1 entries
 constexpr int SM_K = 0, SM_B = EL_LEN;
-constexpr int SM_EX = 0;                               // 6 * FT exchange (aliases SM_K, after a barrier)
-constexpr int SM_PCR = 6 * FT;                         // 2 * 6 * FT     (aliases the rest)
+constexpr int SM_EX = 0;                               // 8 * FT exchange (aliases SM_K, after a barrier)
+constexpr int SM_PCR = 0;                              // 2 * 7 * FT PCR buffers (alias the same space, later)
 constexpr int SM_UH = 2 * EL_LEN;                      // FT + 1 chunk-head values (back-substitution pass)
 constexpr int SM_TOTAL = 2 * EL_LEN + FT + 8;
-static_assert(6 * FT + 2 * 6 * FT <= 2 * EL_LEN, "PCR buffers must fit in the element arrays they alias");
+static_assert(2 * 7 * FT <= 2 * EL_LEN && 8 * FT <= 2 * EL_LEN, "exchange / PCR buffers must fit in the element arrays they alias");
 
 // Element terms of local elements q = t, t + FT, ...; the nodes of the next element are fetched while the
 // current one is being computed.  Node loads are accumulated as (0 + L_i) + R_{i-1}: every element first

@@ -28,13 +28,13 @@ def test_uniform_mesh_vs_oracle(solver, n, k):
     nodes = np.linspace(-1, 1, n)
     u = batch.fem_p1_solve(dev(nodes), k_freq=k, coarse_solver=solver).cpu().numpy()
     ref = fem_p1.solve_fem_p1(nodes, k)
-    # two FP64 direct solvers on identical data: SuperLU vs LAPACK differ by 9e-12 at 1e4 nodes, SuperLU vs
-    # this partition + PCR solve by 1.1e-10 (measured); below 5000 nodes everything is inside 1e-10
-    tol = 1e-10 if (n <= 5000 or solver == 'flux') else 3e-10
+    # nodal parity bar of BASELINE.json; well-posed up to ~1e4 nodes (SuperLU itself is 2.9e-12 off the exact
+    # solution of its own system at 1e4 nodes, 1.2e-10 at 1e5 - scripts/probe_fem_accuracy.py)
+    tol = 1e-10
     assert np.max(np.abs(u - ref)) <= tol * max(1.0, np.max(np.abs(ref)))
     if n >= 9:
         expect = fem_p1.c_factor(2.0 / (n - 1), k) * np.sin(k * np.pi * nodes)   # analytic discrete solution
-        assert np.max(np.abs(u - expect)) <= (1e-12 if solver == 'flux' else tol)
+        assert np.max(np.abs(u - expect)) <= (1e-12 if solver == 'flux' else 1e-11)
 
 
 @pytest.mark.parametrize('solver', ['assembled', 'flux'])
@@ -50,9 +50,11 @@ def test_jittered_mesh_and_dirichlet_data(solver, n):
 
 
 def test_large_mesh_reported_spread():
-    """Beyond ~1e4 nodes FP64 solvers disagree with each other on identical data; check that the GPU
-    solve is no further from SuperLU than LAPACK is (x10), and that the flux form reaches 1e-11 of
-    the analytic discrete solution where the assembled form cannot."""
+    """Beyond ~1e4 nodes FP64 solvers disagree with each other on identical data.  The row-sum (GTH) elimination
+    of the assembled solve stays ~1e-14 from the exact solution of the reference's rounded system, so it must be
+    at least as close to SuperLU as LAPACK is; and both must show the SAME deviation from the analytic discrete
+    solution (2.9e-6 at 1e6 nodes: that deviation belongs to the rounded matrix, not to a solver), which the
+    flux form does not have."""
     n = 10 ** 6 + 1
     nodes = np.linspace(-1, 1, n)
     ref = fem_p1.solve_fem_p1(nodes)
@@ -60,10 +62,12 @@ def test_large_mesh_reported_spread():
     spread = np.max(np.abs(ref - alt))
     d_nodes = dev(nodes)
     u = batch.fem_p1_solve(d_nodes, coarse_solver='assembled').cpu().numpy()
-    assert np.max(np.abs(u - ref)) <= 100.0 * max(spread, 1e-10)
+    assert np.max(np.abs(u - ref)) <= 1.5 * spread
     uf = batch.fem_p1_solve(d_nodes, coarse_solver='flux').cpu().numpy()
     exact = fem_p1.c_factor(2.0 / (n - 1)) * np.sin(np.pi * nodes)
     assert np.max(np.abs(uf - exact)) <= 1e-11
+    da, ds = np.max(np.abs(u - exact)), np.max(np.abs(ref - exact))
+    assert abs(da - ds) <= 0.05 * ds        # same inherent deviation of the assembled system
     print('spread spsolve-vs-banded %.3e, gpu-assembled-vs-spsolve %.3e, gpu-flux-vs-analytic %.3e'
           % (spread, np.max(np.abs(u - ref)), np.max(np.abs(uf - exact))))
 
