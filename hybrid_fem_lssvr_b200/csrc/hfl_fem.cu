@@ -2,18 +2,22 @@
 //
 // The reference assembles the P1 stiffness and a 2-point-Gauss load with scikit-fem, turns the two
 // boundary rows into identity rows and calls a sparse direct solver.  Here the same rounded entries
-// (k_e = fl(1/h)^2 * (h/2) summed over the two Gauss points, load by the same two-point rule) are
-// formed on the fly from the node array and the tridiagonal system is solved by a two-level
-// partition method whose reduced systems are solved by parallel cyclic reduction (PCR):
+// (k_e = fl(1/h)^2 * (h/2) summed over the two Gauss points, d_i = fl(k_{i-1} + k_i), load by the same
+// two-point rule) are formed on the fly from the node array and the tridiagonal system is solved by a
+// two-level partition method whose reduced systems are solved by parallel cyclic reduction (PCR):
 //
 //   level 0  tiles of T*S = 2048 nodes, one CTA each.  Every thread eliminates the S-1 interior nodes
-//            of its chunk (two sweeps give the first/last entries of T^-1 b, T^-1 l e_1, T^-1 r e_s),
-//            the T-1 chunk heads form a tridiagonal system solved by PCR in shared memory
-//            (3 right-hand sides in the reduce pass, 1 in the back-substitution pass).
+//            of its chunk (two sweeps give the first/last entries of T^-1 b, T^-1 l e_1, T^-1 r e_s and of
+//            the "leak" 1 + v + w), the T-1 chunk heads form a tridiagonal system solved by PCR in shared
+//            memory (4 right-hand sides in the reduce pass; the back-substitution pass reuses the stored
+//            head solutions).
 //   top      one CTA solves the system of tile heads the same way (chunk per thread + PCR).
 //
+// Every elimination runs in row-sum form (l, sigma, r), d = sigma - l - r (hfl_fem.cuh): no cancellation,
+// ~1e-14 from the exact solution of the rounded system where LU-type solvers lose cond * eps.
 // Kernels: fem_reduce_kernel -> fem_top_kernel -> fem_backsub_kernel.  Node traffic: the node array
-// is read twice and u written once (24 B/node); the load is recomputed instead of stored.
+// is read twice and u written once (24 B/node) plus 3 B/node of head solutions; the load is recomputed
+// in the second pass instead of stored (re-reading it measured slower than two sinpi per element).
 #include "hfl_fem.cuh"
 
 namespace hfl {
