@@ -132,6 +132,8 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
         __syncthreads();
     }
     double* sPerm = sDe;   // dual form: [2 (NHD + 1)][kThreads] per-thread slots for the pivot-order gather
+    // coefficient staging: [kWarps][32][M] so that the warp writes its 32 x M block of d_coef with coalesced stores
+    double* sCoef = sDe + (NHD > 0 ? 2 * (NHD + 1) * kThreads : a.NH * (ME + MO));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* tile_ptr = smem_raw + warp * TILE;
@@ -348,14 +350,26 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
         }
 
         if (valid && a.status != nullptr) a.status[e] = ok ? 0 : 1;
-        if (valid && a.coef != nullptr) {
-            double* cp = a.coef + e * M;
+        if (a.coef != nullptr) {
+            // stage the thread's M coefficients (row pitch M; odd or even, 64-bit accesses stay conflict-light),
+            // then the warp writes its contiguous 32 x M block of [E][M] with consecutive lanes on consecutive doubles
+            double* cw = sCoef + warp * (32 * M);
+            double* cp = cw + lane * M;
             cp[0] = w0;
             cp[1] = w1;
 #pragma unroll
             for (int i = 0; i < ME; ++i) cp[2 + 2 * i] = re[i];
 #pragma unroll
             for (int i = 0; i < MO; ++i) cp[3 + 2 * i] = ro[i];
+            __syncwarp();
+            const long long rows_here = min((long long)32, a.E - wtile_e0);
+            double* g = a.coef + wtile_e0 * M;
+#pragma unroll
+            for (int q = 0; q < M; ++q) {
+                const int idx = q * 32 + lane;
+                if (idx < rows_here * M) g[idx] = cw[idx];
+            }
+            __syncwarp();
         }
 
         if (STORE == STORE_COOP && FH == 16 && do_fine) {
@@ -611,7 +625,8 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
     DualSmallTables<M, NHD> dt;
     if (dtp) dt = *dtp; else memset(&dt, 0, sizeof(dt));
     const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) +
-                        (NHD > 0 ? (size_t)2 * (NHD + 1) * kThreads : (size_t)a.NH * (ME + MO)) * sizeof(double);
+                        (NHD > 0 ? (size_t)2 * (NHD + 1) * kThreads : (size_t)a.NH * (ME + MO)) * sizeof(double) +
+                        (a.coef != nullptr ? (size_t)kWarps * 32 * M * sizeof(double) : 0);
     HFL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
