@@ -116,8 +116,10 @@ __device__ __forceinline__ int ldl_solve_skip(double (&A)[n * (n + 1) / 2], doub
     return kept;
 }
 
-template <int M, int FH, bool ERR, int STORE, int NHD = 0>
-__global__ void __launch_bounds__(kThreads, NHD > 0 ? 3 : min_ctas(M, ERR))
+// COEF: the coefficient-output path is compiled in (a separate instantiation, so that the fine-grid-only kernel
+// keeps its register budget).
+template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true>
+__global__ void __launch_bounds__(kThreads, NHD > 0 ? 3 : min_ctas(M, ERR || COEF))
 lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
               const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DualSmallTables<M, NHD> dt) {
     constexpr int ME = n_even(M), MO = n_odd(M);
@@ -350,7 +352,7 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
         }
 
         if (valid && a.status != nullptr) a.status[e] = ok ? 0 : 1;
-        if (a.coef != nullptr) {
+        if (COEF && a.coef != nullptr) {
             // stage the thread's M coefficients (row pitch M; odd or even, 64-bit accesses stay conflict-light),
             // then the warp writes its contiguous 32 x M block of [E][M] with consecutive lanes on consecutive doubles
             double* cw = sCoef + warp * (32 * M);
@@ -603,7 +605,7 @@ static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int
     return HFL_OK;
 }
 
-template <int M, int FH, bool ERR, int STORE, int NHD = 0>
+template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true>
 static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t stream,
                        const DualSmallTables<M, NHD>* dtp = nullptr) {
     constexpr int ME = n_even(M), MO = n_odd(M), F = 2 * FH;
@@ -621,7 +623,7 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
         int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F, STORE == STORE_TMA_ROWS);
         if (rc != HFL_OK) return rc;
     }
-    auto kern = lssvr_element_kernel<M, FH, ERR, STORE, NHD>;
+    auto kern = lssvr_element_kernel<M, FH, ERR, STORE, NHD, COEF>;
     DualSmallTables<M, NHD> dt;
     if (dtp) dt = *dtp; else memset(&dt, 0, sizeof(dt));
     const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) +

@@ -173,14 +173,15 @@ primal_generic_kernel(const PrimalArgs a, const GenericTables t, const bool want
 
 template <int M, int FH, bool ERR>
 static int dispatch_store(const hfl_plan* plan, const PrimalArgs& a, int store, cudaStream_t s) {
+    if (a.coef != nullptr) return launch_fast<M, FH, ERR, STORE_TMA, 0, true>(plan, a, s);   // coefficients wanted too
     switch (store) {
-        case STORE_DIRECT: return launch_fast<M, FH, ERR, STORE_DIRECT>(plan, a, s);
-        case STORE_SMEM: return launch_fast<M, FH, ERR, STORE_SMEM>(plan, a, s);
-        case STORE_TMA_ROWS: return launch_fast<M, FH, ERR, STORE_TMA_ROWS>(plan, a, s);
+        case STORE_DIRECT: return launch_fast<M, FH, ERR, STORE_DIRECT, 0, false>(plan, a, s);
+        case STORE_SMEM: return launch_fast<M, FH, ERR, STORE_SMEM, 0, false>(plan, a, s);
+        case STORE_TMA_ROWS: return launch_fast<M, FH, ERR, STORE_TMA_ROWS, 0, false>(plan, a, s);
         case STORE_COOP:
-            if constexpr (FH == 16 && M + 3 <= kCoopPitch) return launch_fast<M, FH, ERR, STORE_COOP>(plan, a, s);
-            else return launch_fast<M, FH, ERR, STORE_TMA>(plan, a, s);
-        default: return launch_fast<M, FH, ERR, STORE_TMA>(plan, a, s);
+            if constexpr (FH == 16 && M + 3 <= kCoopPitch) return launch_fast<M, FH, ERR, STORE_COOP, 0, false>(plan, a, s);
+            else return launch_fast<M, FH, ERR, STORE_TMA, 0, false>(plan, a, s);
+        default: return launch_fast<M, FH, ERR, STORE_TMA, 0, false>(plan, a, s);
     }
 }
 
