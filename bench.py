@@ -364,7 +364,7 @@ def run_ours(args):
         del runner
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:     # timed on rank 0 at N = 1 only
         cpu = cpu_baseline_record(args.cpu_sample, steps=6)
 
     if rank == 0:
