@@ -38,6 +38,7 @@ SIGNATURES = {
     'hfl_lssvr_primal_batch': (_i32, [_vp, _i64, _vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'hfl_lssvr_dual_batch': (_i32, [_vp, _i64, _vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'hfl_lssvr_dual_multi': (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'hfl_lssvr_general_batch': (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'hfl_evaluate_points': (_i32, [_i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     'hfl_error_fine': (_i32, [_i64, _i32, _vp, _vp, _f64, _vp, _vp]),
     'hfl_error_nodal': (_i32, [_i64, _vp, _vp, _f64, _vp, _vp]),

@@ -197,6 +197,27 @@ def lssvr_dual_multi(nodes, u, k_freqs, M, gamma, N=12, F=0, forcing='sine', bc2
     return coef, fine, status
 
 
+def lssvr_general_batch(nodes, u, a, f, M, gamma, N=12, F=0, da=None, c=None, bc2=None, want_coef=True,
+                        want_fine=False, want_status=False):
+    """Per-element LSSVR for -(a u')' + c u = f; a, da (= a'), c, f are [N, E] CUDA tensors of samples at the
+    collocation points (da / c may be None).  Returns (coef, fine, status) like lssvr_primal_batch."""
+    _require_cuda_f64(nodes, 'nodes')
+    E = nodes.numel() - 1
+    _require_cuda_f64(u, 'u', E + 1)
+    for name, t in (('a', a), ('f', f), ('da', da), ('c', c)):
+        if t is not None:
+            _require_cuda_f64(t, name, N * E)
+    dev = nodes.device
+    plan = get_plan(M, N, F if want_fine else 0, gamma)
+    coef = torch.empty((E, M), dtype=torch.float64, device=dev) if want_coef else None
+    fine = torch.empty((E, F), dtype=torch.float64, device=dev) if want_fine else None
+    status = torch.empty(E, dtype=torch.int32, device=dev) if want_status else None
+    _lib.check(_lib.load().hfl_lssvr_general_batch(plan.handle, E, _ptr(nodes), _ptr(u), _ptr(a), _ptr(da), _ptr(c), _ptr(f),
+                                                   _ptr(bc2), _ptr(coef), _ptr(fine), _ptr(status), _stream()),
+               'hfl_lssvr_general_batch')
+    return coef, fine, status
+
+
 def evaluate_points(nodes, coef, x):
     """K3 unstructured: evaluate_solution's element search + legval on the device (P:184-211)."""
     _require_cuda_f64(nodes, 'nodes')

@@ -145,10 +145,16 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
         for (int b = 0; b < mo; ++b) p->fineO[(size_t)i * (mo + 1) + 1 + b] = (double)P[3 + 2 * b];
     }
     p->D2.assign((size_t)N * M, 0.0);
+    p->D0.assign((size_t)N * M, 0.0);
+    p->D1.assign((size_t)N * M, 0.0);
     for (int j = 0; j < N; ++j) {
         long double x = -1.0L + 2.0L * (long double)j / (long double)(N - 1);
         legendre012(M, x, P.data(), d1.data(), d2.data());
-        for (int k = 0; k < M; ++k) p->D2[(size_t)j * M + k] = (double)d2[k];
+        for (int k = 0; k < M; ++k) {
+            p->D2[(size_t)j * M + k] = (double)d2[k];
+            p->D1[(size_t)j * M + k] = (double)d1[k];
+            p->D0[(size_t)j * M + k] = (double)P[k];
+        }
     }
     p->V.assign((size_t)(F > 0 ? F : 1) * M, 0.0);
     for (int i = 0; i < F; ++i) {
@@ -220,6 +226,7 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
     p->off_De = push(p->De); p->off_Do = push(p->Do); p->off_Ge = push(p->Ge); p->off_Go = push(p->Go);
     p->off_fineE = push(p->fineE); p->off_fineO = push(p->fineO); p->off_D2 = push(p->D2); p->off_V = push(p->V);
     p->off_Ct = push(p->Ct); p->off_K0 = push(p->K0);
+    p->off_D0 = push(p->D0); p->off_D1 = push(p->D1);
     p->off_Cpe = push(p->Cpe); p->off_Cpo = push(p->Cpo); p->off_Kpe = push(p->Kpe); p->off_Kpo = push(p->Kpo);
     p->n_tables = blk.size();
     cudaError_t e = cudaMalloc((void**)&p->d_tables, blk.size() * sizeof(double));

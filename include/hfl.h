@@ -126,6 +126,16 @@ int hfl_lssvr_dual_multi(const hfl_plan_t* plan, int64_t E, int R,
                          double* d_coef, double* d_fine, int32_t* d_status, double* d_err3,
                          void* stream);
 
+/* ---- general 1-D elliptic operator  -(a u')' + c u = f  (the reference codes the Poisson residual only, P:43-45; its
+ * README advertises elliptic problems in general).  Same QP with PDE rows (L phi_k)(x_j); a, a', c, f are samples
+ * [N][E] at the collocation points (d_da / d_c may be NULL = zero).  With a = 1, a' = c = 0 this is
+ * hfl_lssvr_primal_batch with HFL_FORCING_SAMPLES.  M <= 12. */
+int hfl_lssvr_general_batch(const hfl_plan_t* plan, int64_t E,
+                            const double* d_nodes, const double* d_u,
+                            const double* d_a, const double* d_da, const double* d_c, const double* d_f,
+                            const double* d_bc2,
+                            double* d_coef, double* d_fine, int32_t* d_status, void* stream);
+
 /* ---- K3 unstructured: replaces FEMLSSVRPrimalSolver.evaluate_solution (P:184-211).
  * For each query x: first element j with nodes[j] <= x <= nodes[j+1] (a shared node goes to the
  * LEFT element), element 0 / E-1 outside the mesh; value = numpy legval(off + scl x, coef[j]). */

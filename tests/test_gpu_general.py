@@ -1,0 +1,66 @@
+"""General elliptic operator -(a u')' + c u = f: the per-element kernel against its oracle,
+against the Poisson kernels when a = 1, a' = c = 0, and on a manufactured solution."""
+import numpy as np
+import pytest
+import torch
+
+from hybrid_fem_lssvr_b200 import batch
+from oracle import general, kkt
+from gpu_util import dev, jittered_mesh, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _pts(nodes, N):
+    return np.linspace(nodes[:-1], nodes[1:], N, axis=0)          # [N, E]
+
+
+@pytest.mark.parametrize('M', [3, 5, 8, 9, 12])
+@pytest.mark.parametrize('E', [1, 33, 1000])
+def test_against_oracle(M, E):
+    N, F, gamma = 12, 32, 1e4
+    nodes = jittered_mesh(E, seed=E + M)
+    x = _pts(nodes, N)
+    rng = np.random.default_rng(M)
+    a = 1.0 + 0.5 * np.sin(2.0 * x) ** 2
+    da = 2.0 * np.sin(2.0 * x) * np.cos(2.0 * x)
+    c = 3.0 + x
+    f = 10.0 * np.cos(3.0 * x) + rng.normal(size=x.shape) * 0.0
+    u = rng.uniform(-1, 1, E + 1)
+    coef, fine, status = batch.lssvr_general_batch(dev(nodes), dev(u), dev(a), dev(f), M, gamma, N=N, F=F, da=dev(da),
+                                                   c=dev(c), want_fine=True, want_status=True)
+    torch.cuda.synchronize()
+    ref = general.lssvr_general_kkt_batch(nodes, u, a.T.copy(), da.T.copy(), c.T.copy(), f.T.copy(), M, gamma)
+    assert not status.cpu().numpy().any()
+    fr = kkt.evaluate_fine(ref, F)
+    assert rel(fine.cpu().numpy(), fr) <= TOL
+    assert np.max(np.abs(coef.cpu().numpy() - ref)) <= TOL * max(1.0, np.max(np.abs(ref)))
+
+
+def test_reduces_to_the_poisson_kernel():
+    E, M, N = 4097, 9, 12
+    nodes = jittered_mesh(E, seed=3)
+    x = _pts(nodes, N)
+    f = (np.pi ** 2) * np.sin(np.pi * x)
+    u = np.sin(np.pi * nodes)
+    ones = np.ones_like(x)
+    _, fg, _ = batch.lssvr_general_batch(dev(nodes), dev(u), dev(ones), dev(f), M, 1e4, N=N, F=32, want_fine=True)
+    _, fp, _ = batch.lssvr_primal_batch(dev(nodes), dev(u), M, 1e4, N=N, F=32, forcing=dev(f), want_fine=True)
+    _, fs, _ = batch.lssvr_primal_batch(dev(nodes), dev(u), M, 1e4, N=N, F=32, forcing='sine', want_fine=True)
+    assert torch.max(torch.abs(fg - fp)).item() <= 1e-12
+    assert torch.max(torch.abs(fg - fs)).item() <= 1e-12
+
+
+def test_manufactured_solution():
+    """u = sin(pi x), a = 1 + x^2/2, c = 2: with exact nodal values the reconstruction is within 1e-9 of u."""
+    E, M, N, F = 200, 9, 12, 32
+    nodes = np.linspace(-1, 1, E + 1)
+    x = _pts(nodes, N)
+    a, da, c = 1.0 + 0.5 * x * x, x, 2.0 + 0.0 * x
+    uu, du, d2 = np.sin(np.pi * x), np.pi * np.cos(np.pi * x), -np.pi ** 2 * np.sin(np.pi * x)
+    f = -(a * d2 + da * du) + c * uu
+    _, fine, status = batch.lssvr_general_batch(dev(nodes), dev(np.sin(np.pi * nodes)), dev(a), dev(f), M, 1e4, N=N, F=F,
+                                                da=dev(da), c=dev(c), want_fine=True, want_status=True)
+    assert not status.cpu().numpy().any()
+    assert np.max(np.abs(fine.cpu().numpy() - np.sin(np.pi * kkt.fine_points(nodes, F)))) <= 1e-9

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from oracle import dual, fem_p1, kkt, kkt_mp, ref_loader
+from oracle import dual, fem_p1, general, kkt, kkt_mp, ref_loader
 
 
 def _rhs(k):
@@ -139,3 +139,13 @@ def test_c_port_matches_numpy_oracle():
     fr = kkt.evaluate_fine(ref, 32)
     assert np.max(np.abs(fine - fr)) <= 1e-10 * np.max(np.abs(fr))
     assert np.max(np.abs(coef - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_general_operator_oracle_reduces_to_poisson():
+    """oracle/general.py with a = 1, a' = c = 0 is oracle/kkt.py (which is pinned on the reference)."""
+    nodes = np.sort(np.concatenate([[-1.0, 1.0], np.random.default_rng(0).uniform(-1, 1, 49)]))
+    u = np.sin(np.pi * nodes)
+    pts = np.linspace(nodes[:-1], nodes[1:], 12, axis=0).T
+    f = fem_p1.forcing(pts)
+    wg = general.lssvr_general_kkt_batch(nodes, u, np.ones_like(f), np.zeros_like(f), np.zeros_like(f), f, 9, 1e4)
+    assert np.max(np.abs(wg - kkt.lssvr_primal_kkt_batch(nodes, u, f, 9, 1e4))) <= 1e-15
