@@ -70,11 +70,19 @@ __global__ void __launch_bounds__(GT, 3) general_kernel(const GeneralArgs g) {
             for (int j = 0; j <= i; ++j)
                 H[i * (i + 1) / 2 + j] = (((i ^ j) & 1) == 0) ? (i == j ? 2.0 * tau : tau) : 0.0;
         }
+        // samples of the next collocation point are fetched while the current rank-1 update runs
+        double na = __ldg(g.a + e), nd = g.da ? __ldg(g.da + e) : 0.0, nc = g.c ? __ldg(g.c + e) : 0.0, nf = __ldg(g.f + e);
         for (int j = 0; j < N; ++j) {
-            const double aj = g.a[(long long)j * g.E + e];
-            const double dj = g.da ? g.da[(long long)j * g.E + e] * hh : 0.0;        // a' h/2
-            const double cj = g.c ? g.c[(long long)j * g.E + e] * isig : 0.0;        // c h^2/4
-            const double fj = g.f[(long long)j * g.E + e] * isig;                    // f / sigma
+            const double aj = na;
+            const double dj = nd * hh;        // a' h/2
+            const double cj = nc * isig;      // c h^2/4
+            const double fj = nf * isig;      // f / sigma
+            if (j + 1 < N) {
+                const long long o = (long long)(j + 1) * g.E + e;
+                na = __ldg(g.a + o); nf = __ldg(g.f + o);
+                if (g.da) nd = __ldg(g.da + o);
+                if (g.c) nc = __ldg(g.c + o);
+            }
             const double* p0 = sP0 + j * M; const double* p1 = sP1 + j * M; const double* p2 = sP2 + j * M;
             const double A0 = cj;                                   // k = 0: P = 1, P' = P'' = 0
             const double A1 = fma(cj, p0[1], -dj);                  // k = 1: P = xi, P' = 1

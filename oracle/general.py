@@ -25,23 +25,65 @@ def basis_tables(M, N):
 
 
 def lssvr_general_kkt_batch(nodes, u, a_s, da_s, c_s, f_s, M, gamma):
-    """nodes (E+1,), u (E+1,), samples (E, N) each.  Returns coefficients (E, M)."""
+    """nodes (E+1,), u (E+1,), samples (E, N) each.  Returns coefficients (E, M).
+
+    Solved as the full KKT system of the problem scaled by 1/sigma^2 (sigma = scl^2):
+        min tau/2 |w|^2 + 1/2 |f/sigma - Ah w|^2  s.t. B w = g,   Ah = A / sigma, tau = 1 / (gamma sigma^2),
+        [[tau I + Ah^T Ah, B^T], [B, 0]] [w; mu] = [Ah^T f / sigma; g]
+    by LU with partial pivoting.  Unlike the Poisson case the first two columns of A do not vanish (c, a' terms),
+    so I + gamma A^T A is no longer block diagonal and its condition number (~gamma sigma^2) would be felt; the
+    scaled KKT matrix is well conditioned because B is invertible on the near-null space of Ah^T Ah.
+    tests/test_oracle.py checks this against an 80-digit solve.
+    """
     nodes = np.asarray(nodes, dtype=np.float64)
     E, N = f_s.shape
     P0, P1, P2 = basis_tables(M, N)
     h = nodes[1:] - nodes[:-1]
-    scl = 2.0 / h
-    A = (-(a_s * (scl * scl)[:, None])[:, :, None] * P2[None]
-         - (da_s * scl[:, None])[:, :, None] * P1[None]
-         + c_s[:, :, None] * P0[None])                                   # (E, N, M)
+    hh, isig = 0.5 * h, 0.25 * h * h
+    Ah = (-a_s[:, :, None] * P2[None]
+          - (da_s * hh[:, None])[:, :, None] * P1[None]
+          + (c_s * isig[:, None])[:, :, None] * P0[None])                # (E, N, M) = A / sigma
+    fh = f_s * isig[:, None]
+    tau = isig * isig / gamma
     Bm = np.stack([(-1.0) ** np.arange(M), np.ones(M)])
-    # scale rows by 1 / max|A| per element (the KKT solution is invariant; keeps H = I s^2 + gamma A^T A in range)
-    H = np.eye(M)[None] + gamma * np.einsum('enk,enm->ekm', A, A)
-    r = gamma * np.einsum('enk,en->ek', A, f_s)
-    rhs = np.concatenate([r[:, :, None], np.broadcast_to(Bm.T, (E, M, 2))], axis=2)
-    X = np.linalg.solve(H, rhs)
-    z, Y = X[:, :, 0], X[:, :, 1:]
-    S = np.einsum('am,emb->eab', Bm, Y)
-    g = np.stack([u[:-1], u[1:]], axis=1)
-    lam = np.linalg.solve(S, (np.einsum('am,em->ea', Bm, z) - g)[:, :, None])[:, :, 0]
-    return z - np.einsum('emb,eb->em', Y, lam)
+    K = np.zeros((E, M + 2, M + 2))
+    K[:, :M, :M] = np.einsum('enk,enm->ekm', Ah, Ah) + tau[:, None, None] * np.eye(M)[None]
+    K[:, :M, M:] = Bm.T[None]
+    K[:, M:, :M] = Bm[None]
+    rhs = np.zeros((E, M + 2))
+    rhs[:, :M] = np.einsum('enk,en->ek', Ah, fh)
+    rhs[:, M] = u[:-1]
+    rhs[:, M + 1] = u[1:]
+    return np.linalg.solve(K, rhs[:, :, None])[:, :M, 0]
+
+
+def lssvr_general_mp(xmin, xmax, u_l, u_r, a_s, da_s, c_s, f_s, M, gamma, dps=80):
+    """The same element problem in mpmath (unscaled KKT system, LU at `dps` digits); returns w as floats."""
+    import mpmath as mp
+    from .kkt_mp import _legendre_012
+    mp.mp.dps = dps
+    N = len(f_s)
+    h = mp.mpf(float(xmax)) - mp.mpf(float(xmin))
+    scl = 2 / h
+    A = mp.zeros(N, M)
+    for j in range(N):
+        P, d1, d2 = _legendre_012(M, -1 + mp.mpf(2 * j) / (N - 1))
+        for k in range(M):
+            A[j, k] = (-mp.mpf(float(a_s[j])) * scl * scl * d2[k] - mp.mpf(float(da_s[j])) * scl * d1[k]
+                       + mp.mpf(float(c_s[j])) * P[k])
+    K = mp.zeros(M + 2, M + 2)
+    H = mp.eye(M) + mp.mpf(float(gamma)) * (A.T * A)
+    r = mp.mpf(float(gamma)) * (A.T * mp.matrix([mp.mpf(float(v)) for v in f_s]))
+    rhs = mp.zeros(M + 2, 1)
+    for i in range(M):
+        for k in range(M):
+            K[i, k] = H[i, k]
+        K[i, M] = (-1) ** i
+        K[M, i] = (-1) ** i
+        K[i, M + 1] = 1
+        K[M + 1, i] = 1
+        rhs[i] = r[i]
+    rhs[M] = mp.mpf(float(u_l))
+    rhs[M + 1] = mp.mpf(float(u_r))
+    sol = mp.lu_solve(K, rhs)
+    return np.array([float(sol[i]) for i in range(M)])

@@ -149,3 +149,17 @@ def test_general_operator_oracle_reduces_to_poisson():
     f = fem_p1.forcing(pts)
     wg = general.lssvr_general_kkt_batch(nodes, u, np.ones_like(f), np.zeros_like(f), np.zeros_like(f), f, 9, 1e4)
     assert np.max(np.abs(wg - kkt.lssvr_primal_kkt_batch(nodes, u, f, 9, 1e4))) <= 1e-15
+
+
+@pytest.mark.parametrize('M,h', [(3, 2e-3), (9, 2e-3), (9, 0.25), (12, 1e-5)])
+def test_general_operator_oracle_matches_mpmath(M, h):
+    N = 12
+    nodes = np.array([0.1, 0.1 + h])
+    x = np.linspace(nodes[0], nodes[1], N)[None, :]
+    a, da, c = 1.0 + 0.5 * np.sin(2 * x) ** 2, np.sin(4 * x), 3.0 + x
+    f = 10.0 * np.cos(3.0 * x)
+    u = np.array([0.3, -0.2])
+    w = general.lssvr_general_kkt_batch(nodes, u, a, da, c, f, M, 1e4)[0]
+    wm = general.lssvr_general_mp(nodes[0], nodes[1], u[0], u[1], a[0], da[0], c[0], f[0], M, 1e4)
+    V = np.polynomial.legendre.legvander(np.linspace(-1, 1, 32), M - 1)
+    assert np.max(np.abs(V @ w - V @ wm)) <= 1e-12 * np.max(np.abs(V @ wm))
