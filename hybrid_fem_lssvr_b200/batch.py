@@ -97,6 +97,25 @@ def fem_p1_solve(nodes, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='asse
     return (u, react) if want_reaction else u
 
 
+GAUSS_X = (0.5 - 0.5 / math.sqrt(3.0), 0.5 + 0.5 / math.sqrt(3.0))   # 2-point Gauss abscissae on [0, 1]
+
+
+def fem_p1_solve_general(nodes, aq, fq, cq=None, u_left=0.0, u_right=0.0, out=None):
+    """Coarse P1 solve of -(a u')' + c u = f; aq, cq, fq are [2, E] samples at the Gauss points
+    x_e + h_e * GAUSS_X[q] of every element."""
+    _require_cuda_f64(nodes, 'nodes')
+    n = nodes.numel()
+    for name, t in (('aq', aq), ('fq', fq), ('cq', cq)):
+        if t is not None:
+            _require_cuda_f64(t, name, 2 * (n - 1))
+    lib = _lib.load()
+    u = out if out is not None else torch.empty(n, dtype=torch.float64, device=nodes.device)
+    ws = _workspace(int(lib.hfl_fem_p1_workspace_bytes(n)), nodes.device)
+    _lib.check(lib.hfl_fem_p1_solve_general(n, _ptr(nodes), _ptr(aq), _ptr(cq), _ptr(fq), float(u_left), float(u_right),
+                                            _ptr(u), _ptr(ws), ws.numel(), _stream()), 'hfl_fem_p1_solve_general')
+    return u
+
+
 def fem_apply_bc(nodes, u, bc_left, bc_right):
     _require_cuda_f64(nodes, 'nodes')
     _require_cuda_f64(u, 'u', nodes.numel())

@@ -133,12 +133,12 @@ __device__ __forceinline__ void head_equation(double lp, double sp, double rp, d
 }
 
 // Level 0, pass 1: one record per tile = {l, sigma, r, b of the tile head, y1, v1, w1, e1, ys, vs, ws, es of the interior}.
-template <bool SPECIAL>
+template <bool SPECIAL, bool GENERAL>
 __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __restrict__ rec, double* __restrict__ yvw,
                                                 double* sm) {
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
-    MeshRows<SPECIAL> rows{sm + SM_K, sm + SM_B, P, a.n, a.uL, a.uR};
+    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
     double e8[8];
     chunk_reduce(rows, t * FS, FS, e8);
     double lp, sp, rp, bp;
@@ -185,13 +185,14 @@ __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __rest
     }
 }
 
-__global__ void __launch_bounds__(FT, 4) fem_reduce_kernel(const FemArgs a, double* __restrict__ rec,
-                                                           double* __restrict__ yvw) {
+template <bool GENERAL>
+__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_reduce_kernel(const FemArgs a, double* __restrict__ rec,
+                                                                         double* __restrict__ yvw) {
     extern __shared__ double sm[];
     const long long P = (long long)blockIdx.x * FTS;
-    load_tile_elements(a, P, sm);
-    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true>(a, rec, yvw, sm);
-    else fem_reduce_body<false>(a, rec, yvw, sm);
+    load_tile_elements<GENERAL>(a, P, sm);
+    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true, GENERAL>(a, rec, yvw, sm);
+    else fem_reduce_body<false, GENERAL>(a, rec, yvw, sm);
 }
 
 // Thomas elimination of a chunk interior between two known head values, in (l, sigma, r) form: s = row sum over
@@ -279,21 +280,21 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
 
 // Level 0, pass 2: tile head values known -> chunk heads from the stored partial solutions
 // (U_t = Y_t - u_P V_t - u_Q W_t) -> chunk interiors by Thomas -> u.
-template <bool SPECIAL>
+template <bool SPECIAL, bool GENERAL>
 __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double* __restrict__ utop, int ntile,
                                                  const double* __restrict__ yvw, double* __restrict__ u, double* sm) {
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
     const double uP = utop[blockIdx.x];
     const double uQ = ((int)blockIdx.x + 1 < ntile) ? utop[blockIdx.x + 1] : 0.0;
-    double* uh = sm + SM_UH;    // FT head values (+1 for the next tile's head)
+    double* uh = sm + sm_uh(GENERAL);    // FT head values (+1 for the next tile's head)
     {
         const double* o = yvw + (size_t)blockIdx.x * 3 * FT;
         uh[t] = (t == 0) ? uP : (o[t] - uP * o[FT + t] - uQ * o[2 * FT + t]);
         if (t == 0) uh[FT] = uQ;
     }
     __syncthreads();
-    MeshRows<SPECIAL> rows{sm + SM_K, sm + SM_B, P, a.n, a.uL, a.uR};
+    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
     const double ua = uh[t], ub = uh[t + 1];
     // Thomas on the chunk interior, compile-time length FS - 1 (row-sum form, see thomas_step)
     double cpv[FS], bpv[FS], xs[FS];
@@ -322,13 +323,15 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
     }
 }
 
-__global__ void __launch_bounds__(FT, 4) fem_backsub_kernel(const FemArgs a, const double* __restrict__ utop, int ntile,
-                                                            const double* __restrict__ yvw, double* __restrict__ u) {
+template <bool GENERAL>
+__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_backsub_kernel(const FemArgs a, const double* __restrict__ utop,
+                                                                          int ntile, const double* __restrict__ yvw,
+                                                                          double* __restrict__ u) {
     extern __shared__ double sm[];
     const long long P = (long long)blockIdx.x * FTS;
-    load_tile_elements(a, P, sm);   // recomputed: re-reading cached terms (16 B/node) measured slower than 2 sinpi
-    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true>(a, utop, ntile, yvw, u, sm);
-    else fem_backsub_body<false>(a, utop, ntile, yvw, u, sm);
+    load_tile_elements<GENERAL>(a, P, sm);   // recomputed: re-reading cached terms (16 B/node) measured slower than 2 sinpi
+    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true, GENERAL>(a, utop, ntile, yvw, u, sm);
+    else fem_backsub_body<false, GENERAL>(a, utop, ntile, yvw, u, sm);
 }
 
 // End-node residuals for the multi-GPU interface system (see hfl.h).
@@ -397,20 +400,9 @@ extern "C" size_t hfl_fem_p1_workspace_bytes(int64_t n_nodes) {
 
 int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes, cudaStream_t s);   // hfl_flux.cu
 
-extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq, double u_left, double u_right,
-                                int coarse_solver, double* d_u, double* d_iface4, void* d_ws, size_t ws_bytes,
-                                void* stream) {
-    HFL_REQUIRE(n >= 2, "hfl_fem_p1_solve: need at least 2 nodes (got %lld)", (long long)n);
-    HFL_REQUIRE(d_nodes != nullptr && d_u != nullptr, "hfl_fem_p1_solve: d_nodes / d_u is NULL");
-    HFL_REQUIRE(coarse_solver == HFL_COARSE_ASSEMBLED_PCR || coarse_solver == HFL_COARSE_FLUX_SCAN,
-                "hfl_fem_p1_solve: unknown coarse_solver %d", coarse_solver);
-    HFL_REQUIRE(d_ws != nullptr && ws_bytes >= hfl_fem_p1_workspace_bytes(n),
-                "hfl_fem_p1_solve: workspace too small (%zu < %zu)", ws_bytes, hfl_fem_p1_workspace_bytes(n));
-    HFL_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "hfl_fem_p1_solve: workspace must be 256-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
-    const double pi = 3.14159265358979323846;
-    FemArgs a;
-    a.n = n; a.nodes = d_nodes; a.k = k_freq; a.kpi = k_freq * pi; a.kp2 = a.kpi * a.kpi; a.uL = u_left; a.uR = u_right;
+static int fem_solve_impl(FemArgs a, int coarse_solver, double* d_u, double* d_iface4, void* d_ws, size_t ws_bytes,
+                          cudaStream_t s) {
+    const long long n = a.n;
     a.gx0 = 0.5 * (-0.5773502691896257) + 0.5;   // 0.5 * leggauss(2) + 0.5
     a.gx1 = 0.5 * (0.5773502691896257) + 0.5;
     if (coarse_solver == HFL_COARSE_FLUX_SCAN) {
@@ -427,17 +419,24 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
         double* utop = rec + (size_t)REC * nt;
         double* wsrows = utop + nt;
         double* yvw = wsrows + 6 * (size_t)nt;
-        const size_t smem0 = (size_t)SM_TOTAL * sizeof(double);
-        {   // per device and cheap: set on every call (the function attributes do not carry over between devices)
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)(11 * TOPT * sizeof(double))));
-        }
-        fem_reduce_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
         const int S = (int)((nt + TOPT - 1) / TOPT);
-        fem_top_kernel<<<1, TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
-        fem_backsub_kernel<<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+        HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(11 * TOPT * sizeof(double))));
+        if (a.aq != nullptr) {
+            const size_t smem0 = (size_t)sm_total(true) * sizeof(double);
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+            fem_reduce_kernel<true><<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
+            fem_top_kernel<<<1, TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
+            fem_backsub_kernel<true><<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+        } else {
+            const size_t smem0 = (size_t)sm_total(false) * sizeof(double);
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+            fem_reduce_kernel<false><<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
+            fem_top_kernel<<<1, TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
+            fem_backsub_kernel<false><<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+        }
         count_launch(3);
         HFL_CUDA_CHECK(cudaGetLastError());
     }
@@ -447,6 +446,37 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
         HFL_CUDA_CHECK(cudaGetLastError());
     }
     return HFL_OK;
+}
+
+extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq, double u_left, double u_right,
+                                int coarse_solver, double* d_u, double* d_iface4, void* d_ws, size_t ws_bytes,
+                                void* stream) {
+    HFL_REQUIRE(n >= 2, "hfl_fem_p1_solve: need at least 2 nodes (got %lld)", (long long)n);
+    HFL_REQUIRE(d_nodes != nullptr && d_u != nullptr, "hfl_fem_p1_solve: d_nodes / d_u is NULL");
+    HFL_REQUIRE(coarse_solver == HFL_COARSE_ASSEMBLED_PCR || coarse_solver == HFL_COARSE_FLUX_SCAN,
+                "hfl_fem_p1_solve: unknown coarse_solver %d", coarse_solver);
+    HFL_REQUIRE(d_ws != nullptr && ws_bytes >= hfl_fem_p1_workspace_bytes(n),
+                "hfl_fem_p1_solve: workspace too small (%zu < %zu)", ws_bytes, hfl_fem_p1_workspace_bytes(n));
+    HFL_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "hfl_fem_p1_solve: workspace must be 256-byte aligned");
+    const double pi = 3.14159265358979323846;
+    FemArgs a;
+    a.n = n; a.nodes = d_nodes; a.k = k_freq; a.kpi = k_freq * pi; a.kp2 = a.kpi * a.kpi; a.uL = u_left; a.uR = u_right;
+    a.aq = nullptr; a.cq = nullptr; a.fq = nullptr;
+    return fem_solve_impl(a, coarse_solver, d_u, d_iface4, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int hfl_fem_p1_solve_general(int64_t n, const double* d_nodes, const double* d_aq, const double* d_cq,
+                                        const double* d_fq, double u_left, double u_right, double* d_u, void* d_ws,
+                                        size_t ws_bytes, void* stream) {
+    HFL_REQUIRE(n >= 2, "hfl_fem_p1_solve_general: need at least 2 nodes (got %lld)", (long long)n);
+    HFL_REQUIRE(d_nodes && d_u && d_aq && d_fq, "hfl_fem_p1_solve_general: d_nodes / d_u / d_aq / d_fq is NULL");
+    HFL_REQUIRE(d_ws != nullptr && ws_bytes >= hfl_fem_p1_workspace_bytes(n),
+                "hfl_fem_p1_solve_general: workspace too small (%zu < %zu)", ws_bytes, hfl_fem_p1_workspace_bytes(n));
+    HFL_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "hfl_fem_p1_solve_general: workspace must be 256-byte aligned");
+    FemArgs a;
+    a.n = n; a.nodes = d_nodes; a.k = 0.0; a.kpi = 0.0; a.kp2 = 0.0; a.uL = u_left; a.uR = u_right;
+    a.aq = d_aq; a.cq = d_cq; a.fq = d_fq;
+    return fem_solve_impl(a, HFL_COARSE_ASSEMBLED_PCR, d_u, nullptr, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int hfl_fem_apply_bc(int64_t n, const double* d_nodes, double* d_u, double bl, double br, void* stream) {

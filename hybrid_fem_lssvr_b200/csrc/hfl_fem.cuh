@@ -21,6 +21,9 @@ struct FemArgs {
     double kp2;      // (k pi)^2
     double uL, uR;
     double gx0, gx1; // Gauss points on [0, 1]
+    // general operator -(a u')' + c u = f: coefficient / forcing samples at the two Gauss points of every element,
+    // [2][n-1] each (NULL = the reference's Poisson problem with the sine forcing family)
+    const double* aq; const double* cq; const double* fq;
 };
 
 // Row representation used by every elimination below: (l, sigma, r, b) with sigma = l + d + r the ROW SUM, the
@@ -33,9 +36,9 @@ struct FemArgs {
 // Rows of the level-0 system from shared memory: k[q] = stiffness entry of local element q (global element
 // P - 1 + q), b[m] = load of local node m (global node P + m).  SPECIAL = the tile contains a Dirichlet node
 // or padding past the mesh (first / last tile only); interior tiles take the branch-free path.
-template <bool SPECIAL>
+template <bool SPECIAL, bool GENERAL = false>
 struct MeshRows {
-    const double* k; const double* b;
+    const double* k; const double* b; const double* s;    // s: row sums per node (general operator only)
     long long P, n; double uL, uR;
     __device__ __forceinline__ void get(int m, double& l, double& sg, double& r, double& bo) const {
         if (SPECIAL) {
@@ -46,11 +49,12 @@ struct MeshRows {
         }
         const double kl = k[padi(m)], kr = k[padi(m + 1)];
         l = -kl; r = -kr;
+        bo = b[padi(m)];
+        if (GENERAL) { sg = s[padi(m)]; return; }          // mass-matrix row sum, assembled without cancellation
         // d = fl(kl + kr) is the reference's assembled diagonal; kl + kr = d + err exactly (TwoSum), so sigma = -err
         const double d = __dadd_rn(kl, kr);
         const double t = __dsub_rn(d, kl);
         sg = -__dadd_rn(__dsub_rn(kl, __dsub_rn(d, t)), __dsub_rn(kr, t));
-        bo = b[padi(m)];
     }
 };
 
@@ -79,19 +83,39 @@ __device__ __forceinline__ void element_terms(const FemArgs& a, double x0, doubl
     Rs = __dadd_rn(__dmul_rn(__dmul_rn(f0, a.gx0), hw), __dmul_rn(__dmul_rn(f1, a.gx1), hw));
 }
 
+// General operator: P1 stiffness of a (2-point Gauss), mass matrix of c, load of f, all from samples at the two
+// Gauss points.  k = -(off-diagonal entry) = k_a - m_LR; sL, sR = the element's share of the row sums of its
+// left / right node (the stiffness part cancels analytically: only the mass row sums c phi_i remain).
+__device__ __forceinline__ void element_terms_general(const FemArgs& a, long long ge, double x0, double x1, double& k,
+                                                      double& sL, double& sR, double& Ls, double& Rs) {
+    const long long E = a.n - 1;
+    const double h = x1 - x0, hw = 0.5 * h, invh = 1.0 / h;
+    const double a0 = __ldg(a.aq + ge), a1 = __ldg(a.aq + E + ge);
+    const double c0 = a.cq ? __ldg(a.cq + ge) : 0.0, c1 = a.cq ? __ldg(a.cq + E + ge) : 0.0;
+    const double f0 = __ldg(a.fq + ge), f1 = __ldg(a.fq + E + ge);
+    const double pL0 = 1.0 - a.gx0, pL1 = 1.0 - a.gx1, pR0 = a.gx0, pR1 = a.gx1;
+    k = (a0 + a1) * (invh * invh) * hw - (c0 * pL0 * pR0 + c1 * pL1 * pR1) * hw;
+    sL = (c0 * pL0 + c1 * pL1) * hw;
+    sR = (c0 * pR0 + c1 * pR1) * hw;
+    Ls = (f0 * pL0 + f1 * pL1) * hw;
+    Rs = (f0 * pR0 + f1 * pR1) * hw;
+}
+
 // Shared-memory layout of the level-0 kernels (doubles): two padded arrays (element stiffness, node load);
 // the exchange and PCR buffers of the reduce pass alias them once the chunk sweeps are done.
 constexpr int EL_LEN = FTS + 1 + (FTS + 1) / 8 + 8;   // padded array of FTS + 1 entries
 constexpr int SM_K = 0, SM_B = EL_LEN;
 constexpr int SM_EX = 0;                               // 8 * FT exchange (aliases SM_K, after a barrier)
 constexpr int SM_PCR = 0;                              // 2 * 7 * FT PCR buffers (alias the same space, later)
-constexpr int SM_UH = 2 * EL_LEN;                      // FT + 1 chunk-head values (back-substitution pass)
-constexpr int SM_TOTAL = 2 * EL_LEN + FT + 8;
+constexpr int SM_S = 2 * EL_LEN;                       // general operator only: row sums per node
+__host__ __device__ constexpr int sm_uh(bool general) { return (general ? 3 : 2) * EL_LEN; }   // FT + 1 chunk-head values
+__host__ __device__ constexpr int sm_total(bool general) { return sm_uh(general) + FT + 8; }
 static_assert(2 * 7 * FT <= 2 * EL_LEN && 8 * FT <= 2 * EL_LEN, "exchange / PCR buffers must fit in the element arrays they alias");
 
 // Element terms of local elements q = t, t + FT, ...; the nodes of the next element are fetched while the
 // current one is being computed.  Node loads are accumulated as (0 + L_i) + R_{i-1}: every element first
 // writes its left-node share, then (after a barrier) adds its right-node share.
+template <bool GENERAL = false>
 __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P, double* sm) {
     auto fetch = [&](int q, double& x0, double& x1) {
         const long long ge = P - 1 + q;
@@ -100,29 +124,37 @@ __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P
         x1 = ok ? __ldg(a.nodes + ge + 1) : 1.0;
     };
     constexpr int NQ = (FTS + FT) / FT;     // elements per thread (the last one only for thread 0)
-    double rs[NQ];
+    double rs[NQ], ss[NQ];
     double nx0, nx1;
     fetch(threadIdx.x, nx0, nx1);
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
         const int q = threadIdx.x + j * FT;
-        rs[j] = 0.0;
+        rs[j] = 0.0; ss[j] = 0.0;
         if (q <= FTS) {
             const double x0 = nx0, x1 = nx1;
             fetch(q + FT, nx0, nx1);
             const long long ge = P - 1 + q;
-            double k = 0.0, Ls = 0.0, Rs = 0.0;
-            if (ge >= 0 && ge <= a.n - 2) element_terms(a, x0, x1, k, Ls, Rs);
+            double k = 0.0, Ls = 0.0, Rs = 0.0, sL = 0.0, sR = 0.0;
+            if (ge >= 0 && ge <= a.n - 2) {
+                if (GENERAL) element_terms_general(a, ge, x0, x1, k, sL, sR, Ls, Rs);
+                else element_terms(a, x0, x1, k, Ls, Rs);
+            }
             sm[SM_K + padi(q)] = k;
             if (q >= 1) sm[SM_B + padi(q - 1)] = Ls;       // left node of local element q is local node q - 1
+            if (GENERAL && q >= 1) sm[SM_S + padi(q - 1)] = sL;
             rs[j] = Rs;
+            ss[j] = sR;
         }
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
         const int q = threadIdx.x + j * FT;
-        if (q < FTS) sm[SM_B + padi(q)] += rs[j];          // right node of local element q is local node q
+        if (q < FTS) {
+            sm[SM_B + padi(q)] += rs[j];                   // right node of local element q is local node q
+            if (GENERAL) sm[SM_S + padi(q)] += ss[j];
+        }
     }
     __syncthreads();
 }

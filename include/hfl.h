@@ -70,6 +70,15 @@ int hfl_fem_p1_solve(int64_t n_nodes, const double* d_nodes, double k_freq,
                      double* d_u, double* d_iface4,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Coarse P1 solve of the general operator -(a u')' + c u = f (stiffness of a, mass matrix of c, load of f, each by
+ * the same 2-point Gauss rule): d_aq, d_cq, d_fq are samples [2][n-1] at the two Gauss points
+ * x_e + h_e (1/2 -+ 1/(2 sqrt 3)) of every element (d_cq may be NULL = 0).  Assembled partition + PCR solver in
+ * row-sum form; same workspace as hfl_fem_p1_solve. */
+int hfl_fem_p1_solve_general(int64_t n_nodes, const double* d_nodes,
+                             const double* d_aq, const double* d_cq, const double* d_fq,
+                             double u_left, double u_right, double* d_u,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Interface (SPIKE) system of a mesh split into G contiguous ranges, one per GPU.  Host function.
  * gathered[4 * r + {0,1,2,3}] = {x_first, x_last, r_left, r_right} of rank r (its local solve had
  * zero Dirichlet data at both ends).  Writes the G + 1 interface values (iface[0] = u_left,

@@ -101,3 +101,32 @@ def c_factor(h, k_freq=1.0):
     x2 = 0.5 + 0.5 / np.sqrt(3.0)
     s = np.sin(0.5 * t)
     return t * t * (x2 * np.cos(t * x1) + x1 * np.cos(t * x2)) / (4.0 * s * s)   # 2 - 2 cos t without cancellation
+
+
+def solve_fem_p1_general(nodes, a_func, c_func, f_func, u_left=0.0, u_right=0.0):
+    """P1 FEM for -(a u')' + c u = f with the same 2-point Gauss rule (stiffness of a, mass matrix of c, load of f),
+    Dirichlet rows as identity rows, SuperLU.  Restatement for the general-operator row (SURVEY.md section 8f-2);
+    the reference has no such code, so this is its own anchor (checked on a manufactured solution)."""
+    nodes = np.asarray(nodes, dtype=np.float64)
+    n = nodes.size
+    h = nodes[1:] - nodes[:-1]
+    b = np.zeros(n)
+    kd = np.zeros(n); ko = np.zeros(n - 1)
+    for q in range(2):
+        xq = h * _GX[q] + nodes[:-1]
+        w = h * _GW[q]
+        aq, cq, fq = a_func(xq), c_func(xq), f_func(xq)
+        pl, pr = 1.0 - _GX[q], _GX[q]
+        ka = aq / h / h * w
+        kd[:-1] += ka + cq * pl * pl * w
+        kd[1:] += ka + cq * pr * pr * w
+        ko += -ka + cq * pl * pr * w
+        b[:-1] += fq * pl * w
+        b[1:] += fq * pr * w
+    lower, upper, diag = ko.copy(), ko.copy(), kd.copy()
+    diag[0] = diag[-1] = 1.0
+    upper[0] = 0.0
+    lower[-1] = 0.0
+    b[0], b[-1] = u_left, u_right
+    A = sp.diags([lower, diag, upper], [-1, 0, 1], format='csr')
+    return spla.spsolve(A, b)

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from hybrid_fem_lssvr_b200 import batch
-from oracle import general, kkt
+from oracle import fem_p1, general, kkt
 from gpu_util import dev, jittered_mesh, rel
 
 pytestmark = pytest.mark.gpu
@@ -64,3 +64,56 @@ def test_manufactured_solution():
                                                 da=dev(da), c=dev(c), want_fine=True, want_status=True)
     assert not status.cpu().numpy().any()
     assert np.max(np.abs(fine.cpu().numpy() - np.sin(np.pi * kkt.fine_points(nodes, F)))) <= 1e-9
+
+
+def _coef_funcs():
+    a = lambda x: 1.0 + 0.5 * x * x
+    da = lambda x: x
+    c = lambda x: 2.0 + 0.0 * x
+    f = lambda x: -((1.0 + 0.5 * x * x) * (-np.pi ** 2 * np.sin(np.pi * x)) + x * np.pi * np.cos(np.pi * x)) + 2.0 * np.sin(np.pi * x)
+    return a, da, c, f
+
+
+def _gauss_samples(nodes, fn):
+    h = np.diff(nodes)
+    return np.stack([fn(nodes[:-1] + h * batch.GAUSS_X[q]) for q in range(2)])          # [2, E]
+
+
+@pytest.mark.parametrize('n', [2, 3, 50, 2048, 2049, 5001])
+def test_general_coarse_solve_vs_oracle(n):
+    a, da, c, f = _coef_funcs()
+    nodes = jittered_mesh(n - 1, seed=n)
+    u = batch.fem_p1_solve_general(dev(nodes), dev(_gauss_samples(nodes, a)), dev(_gauss_samples(nodes, f)),
+                                   cq=dev(_gauss_samples(nodes, c)), u_left=0.1, u_right=-0.2).cpu().numpy()
+    ref = fem_p1.solve_fem_p1_general(nodes, a, c, f, 0.1, -0.2)
+    assert u[0] == 0.1 and u[-1] == -0.2
+    assert np.max(np.abs(u - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_general_coarse_solve_reduces_to_poisson():
+    n = 4097
+    nodes = np.linspace(-1, 1, n)
+    one = lambda x: 1.0 + 0.0 * x
+    f = lambda x: np.pi ** 2 * np.sin(np.pi * x)
+    ug = batch.fem_p1_solve_general(dev(nodes), dev(_gauss_samples(nodes, one)), dev(_gauss_samples(nodes, f))).cpu().numpy()
+    up = batch.fem_p1_solve(dev(nodes)).cpu().numpy()
+    assert np.max(np.abs(ug - up)) <= 1e-11
+
+
+def test_general_pipeline_end_to_end():
+    """Hybrid method for -(a u')' + c u = f with u = sin(pi x): coarse P1 solve -> element LSSVR -> fine grid.
+    The enhancement removes the interpolation error: what is left is the (O(h^2)) nodal error of the P1 solve."""
+    a, da, c, f = _coef_funcs()
+    E, M, N, F = 400, 9, 12, 32
+    nodes = np.linspace(-1, 1, E + 1)
+    d_nodes = dev(nodes)
+    u = batch.fem_p1_solve_general(d_nodes, dev(_gauss_samples(nodes, a)), dev(_gauss_samples(nodes, f)),
+                                   cq=dev(_gauss_samples(nodes, c)))
+    nodal_err = np.max(np.abs(u.cpu().numpy() - np.sin(np.pi * nodes)))
+    x = _pts(nodes, N)
+    _, fine, status = batch.lssvr_general_batch(d_nodes, u, dev(a(x)), dev(f(x)), M, 1e4, N=N, F=F, da=dev(da(x)), c=dev(c(x)),
+                                                want_fine=True, want_status=True)
+    assert not status.cpu().numpy().any()
+    fine_err = np.max(np.abs(fine.cpu().numpy() - np.sin(np.pi * kkt.fine_points(nodes, F))))
+    assert 1e-7 < nodal_err < 1e-3
+    assert fine_err <= 1.05 * nodal_err + 1e-9
