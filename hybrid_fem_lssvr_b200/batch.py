@@ -68,7 +68,10 @@ _WORKSPACES = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    # one scratch buffer per (device, stream): calls on the same stream are ordered, calls on different
+    # streams must not share scratch space
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = _WORKSPACES[key] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
