@@ -17,7 +17,7 @@
 //    from one sincospi of the centre and one of the base angle (even part ~ cos, odd part ~ sin).
 //  * fine grid: u(+-xi) = E(xi) +- O(xi) with the basis values as immediate constant-bank operands
 //    (kernel parameter block), rows staged in swizzled shared memory and written by TMA tensor stores.
-#include "hfl_element_kernel.cuh"
+#include "hfl_primal_dispatch.cuh"
 
 namespace hfl {
 
@@ -171,44 +171,8 @@ primal_generic_kernel(const PrimalArgs a, const GenericTables t, const bool want
     }
 }
 
-template <int M, int FH, bool ERR>
-static int dispatch_store(const hfl_plan* plan, const PrimalArgs& a, int store, cudaStream_t s) {
-    // Coefficient output and the fused error norms always take the TMA-store instantiation that has the coefficient
-    // path compiled in: measured 0.54 ms against 0.60 ms for the fused-error kernel without it (register allocation),
-    // while the plain fine-grid kernel is 7 % faster without it.  The store-path option applies to the plain kernel.
-    if (a.coef != nullptr || ERR) return launch_fast<M, FH, ERR, STORE_TMA, 0, true>(plan, a, s);
-    if constexpr (!ERR) {
-    switch (store) {
-        case STORE_DIRECT: return launch_fast<M, FH, ERR, STORE_DIRECT, 0, false>(plan, a, s);
-        case STORE_SMEM: return launch_fast<M, FH, ERR, STORE_SMEM, 0, false>(plan, a, s);
-        case STORE_TMA_ROWS: return launch_fast<M, FH, ERR, STORE_TMA_ROWS, 0, false>(plan, a, s);
-        case STORE_COOP:
-            if constexpr (FH == 16 && M + 3 <= kCoopPitch) return launch_fast<M, FH, ERR, STORE_COOP, 0, false>(plan, a, s);
-            else return launch_fast<M, FH, ERR, STORE_TMA, 0, false>(plan, a, s);
-        default: return launch_fast<M, FH, ERR, STORE_TMA, 0, false>(plan, a, s);
-    }
-    }
-    return HFL_ERR_UNSUPPORTED;
-}
-
-template <int M, int FH>
-static int dispatch_err(const hfl_plan* plan, const PrimalArgs& a, bool err, int store, cudaStream_t s) {
-    return err ? dispatch_store<M, FH, true>(plan, a, store, s) : dispatch_store<M, FH, false>(plan, a, store, s);
-}
-
-template <int FH>
-static int dispatch_M(const hfl_plan* plan, const PrimalArgs& a, bool err, int store, cudaStream_t s) {
-    switch (plan->M) {
-#define HFL_CASE(m)                                                                        \
-    case m:                                                                                \
-        if constexpr (FH == 0) return launch_fast<m, 0, false, STORE_DIRECT>(plan, a, s);  \
-        else return dispatch_err<m, FH>(plan, a, err, store, s);
-        HFL_CASE(3) HFL_CASE(4) HFL_CASE(5) HFL_CASE(6) HFL_CASE(7) HFL_CASE(8) HFL_CASE(9) HFL_CASE(10)
-        HFL_CASE(11) HFL_CASE(12) HFL_CASE(13) HFL_CASE(14)
-#undef HFL_CASE
-        default: return -1;
-    }
-}
+int primal_dispatch_fh8(const hfl_plan* plan, const PrimalArgs& a, bool err, int store, cudaStream_t s);    // hfl_primal_f16.cu
+int primal_dispatch_fh32(const hfl_plan* plan, const PrimalArgs& a, bool err, int store, cudaStream_t s);   // hfl_primal_f64.cu
 
 }  // namespace hfl
 
@@ -247,6 +211,10 @@ extern "C" int hfl_lssvr_primal_batch(const hfl_plan_t* plan, int64_t E, const d
     if (plan->F == 32 && aligned16) {
         if (store == 0) store = STORE_TMA;
         rc = dispatch_M<16>(plan, a, want_err, store, s);
+    } else if (plan->F == 16 && aligned16) {      // TMA-store instantiations only
+        rc = primal_dispatch_fh8(plan, a, want_err, STORE_TMA, s);
+    } else if (plan->F == 64 && aligned16) {
+        rc = primal_dispatch_fh32(plan, a, want_err, STORE_TMA, s);
     } else if (plan->F == 0) {
         rc = dispatch_M<0>(plan, a, false, STORE_DIRECT, s);
     }

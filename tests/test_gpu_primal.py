@@ -204,3 +204,26 @@ def test_full_size_properties():
     for j, e in enumerate(idx[:200]):
         ref = oracle_coef(nh[e:e + 2], uh[e:e + 2], 9, 1e4, 12, k=1.0)
         assert rel(fh[j:j + 1], kkt.evaluate_fine(ref, 32)) <= TOL
+
+
+@pytest.mark.parametrize('M,F', [(9, 16), (9, 64), (3, 64), (14, 16), (14, 64)])
+def test_specialised_other_fine_sizes(M, F):
+    """F = 16 and F = 64 have their own instantiations (TMA stores, fused error norms, coefficient output)."""
+    E, N, gamma, k = 2000 + 5, 12, 1e4, 2.0
+    nodes = jittered_mesh(E, seed=F + M)
+    u = np.sin(2 * np.pi * nodes)
+    err3 = batch.new_error_accumulator()
+    coef, fine, status = _run(nodes, u, M, gamma, N=N, F=F, k=k, err3=err3)
+    ref = oracle_coef(nodes, u, M, gamma, N, k=k)
+    fr = kkt.evaluate_fine(ref, F)
+    assert not status.any()
+    assert rel(fine, fr) <= TOL
+    assert np.max(np.abs(coef - ref)) <= TOL * max(1.0, np.max(np.abs(ref)))
+    _, fine2, _ = batch.lssvr_primal_batch(dev(nodes), dev(u), M, gamma, N=N, F=F, k_freq=k, want_coef=False, want_fine=True)
+    assert np.array_equal(fine, fine2.cpu().numpy())                      # plain and fused-error instantiations agree bit for bit
+    x = kkt.fine_points(nodes, F)
+    d = fine - np.sin(k * np.pi * x)
+    w = np.ones(F); w[0] = w[-1] = 0.5
+    l2 = np.sqrt(np.sum((np.diff(nodes) / (F - 1.0))[:, None] * w[None, :] * d * d))
+    l2g, mxg = batch.finish_error(err3)
+    assert abs(l2g - l2) <= 1e-9 * l2 and abs(mxg - np.max(np.abs(d))) <= 1e-9 * np.max(np.abs(d)) + 1e-15
