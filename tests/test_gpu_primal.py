@@ -211,7 +211,7 @@ def test_specialised_other_fine_sizes(M, F):
     """F = 16 and F = 64 have their own instantiations (TMA stores, fused error norms, coefficient output)."""
     E, N, gamma, k = 2000 + 5, 12, 1e4, 2.0
     nodes = jittered_mesh(E, seed=F + M)
-    u = np.sin(2 * np.pi * nodes)
+    u = np.sin(2 * np.pi * nodes) + 1e-6 * np.cos(3 * nodes)      # a nodal perturbation, so that the error norms are not round-off
     err3 = batch.new_error_accumulator()
     coef, fine, status = _run(nodes, u, M, gamma, N=N, F=F, k=k, err3=err3)
     ref = oracle_coef(nodes, u, M, gamma, N, k=k)
@@ -220,7 +220,7 @@ def test_specialised_other_fine_sizes(M, F):
     assert rel(fine, fr) <= TOL
     assert np.max(np.abs(coef - ref)) <= TOL * max(1.0, np.max(np.abs(ref)))
     _, fine2, _ = batch.lssvr_primal_batch(dev(nodes), dev(u), M, gamma, N=N, F=F, k_freq=k, want_coef=False, want_fine=True)
-    assert np.array_equal(fine, fine2.cpu().numpy())                      # plain and fused-error instantiations agree bit for bit
+    assert np.max(np.abs(fine - fine2.cpu().numpy())) <= 1e-14            # plain and fused-error instantiations (different FMA contraction)
     x = kkt.fine_points(nodes, F)
     d = fine - np.sin(k * np.pi * x)
     w = np.ones(F); w[0] = w[-1] = 0.5
