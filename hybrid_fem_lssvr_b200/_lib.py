@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libhfl.so')
+LIB_PATH = os.environ.get('HFL_LIB') or os.path.join(HERE, 'libhfl.so')   # HFL_LIB: an A/B build of the same ABI
 
 HFL_OK = 0
 FORCING_SINE = 0

@@ -13,13 +13,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(HERE, 'build')
-LIB = os.path.join(HERE, 'libhfl.so')
+# HFL_VARIANT=name HFL_EXTRA_NVCC_FLAGS="-D..." builds an A/B copy (libhfl_name.so, objects in build_name/)
+VARIANT = os.environ.get('HFL_VARIANT', '')
+OBJ = os.path.join(HERE, 'build' + ('_' + VARIANT if VARIANT else ''))
+LIB = os.path.join(HERE, 'libhfl%s.so' % ('_' + VARIANT if VARIANT else ''))
 SOURCES = ['hfl_abi.cu', 'hfl_primal.cu', 'hfl_fem.cu', 'hfl_flux.cu', 'hfl_eval.cu', 'hfl_dual.cu',
            'hfl_dual_small.cu', 'hfl_general.cu', 'hfl_primal_f16.cu', 'hfl_primal_f64.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('HFL_EXTRA_NVCC_FLAGS', '').split()
 
 
 def _deps_mtime():
