@@ -32,6 +32,8 @@ SIGNATURES = {
     'hfl_mesh_linspace': (_i32, [_f64, _f64, _i64, _i64, _i64, _vp, _vp]),
     'hfl_fem_p1_workspace_bytes': (_sz, [_i64]),
     'hfl_fem_p1_solve': (_i32, [_i64, _vp, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    'hfl_fem_p1_multi_workspace_bytes': (_sz, [_i64, _i32]),
+    'hfl_fem_p1_solve_multi': (_i32, [_i64, _vp, _i32, _vp, _f64, _f64, _i32, _vp, _vp, _sz, _vp]),
     'hfl_fem_p1_solve_general': (_i32, [_i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _sz, _vp]),
     'hfl_spike_interface_solve': (_i32, [_i32, C.POINTER(_f64), _f64, _f64, C.POINTER(_f64)]),
     'hfl_spike_interface_solve_device': (_i32, [_i32, _vp, _f64, _f64, _i32, _vp, _vp]),

@@ -100,6 +100,24 @@ def fem_p1_solve(nodes, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='asse
     return (u, react) if want_reaction else u
 
 
+def fem_p1_solve_multi(nodes, k_freqs, u_left=0.0, u_right=0.0, coarse_solver='assembled', out=None):
+    """K1 for R forcing frequencies on one mesh in a single launch sequence: u [R, n], row r bit-identical to
+    fem_p1_solve(nodes, k_freq=k_freqs[r]).  k_freqs: float64 device tensor [R]."""
+    _require_cuda_f64(nodes, 'nodes')
+    n = nodes.numel()
+    R = k_freqs.numel()
+    _require_cuda_f64(k_freqs, 'k_freqs', R)
+    lib = _lib.load()
+    mode = {'assembled': _lib.COARSE_ASSEMBLED_PCR, 'pcr': _lib.COARSE_ASSEMBLED_PCR,
+            'flux': _lib.COARSE_FLUX_SCAN}[coarse_solver]
+    u = out if out is not None else torch.empty((R, n), dtype=torch.float64, device=nodes.device)
+    _require_cuda_f64(u, 'out', R * n)
+    ws = _workspace(int(lib.hfl_fem_p1_multi_workspace_bytes(n, R)), nodes.device)
+    _lib.check(lib.hfl_fem_p1_solve_multi(n, _ptr(nodes), R, _ptr(k_freqs), float(u_left), float(u_right), mode,
+                                          _ptr(u), _ptr(ws), ws.numel(), _stream()), 'hfl_fem_p1_solve_multi')
+    return u
+
+
 GAUSS_X = (0.5 - 0.5 / math.sqrt(3.0), 0.5 + 0.5 / math.sqrt(3.0))   # 2-point Gauss abscissae on [0, 1]
 
 

@@ -186,9 +186,11 @@ __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __rest
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_reduce_kernel(const FemArgs a, double* __restrict__ rec,
+__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_reduce_kernel(const FemArgs a_in, double* __restrict__ rec,
                                                                          double* __restrict__ yvw) {
     extern __shared__ double sm[];
+    const FemArgs a = select_rhs(a_in);
+    rec += (size_t)blockIdx.y * a.ws_stride; yvw += (size_t)blockIdx.y * a.ws_stride;
     const long long P = (long long)blockIdx.x * FTS;
     load_tile_elements<GENERAL>(a, P, sm);
     if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true, GENERAL>(a, rec, yvw, sm);
@@ -209,9 +211,11 @@ __device__ __forceinline__ void thomas_step(double l, double sg, double r, doubl
 // Top level: solve the system of tile heads.  One CTA of TOPT threads, chunk of S heads per thread.
 // ws: rows l, sigma, r, b [4][cnt] followed by Thomas scratch c', b' [2][cnt].
 __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict__ rec, int cnt, int S,
-                                                       double* __restrict__ wsrows, double* __restrict__ utop) {
+                                                       double* __restrict__ wsrows, double* __restrict__ utop,
+                                                       long long ws_stride) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
+    rec += (size_t)blockIdx.y * ws_stride; wsrows += (size_t)blockIdx.y * ws_stride; utop += (size_t)blockIdx.y * ws_stride;
     double* rl = wsrows; double* rs = wsrows + cnt; double* rr = wsrows + 2 * (size_t)cnt; double* rb = wsrows + 3 * (size_t)cnt;
     double* tc = wsrows + 4 * (size_t)cnt; double* tb = wsrows + 5 * (size_t)cnt;
     for (int c = t; c < cnt; c += TOPT) {
@@ -324,10 +328,12 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_backsub_kernel(const FemArgs a, const double* __restrict__ utop,
+__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_backsub_kernel(const FemArgs a_in, const double* __restrict__ utop,
                                                                           int ntile, const double* __restrict__ yvw,
                                                                           double* __restrict__ u) {
     extern __shared__ double sm[];
+    const FemArgs a = select_rhs(a_in);
+    utop += (size_t)blockIdx.y * a.ws_stride; yvw += (size_t)blockIdx.y * a.ws_stride; u += (size_t)blockIdx.y * a.n;
     const long long P = (long long)blockIdx.x * FTS;
     load_tile_elements<GENERAL>(a, P, sm);   // recomputed: re-reading cached terms (16 B/node) measured slower than 2 sinpi
     if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true, GENERAL>(a, utop, ntile, yvw, u, sm);
@@ -391,22 +397,32 @@ __global__ void spike_iface_kernel(int G, const double* __restrict__ g, double u
 using namespace hfl;
 
 static inline long long fem_ntile(long long n) { return (n + FTS - 1) / FTS; }
+static size_t fem_ws_doubles(long long nt) { return (size_t)(REC + 1 + 6 + 3 * FT) * (size_t)nt; }
 
 extern "C" size_t hfl_fem_p1_workspace_bytes(int64_t n_nodes) {
     if (n_nodes < 2) return 256;
     const long long nt = fem_ntile(n_nodes);
-    return (size_t)(REC + 1 + 6 + 3 * FT) * (size_t)nt * sizeof(double) + 256;
+    return fem_ws_doubles(nt) * sizeof(double) + 256;
 }
 
-int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes, cudaStream_t s);   // hfl_flux.cu
+// per right-hand side: the single-solve layout rounded up to 256 bytes
+static size_t fem_multi_stride_doubles(int64_t n_nodes) { return ((hfl_fem_p1_workspace_bytes(n_nodes) + 255) / 256) * 32; }
 
-static int fem_solve_impl(FemArgs a, int coarse_solver, double* d_u, double* d_iface4, void* d_ws, size_t ws_bytes,
+extern "C" size_t hfl_fem_p1_multi_workspace_bytes(int64_t n_nodes, int R) {
+    if (R < 1) R = 1;
+    return fem_multi_stride_doubles(n_nodes) * sizeof(double) * (size_t)R;
+}
+
+int hfl_fem_flux_scan(const FemArgs& a, int R, double* d_u, void* d_ws, size_t ws_bytes, cudaStream_t s);   // hfl_flux.cu
+
+// R right-hand sides (grid.y): a.kfreqs / a.ws_stride set by the caller for R > 1, NULL / 0 for a single solve.
+static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, double* d_iface4, void* d_ws, size_t ws_bytes,
                           cudaStream_t s) {
     const long long n = a.n;
     a.gx0 = 0.5 * (-0.5773502691896257) + 0.5;   // 0.5 * leggauss(2) + 0.5
     a.gx1 = 0.5 * (0.5773502691896257) + 0.5;
     if (coarse_solver == HFL_COARSE_FLUX_SCAN) {
-        int rc = hfl_fem_flux_scan(a, d_u, d_ws, ws_bytes, s);
+        int rc = hfl_fem_flux_scan(a, R, d_u, d_ws, ws_bytes, s);
         if (rc != HFL_OK) return rc;
     } else {
         const long long nt = fem_ntile(n);
@@ -420,22 +436,23 @@ static int fem_solve_impl(FemArgs a, int coarse_solver, double* d_u, double* d_i
         double* wsrows = utop + nt;
         double* yvw = wsrows + 6 * (size_t)nt;
         const int S = (int)((nt + TOPT - 1) / TOPT);
+        const dim3 grid((unsigned)nt, (unsigned)R);
         HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(11 * TOPT * sizeof(double))));
         if (a.aq != nullptr) {
             const size_t smem0 = (size_t)sm_total(true) * sizeof(double);
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            fem_reduce_kernel<true><<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
-            fem_top_kernel<<<1, TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
-            fem_backsub_kernel<true><<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+            fem_reduce_kernel<true><<<grid, FT, smem0, s>>>(a, rec, yvw);
+            fem_top_kernel<<<dim3(1, R), TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+            fem_backsub_kernel<true><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
         } else {
             const size_t smem0 = (size_t)sm_total(false) * sizeof(double);
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            fem_reduce_kernel<false><<<(unsigned)nt, FT, smem0, s>>>(a, rec, yvw);
-            fem_top_kernel<<<1, TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop);
-            fem_backsub_kernel<false><<<(unsigned)nt, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+            fem_reduce_kernel<false><<<grid, FT, smem0, s>>>(a, rec, yvw);
+            fem_top_kernel<<<dim3(1, R), TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+            fem_backsub_kernel<false><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
         }
         count_launch(3);
         HFL_CUDA_CHECK(cudaGetLastError());
@@ -461,8 +478,26 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
     const double pi = 3.14159265358979323846;
     FemArgs a;
     a.n = n; a.nodes = d_nodes; a.k = k_freq; a.kpi = k_freq * pi; a.kp2 = a.kpi * a.kpi; a.uL = u_left; a.uR = u_right;
+    a.aq = nullptr; a.cq = nullptr; a.fq = nullptr; a.kfreqs = nullptr; a.ws_stride = 0;
+    return fem_solve_impl(a, 1, coarse_solver, d_u, d_iface4, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int hfl_fem_p1_solve_multi(int64_t n, const double* d_nodes, int R, const double* d_k_freq, double u_left,
+                                      double u_right, int coarse_solver, double* d_u, void* d_ws, size_t ws_bytes,
+                                      void* stream) {
+    HFL_REQUIRE(n >= 2, "hfl_fem_p1_solve_multi: need at least 2 nodes (got %lld)", (long long)n);
+    HFL_REQUIRE(R >= 1 && R <= 65535, "hfl_fem_p1_solve_multi: R = %d outside 1..65535", R);
+    HFL_REQUIRE(d_nodes != nullptr && d_u != nullptr && d_k_freq != nullptr, "hfl_fem_p1_solve_multi: d_nodes / d_u / d_k_freq is NULL");
+    HFL_REQUIRE(coarse_solver == HFL_COARSE_ASSEMBLED_PCR || coarse_solver == HFL_COARSE_FLUX_SCAN,
+                "hfl_fem_p1_solve_multi: unknown coarse_solver %d", coarse_solver);
+    HFL_REQUIRE(d_ws != nullptr && ws_bytes >= hfl_fem_p1_multi_workspace_bytes(n, R),
+                "hfl_fem_p1_solve_multi: workspace too small (%zu < %zu)", ws_bytes, hfl_fem_p1_multi_workspace_bytes(n, R));
+    HFL_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "hfl_fem_p1_solve_multi: workspace must be 256-byte aligned");
+    FemArgs a;
+    a.n = n; a.nodes = d_nodes; a.k = 0.0; a.kpi = 0.0; a.kp2 = 0.0; a.uL = u_left; a.uR = u_right;
     a.aq = nullptr; a.cq = nullptr; a.fq = nullptr;
-    return fem_solve_impl(a, coarse_solver, d_u, d_iface4, d_ws, ws_bytes, (cudaStream_t)stream);
+    a.kfreqs = d_k_freq; a.ws_stride = (long long)fem_multi_stride_doubles(n);
+    return fem_solve_impl(a, R, coarse_solver, d_u, nullptr, d_ws, a.ws_stride * sizeof(double), (cudaStream_t)stream);
 }
 
 extern "C" int hfl_fem_p1_solve_general(int64_t n, const double* d_nodes, const double* d_aq, const double* d_cq,
@@ -475,8 +510,8 @@ extern "C" int hfl_fem_p1_solve_general(int64_t n, const double* d_nodes, const 
     HFL_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "hfl_fem_p1_solve_general: workspace must be 256-byte aligned");
     FemArgs a;
     a.n = n; a.nodes = d_nodes; a.k = 0.0; a.kpi = 0.0; a.kp2 = 0.0; a.uL = u_left; a.uR = u_right;
-    a.aq = d_aq; a.cq = d_cq; a.fq = d_fq;
-    return fem_solve_impl(a, HFL_COARSE_ASSEMBLED_PCR, d_u, nullptr, d_ws, ws_bytes, (cudaStream_t)stream);
+    a.aq = d_aq; a.cq = d_cq; a.fq = d_fq; a.kfreqs = nullptr; a.ws_stride = 0;
+    return fem_solve_impl(a, 1, HFL_COARSE_ASSEMBLED_PCR, d_u, nullptr, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int hfl_fem_apply_bc(int64_t n, const double* d_nodes, double* d_u, double bl, double br, void* stream) {

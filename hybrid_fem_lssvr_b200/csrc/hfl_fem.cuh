@@ -24,7 +24,20 @@ struct FemArgs {
     // general operator -(a u')' + c u = f: coefficient / forcing samples at the two Gauss points of every element,
     // [2][n-1] each (NULL = the reference's Poisson problem with the sine forcing family)
     const double* aq; const double* cq; const double* fq;
+    // several right-hand sides of the same mesh in one launch (hfl_fem_p1_solve_multi): grid.y = R, right-hand side
+    // r = blockIdx.y uses forcing frequency kfreqs[r], workspace slice r * ws_stride (doubles) and output row r * n
+    const double* kfreqs; long long ws_stride;
 };
+
+// The launch arguments specialised to this CTA's right-hand side (no-op for a single solve).
+__device__ __forceinline__ FemArgs select_rhs(FemArgs a) {
+    if (a.kfreqs != nullptr) {
+        a.k = __ldg(a.kfreqs + blockIdx.y);
+        a.kpi = __dmul_rn(a.k, 3.14159265358979323846);      // the same two roundings as the host does for one solve
+        a.kp2 = __dmul_rn(a.kpi, a.kpi);
+    }
+    return a;
+}
 
 // Row representation used by every elimination below: (l, sigma, r, b) with sigma = l + d + r the ROW SUM, the
 // diagonal being recovered as d = sigma - l - r.  For this M-matrix l, r <= 0 and sigma is tiny (exactly the

@@ -66,8 +66,10 @@ __device__ __forceinline__ Tri cta_exclusive_scan(Tri v, double* sm, Tri& total)
     return ex;
 }
 
-__global__ void __launch_bounds__(FT, 4) flux_tile_kernel(const FemArgs a, double* __restrict__ agg3) {
+__global__ void __launch_bounds__(FT, 4) flux_tile_kernel(const FemArgs a_in, double* __restrict__ agg3) {
     extern __shared__ double sm[];
+    const FemArgs a = select_rhs(a_in);
+    agg3 += (size_t)blockIdx.y * a.ws_stride;
     Tri inc[FS], agg, total;
     tile_local(a, (long long)blockIdx.x * FTS, sm, inc, agg);
     cta_exclusive_scan<FT>(agg, sm + FLUX_SCAN, total);
@@ -80,9 +82,10 @@ __global__ void __launch_bounds__(FT, 4) flux_tile_kernel(const FemArgs a, doubl
 
 // One CTA: exclusive scan of the tile aggregates; out: prefix per tile [3 * nt], q0 at prefix[3 * nt].
 __global__ void __launch_bounds__(TOPT) flux_top_kernel(const double* __restrict__ agg3, int nt, int S, double uL,
-                                                        double uR, double* __restrict__ prefix) {
+                                                        double uR, double* __restrict__ prefix, long long ws_stride) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
+    agg3 += (size_t)blockIdx.y * ws_stride; prefix += (size_t)blockIdx.y * ws_stride;
     Tri acc{0.0, 0.0, 0.0};
     for (int i = 0; i < S; ++i) {
         const int c = t * S + i;
@@ -100,10 +103,12 @@ __global__ void __launch_bounds__(TOPT) flux_top_kernel(const double* __restrict
     if (t == 0) prefix[3 * (size_t)nt] = (uR - uL + total.d) / total.c;
 }
 
-__global__ void __launch_bounds__(FT, 4) flux_apply_kernel(const FemArgs a, const double* __restrict__ prefix, int nt,
+__global__ void __launch_bounds__(FT, 4) flux_apply_kernel(const FemArgs a_in, const double* __restrict__ prefix, int nt,
                                                         double* __restrict__ u) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
+    const FemArgs a = select_rhs(a_in);
+    prefix += (size_t)blockIdx.y * a.ws_stride; u += (size_t)blockIdx.y * a.n;
     const long long P = (long long)blockIdx.x * FTS;
     Tri inc[FS], agg, total;
     tile_local(a, P, sm, inc, agg);
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(FT, 4) flux_apply_kernel(const FemArgs a, cons
 
 using namespace hfl;
 
-int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+int hfl_fem_flux_scan(const FemArgs& a, int R, double* d_u, void* d_ws, size_t ws_bytes, cudaStream_t s) {
     const long long nt = (a.n - 1 + FTS - 1) / FTS;   // tiles of elements
     if (nt > (long long)TOPT * TOP_MAX_CHUNK) {
         set_error("hfl_fem_p1_solve: %lld nodes exceed the single-call limit; split the mesh across GPUs", a.n);
@@ -148,9 +153,10 @@ int hfl_fem_flux_scan(const FemArgs& a, double* d_u, void* d_ws, size_t ws_bytes
         HFL_CUDA_CHECK(cudaFuncSetAttribute(flux_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int S = (int)((nt + TOPT - 1) / TOPT);
-    flux_tile_kernel<<<(unsigned)nt, FT, smem, s>>>(a, agg3);
-    flux_top_kernel<<<1, TOPT, 3 * TOPT * sizeof(double), s>>>(agg3, (int)nt, S, a.uL, a.uR, prefix);
-    flux_apply_kernel<<<(unsigned)nt, FT, smem, s>>>(a, prefix, (int)nt, d_u);
+    const dim3 grid((unsigned)nt, (unsigned)R);
+    flux_tile_kernel<<<grid, FT, smem, s>>>(a, agg3);
+    flux_top_kernel<<<dim3(1, R), TOPT, 3 * TOPT * sizeof(double), s>>>(agg3, (int)nt, S, a.uL, a.uR, prefix, a.ws_stride);
+    flux_apply_kernel<<<grid, FT, smem, s>>>(a, prefix, (int)nt, d_u);
     count_launch(3);
     HFL_CUDA_CHECK(cudaGetLastError());
     return HFL_OK;

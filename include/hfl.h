@@ -70,6 +70,15 @@ int hfl_fem_p1_solve(int64_t n_nodes, const double* d_nodes, double k_freq,
                      double* d_u, double* d_iface4,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* R solves on the same mesh in one launch sequence, one forcing frequency each (BASELINE configs[4]: the nodal data
+ * of hfl_lssvr_dual_multi; R calls of solve_fem P:117-145 with rhs (k pi)^2 sin(k pi x)): d_k_freq [R] (device),
+ * d_u [R][n_nodes].  Each row is bit-identical to hfl_fem_p1_solve with that k_freq.  1 <= R <= 65535.
+ * Workspace: hfl_fem_p1_multi_workspace_bytes(n, R) bytes, 256-byte aligned. */
+size_t hfl_fem_p1_multi_workspace_bytes(int64_t n_nodes, int R);
+int hfl_fem_p1_solve_multi(int64_t n_nodes, const double* d_nodes, int R, const double* d_k_freq,
+                           double u_left, double u_right, int coarse_solver,
+                           double* d_u, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Coarse P1 solve of the general operator -(a u')' + c u = f (stiffness of a, mass matrix of c, load of f, each by
  * the same 2-point Gauss rule): d_aq, d_cq, d_fq are samples [2][n-1] at the two Gauss points
  * x_e + h_e (1/2 -+ 1/(2 sqrt 3)) of every element (d_cq may be NULL = 0).  Assembled partition + PCR solver in

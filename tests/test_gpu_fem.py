@@ -50,6 +50,21 @@ def test_jittered_mesh_and_dirichlet_data(solver, n):
     assert np.max(np.abs(u - ref)) <= 1e-10
 
 
+@pytest.mark.parametrize('solver', ['assembled', 'flux'])
+@pytest.mark.parametrize('n,R', [(2, 3), (25, 1), (2049, 5), (10001, 64)])
+def test_multi_rhs_rows_equal_single_solves(solver, n, R):
+    """hfl_fem_p1_solve_multi: row r is bit-identical to the single solve with k_freqs[r] (BASELINE configs[4])."""
+    nodes = dev(jittered_mesh(n - 1, seed=n) if n > 2 else np.array([-1.0, 1.0]))
+    ks = torch.tensor([0.5 + 1.25 * r for r in range(R)], dtype=torch.float64, device='cuda')
+    u = batch.fem_p1_solve_multi(nodes, ks, u_left=0.25, u_right=-0.5, coarse_solver=solver)
+    assert u.shape == (R, n)
+    for r in range(R):
+        one = batch.fem_p1_solve(nodes, k_freq=float(ks[r]), u_left=0.25, u_right=-0.5, coarse_solver=solver)
+        assert torch.equal(u[r], one), (solver, n, r)
+    with pytest.raises(Exception):
+        batch.fem_p1_solve_multi(nodes, ks, out=torch.empty(R * n + 1, dtype=torch.float64, device='cuda'))
+
+
 def test_large_mesh_reported_spread():
     """Beyond ~1e4 nodes FP64 solvers disagree with each other on identical data.  The row-sum (GTH) elimination
     of the assembled solve stays ~1e-14 from the exact solution of the reference's rounded system, so it must be
