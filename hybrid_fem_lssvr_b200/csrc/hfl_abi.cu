@@ -80,8 +80,9 @@ extern "C" int hfl_set_option(const char* key, int value) {
         g_opt_store.store(value);
         return HFL_OK;
     }
-    if (strcmp(key, "dual_team") == 0) {   // 1 = skip the register kernel; 2 = also skip the parity-split team kernel
-        HFL_REQUIRE(value >= 0 && value <= 2, "dual_team must be 0..2");
+    // 1 = skip the N = 12 register kernel; 2 = also skip the parity-split kernels; 3 = parity split in shared memory only
+    if (strcmp(key, "dual_team") == 0) {
+        HFL_REQUIRE(value >= 0 && value <= 3, "dual_team must be 0..3");
         g_opt_dual_team.store(value);
         return HFL_OK;
     }
@@ -227,6 +228,10 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
     p->off_fineE = push(p->fineE); p->off_fineO = push(p->fineO); p->off_D2 = push(p->D2); p->off_V = push(p->V);
     p->off_Ct = push(p->Ct); p->off_K0 = push(p->K0);
     p->off_D0 = push(p->D0); p->off_D1 = push(p->D1);
+    p->Vt.assign(p->V.size(), 0.0);
+    for (int i = 0; i < (F > 0 ? F : 0); ++i)
+        for (int k = 0; k < M; ++k) p->Vt[(size_t)k * F + i] = p->V[(size_t)i * M + k];
+    p->off_Vt = push(p->Vt);
     p->off_Cpe = push(p->Cpe); p->off_Cpo = push(p->Cpo); p->off_Kpe = push(p->Kpe); p->off_Kpo = push(p->Kpo);
     p->n_tables = blk.size();
     cudaError_t e = cudaMalloc((void**)&p->d_tables, blk.size() * sizeof(double));

@@ -59,6 +59,7 @@ struct hfl_plan {
     std::vector<double> D2;     // [N][M]  P_k''(xi_j)
     std::vector<double> D0, D1; // [N][M]  P_k(xi_j), P_k'(xi_j)  (general operators)
     std::vector<double> V;      // [F][M]  P_k(xi_i)
+    std::vector<double> Vt;     // [M][F]  the same, transposed (coalesced reads with one thread per fine point)
     std::vector<double> Ct;     // [N+2][M] rows -P_k''(xi_j) (j < N), then (-1)^k, then 1: the scaled [A; B]
     std::vector<double> K0;     // [N+2][N+2] Ct Ct^T (dual kernel matrix without the tau I block)
     // Parity blocks of the dual system (even N): nh = N/2 + 1 rows {-P''_k(xi+_j), j < N/2; 1}, even / odd k
@@ -66,5 +67,5 @@ struct hfl_plan {
     std::vector<double> Kpe, Kpo;   // [nh][nh] Cp Cp^T
     // Device block holding all of the above back to back
     double* d_tables = nullptr;
-    size_t off_De, off_Do, off_Ge, off_Go, off_fineE, off_fineO, off_D2, off_V, off_Ct, off_K0, off_Cpe, off_Cpo, off_Kpe, off_Kpo, off_D0, off_D1, n_tables;
+    size_t off_De, off_Do, off_Ge, off_Go, off_fineE, off_fineO, off_D2, off_V, off_Ct, off_K0, off_Cpe, off_Cpo, off_Kpe, off_Kpo, off_D0, off_D1, off_Vt, n_tables;
 };

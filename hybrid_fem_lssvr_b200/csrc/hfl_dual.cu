@@ -17,31 +17,9 @@
 // factorisation is right-looking with the trailing update spread over the team.  Right-hand sides (R
 // forcing frequencies per element, BASELINE configs[4]) share the factorisation: thread r solves RHS r
 // with broadcast reads of L, then the whole team evaluates the R x F fine values.
-#include "hfl_device.cuh"
+#include "hfl_dual.cuh"
 
 namespace hfl {
-
-struct DualArgs {
-    long long E;
-    int R;                  // right-hand sides per element
-    const double* nodes;    // [E+1]
-    const double* u;        // [R][E+1]
-    const double* f;        // samples [R][N][E] or NULL
-    const double* kf;       // [R] forcing frequencies (device) or NULL -> k_scalar
-    double k_scalar;
-    const double* bc2;      // optional {bc_left, bc_right}
-    double* coef;           // optional [R][E][M]
-    double* fine;           // optional [R][E][F]
-    int* status;            // optional [E]
-    double* err3;           // optional [R][3]
-    const double* K0;       // [n][n]
-    const double* Ct;       // [n][M]
-    const double* V;        // [F][M]
-    int M, N, F, n, ld;
-    int forcing;
-    double c_tau;           // 1 / (16 gamma)
-    bool want_err;
-};
 
 template <int TS>
 __device__ __forceinline__ void team_sync() {
@@ -71,7 +49,6 @@ __device__ __forceinline__ void team_argmax(double& v, int& idx, double* red) {
     }
 }
 
-constexpr int DUAL_NMAX = 160 + 2;     // largest system this kernel holds in shared memory
 
 template <int TS>
 __global__ void __launch_bounds__(TS == 32 ? 128 : TS) dual_kernel(const DualArgs a) {
@@ -244,12 +221,6 @@ __global__ void __launch_bounds__(TS == 32 ? 128 : TS) dual_kernel(const DualArg
 // factorises the even block, team 1 the odd one, concurrently (named barriers); the R right-hand sides are solved
 // one per thread inside each team; the whole CTA then evaluates the R x F fine values.  Compared with the
 // full-system kernel above: 4x fewer flops per pivot step, half the pivot steps per team, half the shared memory.
-struct DualParityArgs {
-    DualArgs d;
-    const double* Kp[2];    // [nh][nh] per parity
-    const double* Cp[2];    // [nh][MA] per parity
-    int nh, ldh, MA[2];
-};
 
 __device__ __forceinline__ void half_sync(int team) {
     asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory");
@@ -476,6 +447,12 @@ static int launch_dual(const hfl_plan* plan, long long E, int R, const double* d
         pa.Kp[0] = plan->d_tables + plan->off_Kpe; pa.Kp[1] = plan->d_tables + plan->off_Kpo;
         pa.Cp[0] = plan->d_tables + plan->off_Cpe; pa.Cp[1] = plan->d_tables + plan->off_Cpo;
         pa.MA[0] = n_even(plan->M) + 1; pa.MA[1] = n_odd(plan->M) + 1;
+        pa.Vt = plan->d_tables + plan->off_Vt;
+        if (get_option_dual_team() != 3 && launch_dual_parity_left(pa, max_smem, s)) {   // left-looking kernel (nh <= 96)
+            count_launch();
+            HFL_CUDA_CHECK(cudaGetLastError());
+            return HFL_OK;
+        }
         const size_t td = (size_t)pa.nh * pa.ldh + pa.nh + 8;
         const size_t tb = ((td * 8 + (size_t)(pa.nh + 2) * 4) + 15) / 16 * 16;
         const size_t smem = 2 * tb + ((size_t)R * a.M + 2 * (size_t)R) * 8;

@@ -72,10 +72,10 @@ def test_dual_matches_primal_kernel_full_size():
     assert mx <= 1e-10
 
 
-@pytest.mark.parametrize('M,team', [(5, 0), (9, 0), (13, 0), (17, 0), (21, 0), (25, 0), (9, 2), (25, 2)])
+@pytest.mark.parametrize('M,team', [(5, 0), (9, 0), (13, 0), (17, 0), (21, 0), (25, 0), (9, 2), (25, 2), (9, 3), (25, 3)])
 def test_large_system_multi_rhs(M, team):
-    """BASELINE configs[4]: N = 128, R forcing frequencies sharing one factorisation.  team = 0: parity-split
-    team kernel (two 65 x 65 blocks); team = 2: full 130 x 130 system kernel."""
+    """BASELINE configs[4]: N = 128, R forcing frequencies sharing one factorisation.  team = 0: left-looking parity
+    kernel (two 65 x 65 blocks); 3: parity split in shared memory; 2: full 130 x 130 system kernel."""
     E, N, F, gamma, R = 64, 128, 32, 1e4, 8
     batch.set_option('dual_team', team)
     nodes = np.linspace(-1, 1, E + 1) * 0.01 + 0.3          # h = 3.1e-4: k h <= 0.02, resolved for every k
@@ -98,6 +98,38 @@ def test_large_system_multi_rhs(M, team):
         assert rel(fine[r].cpu().numpy(), fp) <= dual_tol(kkt.evaluate_fine(ref_d, F), fp[sl]), (M, k)
     e = err3.cpu().numpy()
     assert np.all(e[:, 1] < 1e-6) and np.all(e[:, 2] == 0)
+
+
+@pytest.mark.parametrize('N,M', [(32, 7), (64, 9), (70, 6), (128, 12), (136, 9), (160, 10)])
+@pytest.mark.parametrize('scale', [1.0, 1e-3])
+def test_parity_left_looking_sizes(N, M, scale):
+    """The left-looking parity kernel (default for even N with N + 2 > 32) on a coarse mesh (tau not negligible: every pivot is taken, rank = N/2 + 1) and on a fine one (early stop at the
+    numerical rank), sine forcing and sampled forcing with the boundary correction: same answers as the
+    shared-memory parity kernel and within the dual tolerance of the primal oracle."""
+    E, F, gamma = 37, 32, 1e4
+    rng = np.random.default_rng(N + M)
+    nodes = jittered_mesh(E, seed=N) * scale + 0.1
+    u = np.sin(np.pi * nodes) + 0.1 * rng.uniform(-1, 1, E + 1) * scale ** 2
+    fs = np.exp(np.linspace(nodes[:-1], nodes[1:], N, axis=0))
+    bc2 = torch.tensor([0.25, -0.5], dtype=torch.float64, device='cuda')
+    ub = u + (0.25 * (nodes[-1] - nodes) - 0.5 * (nodes - nodes[0])) / (nodes[-1] - nodes[0])
+    out = {}
+    for team in (0, 3):
+        batch.set_option('dual_team', team)
+        try:
+            out[team] = (_run_dual(nodes, u, M, gamma, N=N, F=F, k=1.0), _run_dual(nodes, u, M, gamma, N=N, F=F, samples=fs, bc2=bc2))
+        finally:
+            batch.set_option('dual_team', 0)
+    for which, ref in ((0, oracle_coef(nodes, u, M, gamma, N, k=1.0)), (1, oracle_coef(nodes, ub, M, gamma, N, f_samples=fs))):
+        fp = kkt.evaluate_fine(ref, F)
+        f_samp = sine_samples(nodes, N, 1.0).T.copy() if which == 0 else fs.T.copy()
+        ref_d = dual.lssvr_dual_batch(nodes, u if which == 0 else ub, f_samp, M, gamma)
+        tol = dual_tol(kkt.evaluate_fine(ref_d, F), fp)
+        coef, fine, status = out[0][which]
+        assert not status.any()
+        assert rel(fine, fp) <= tol, (N, M, scale, which, rel(fine, fp), tol)
+        assert rel(kkt.evaluate_fine(coef, F), fine) <= 1e-13
+        assert rel(fine, out[3][which][1]) <= tol
 
 
 def test_samples_forcing_and_boundary_correction():
