@@ -246,9 +246,28 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
     return HFL_OK;
 }
 
+double* hfl::plan_scratch(const hfl_plan* p, cudaStream_t s, size_t bytes) {
+    std::lock_guard<std::mutex> guard(p->scratch_mu);
+    auto& slot = p->scratch[s];
+    if (slot.second < bytes) {
+        if (slot.first) cudaFree(slot.first);      // synchronises: work queued on the old buffer finishes first
+        slot = {nullptr, 0};
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) {
+            set_error("plan scratch: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            return nullptr;
+        }
+        slot = {q, bytes};
+    }
+    return reinterpret_cast<double*>(slot.first);
+}
+
 extern "C" int hfl_plan_destroy(hfl_plan_t* p) {
     if (!p) return HFL_OK;
     if (p->d_tables) cudaFree(p->d_tables);
+    for (auto& kv : p->scratch)
+        if (kv.second.first) cudaFree(kv.second.first);
     delete p;
     return HFL_OK;
 }

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/hfl.h"
@@ -67,5 +69,14 @@ struct hfl_plan {
     std::vector<double> Kpe, Kpo;   // [nh][nh] Cp Cp^T
     // Device block holding all of the above back to back
     double* d_tables = nullptr;
+    // Scratch buffers owned by the plan, one per stream that asked for one (kernels on one stream serialise, so a
+    // buffer per stream is race-free); grown on demand, released by hfl_plan_destroy.
+    mutable std::mutex scratch_mu;
+    mutable std::map<cudaStream_t, std::pair<void*, size_t>> scratch;
     size_t off_De, off_Do, off_Ge, off_Go, off_fineE, off_fineO, off_D2, off_V, off_Ct, off_K0, off_Cpe, off_Cpo, off_Kpe, off_Kpo, off_D0, off_D1, off_Vt, n_tables;
 };
+
+namespace hfl {
+// At least `bytes` of device scratch tied to (plan, stream); NULL (and the error string set) when the allocation fails.
+double* plan_scratch(const hfl_plan* plan, cudaStream_t s, size_t bytes);
+}

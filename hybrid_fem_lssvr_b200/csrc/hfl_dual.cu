@@ -448,7 +448,7 @@ static int launch_dual(const hfl_plan* plan, long long E, int R, const double* d
         pa.Cp[0] = plan->d_tables + plan->off_Cpe; pa.Cp[1] = plan->d_tables + plan->off_Cpo;
         pa.MA[0] = n_even(plan->M) + 1; pa.MA[1] = n_odd(plan->M) + 1;
         pa.Vt = plan->d_tables + plan->off_Vt;
-        if (get_option_dual_team() != 3 && launch_dual_parity_left(pa, max_smem, s)) {   // left-looking kernel (nh <= 96)
+        if (get_option_dual_team() != 3 && launch_dual_parity_left(pa, max_smem, plan, s)) {   // left-looking kernel (nh <= 96)
             count_launch();
             HFL_CUDA_CHECK(cudaGetLastError());
             return HFL_OK;

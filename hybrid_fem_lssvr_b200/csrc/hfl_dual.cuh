@@ -35,10 +35,12 @@ struct DualParityArgs {
     const double* Cp[2];    // [nh][MA] per parity
     int nh, ldh, MA[2];
     const double* Vt;       // [M][F]
+    double* spill;          // left-looking kernel: global scratch for L columns kc.. (per CTA and team)
+    int kc;                 // L columns held in shared memory
 };
 
 // hfl_dual_parity.cu (left-looking parity kernel); returns false when the shape is not covered (nh > 96 or not
 // enough shared memory) and the caller falls back to the shared-memory right-looking kernel
-bool launch_dual_parity_left(const DualParityArgs& pa, int max_smem, cudaStream_t s);
+bool launch_dual_parity_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cudaStream_t s);
 
 }  // namespace hfl

@@ -38,27 +38,47 @@ __device__ __forceinline__ unsigned long long lt_max_key(unsigned long long key,
     return m > k2 ? m : k2;
 }
 
-// Shared memory per team: Lc [nh][ldl] (doubles), invl [nh], red [4] (64-bit); perm [nh] + rank (int).
-__host__ __device__ inline size_t lt_team_bytes(int nh, int ldl) {
-    return ((((size_t)nh * ldl + nh + 4) * 8 + (size_t)(nh + 2) * 4) + 15) / 16 * 16;
+__device__ __forceinline__ double lt_back_dot(const double* lk, const int* perm, const double* y, int k, int rank) {
+    double d0 = 0.0, d1 = 0.0;
+    int j = k + 1;
+    for (; j + 1 < rank; j += 2) {
+        d0 = fma(lk[perm[j]], y[j], d0);
+        d1 = fma(lk[perm[j + 1]], y[j + 1], d1);
+    }
+    if (j < rank) d0 = fma(lk[perm[j]], y[j], d0);
+    return d0 + d1;
 }
 
-__global__ void __launch_bounds__(2 * LT) dual_parity_left_kernel(const DualParityArgs pa) {
+// Shared memory per team: Lc [kc][ldl] (doubles; the first kc = min(nh, LT_KC) columns of L), invl [nh], red [4]
+// (64-bit); perm [nh] + rank (int).  Columns kc.. (only reached on coarse meshes, where tau keeps the block at full
+// rank) go to a per-CTA slice of a global scratch buffer: shared memory per CTA drops from 83 KB to 40 KB at N = 128
+// (5 resident CTAs per SM instead of 2), which is worth 1.6x on this latency-bound kernel.
+constexpr int LT_KC = 24;
+__host__ __device__ inline size_t lt_team_bytes(int nh, int ldl, int kc) {
+    return ((((size_t)kc * ldl + nh + 4) * 8 + (size_t)(nh + 2) * 4) + 15) / 16 * 16;
+}
+
+#ifndef HFL_DUAL_LEFT_MINB
+#define HFL_DUAL_LEFT_MINB 4      // <= 85 registers: 4 CTAs per SM (measured 2x faster than the uncapped build, same as 5)
+#endif
+__global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_kernel(const DualParityArgs pa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DualArgs& a = pa.d;
     const int nh = pa.nh, ldl = pa.ldh, M = a.M, N = a.N, NHc = N / 2, F = a.F, R = a.R;
     const int team = threadIdx.x / LT, row = threadIdx.x - team * LT;
-    const size_t team_bytes = lt_team_bytes(nh, ldl);
+    const int kc = pa.kc;
+    const size_t team_bytes = lt_team_bytes(nh, ldl, kc);
     unsigned char* base = smem_raw + team * team_bytes;
     double* Lc = reinterpret_cast<double*>(base);
-    double* invl = Lc + (size_t)nh * ldl;
+    double* invl = Lc + (size_t)kc * ldl;
+    double* Lg = pa.spill + ((size_t)blockIdx.x * 2 + team) * (size_t)(nh - kc) * ldl;   // columns kc.. (unused when kc = nh)
     unsigned long long* red = reinterpret_cast<unsigned long long*>(invl + nh);
     int* perm = reinterpret_cast<int*>(red + 4);
     int* rank_s = perm + nh;
     double* wbuf = reinterpret_cast<double*>(smem_raw + 2 * team_bytes);
     double* eacc = wbuf + (size_t)R * M;
     const int* rank_other = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw + (1 - team) * team_bytes) +
-                                                   (size_t)nh * ldl + nh + 4) + nh;
+                                                   (size_t)kc * ldl + nh + 4) + nh;
 
     double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
     if (a.bc2 != nullptr) {
@@ -101,24 +121,36 @@ __global__ void __launch_bounds__(2 * LT) dual_parity_left_kernel(const DualPari
             if (live_row) a0 = __ldg(Kp + (size_t)p * nh + row) + ((row == p && row < NHc) ? th : 0.0);   // symmetric table
             v0 = __ldg(Kp + (size_t)p * nh + p) + (p < NHc ? th : 0.0);
             const int rs = live_row ? row : 0;
+            const double* cp = Lc + p;             // column walkers: entry p / this row's entry of column j
+            const double* cr = Lc + rs;
+            const int ks = min(k, kc);             // columns held in shared memory
             int j = 0;
-            for (; j + 1 < k; j += 2) {
-                const double lp0 = Lc[(size_t)j * ldl + p], lp1 = Lc[(size_t)(j + 1) * ldl + p];
-                a0 = fma(-Lc[(size_t)j * ldl + rs], lp0, a0);
-                a1 = fma(-Lc[(size_t)(j + 1) * ldl + rs], lp1, a1);
+            for (; j + 1 < ks; j += 2, cp += 2 * ldl, cr += 2 * ldl) {
+                const double lp0 = cp[0], lp1 = cp[ldl];
+                a0 = fma(-cr[0], lp0, a0);
+                a1 = fma(-cr[ldl], lp1, a1);
                 v0 = fma(-lp0, lp0, v0);
                 v1 = fma(-lp1, lp1, v1);
             }
-            if (j < k) {
-                const double lp0 = Lc[(size_t)j * ldl + p];
-                a0 = fma(-Lc[(size_t)j * ldl + rs], lp0, a0);
+            if (j < ks) {
+                const double lp0 = cp[0];
+                a0 = fma(-cr[0], lp0, a0);
                 v0 = fma(-lp0, lp0, v0);
+            }
+            for (j = kc; j < k; ++j) {             // spilled columns
+                const double* g = Lg + (size_t)(j - kc) * ldl;
+                const double lp0 = g[p];
+                a1 = fma(-g[rs], lp0, a1);
+                v1 = fma(-lp0, lp0, v1);
             }
             const double v = v0 + v1;
             if (!(v > 0.0)) break;                  // team-uniform: the tracked diagonal overestimated a vanishing pivot
             const double il = rsqrt(v);
             const double l = alive ? (a0 + a1) * il : 0.0;
-            if (live_row) Lc[(size_t)k * ldl + row] = l;
+            if (live_row) {
+                if (k < kc) Lc[(size_t)k * ldl + row] = l;
+                else Lg[(size_t)(k - kc) * ldl + row] = l;
+            }
             dii = fma(-l, l, dii);
             if (row == p) { alive = false; perm[k] = p; invl[k] = il; }
             rank = k + 1;
@@ -163,27 +195,25 @@ __global__ void __launch_bounds__(2 * LT) dual_parity_left_kernel(const DualPari
                         b = gpar;
                     }
                     double b1 = 0.0;
+                    const double* cp = Lc + pk;                                  // L[pk][j] = column j, entry pk
+                    const int ks = min(k, kc);
                     int j = 0;
-                    for (; j + 1 < k; j += 2) {
-                        b = fma(-Lc[(size_t)j * ldl + pk], y[j], b);                   // L[pk][j]
-                        b1 = fma(-Lc[(size_t)(j + 1) * ldl + pk], y[j + 1], b1);
+                    for (; j + 1 < ks; j += 2, cp += 2 * ldl) {
+                        b = fma(-cp[0], y[j], b);
+                        b1 = fma(-cp[ldl], y[j + 1], b1);
                     }
-                    if (j < k) b = fma(-Lc[(size_t)j * ldl + pk], y[j], b);
+                    if (j < ks) b = fma(-cp[0], y[j], b);
+                    for (j = kc; j < k; ++j) b1 = fma(-Lg[(size_t)(j - kc) * ldl + pk], y[j], b1);
                     y[k] = (b + b1) * invl[k];
                 }
                 double wq[LMAXMA];
 #pragma unroll
                 for (int q = 0; q < LMAXMA; ++q) wq[q] = 0.0;
                 for (int k = rank - 1; k >= 0; --k) {                      // L^T z = y, and w += C[perm[k]][:] z_k on the way
-                    const double* lk = Lc + (size_t)k * ldl;
-                    double b = y[k], b1 = 0.0;
-                    int j = k + 1;
-                    for (; j + 1 < rank; j += 2) {
-                        b = fma(-lk[perm[j]], y[j], b);                                 // L[perm[j]][k]
-                        b1 = fma(-lk[perm[j + 1]], y[j + 1], b1);
-                    }
-                    if (j < rank) b = fma(-lk[perm[j]], y[j], b);
-                    const double zk = (b + b1) * invl[k];
+                    // sum_j L[perm[j]][k] z_j over the later pivots; the two call sites keep the address space static
+                    const double dot = k < kc ? lt_back_dot(Lc + (size_t)k * ldl, perm, y, k, rank)
+                                              : lt_back_dot(Lg + (size_t)(k - kc) * ldl, perm, y, k, rank);
+                    const double zk = (y[k] - dot) * invl[k];
                     y[k] = zk;
                     const double* crow = Cp + (size_t)perm[k] * MA;
 #pragma unroll
@@ -205,9 +235,9 @@ __global__ void __launch_bounds__(2 * LT) dual_parity_left_kernel(const DualPari
                 for (int idx = threadIdx.x; idx < rb * F; idx += 2 * LT) {
                     const int rr = idx / F, i = idx - rr * F;
                     const double* w = wbuf + (size_t)(r0 + rr) * M;
-                    const double* vt = pa.Vt + i;
+                    const double* vt = pa.Vt + i + (size_t)(M - 1) * F;
                     double s = 0.0;
-                    for (int mm = M - 1; mm >= 0; --mm) s = fma(w[mm], __ldg(vt + (size_t)mm * F), s);
+                    for (int mm = M - 1; mm >= 0; --mm, vt -= F) s = fma(w[mm], __ldg(vt), s);
                     if (a.fine != nullptr) a.fine[((long long)(r0 + rr) * a.E + e) * F + i] = s;
                     if (a.want_err) {
                         const double kf = a.kf ? a.kf[r0 + rr] : a.k_scalar;
@@ -234,10 +264,18 @@ __global__ void __launch_bounds__(2 * LT) dual_parity_left_kernel(const DualPari
     }
 }
 
-bool launch_dual_parity_left(const DualParityArgs& pa, int max_smem, cudaStream_t s) {
+int dual_parity_left_kc(int nh) { return nh < LT_KC ? nh : LT_KC; }
+
+// Doubles of spill scratch the launch needs: grid x 2 teams x (nh - kc) columns.  0 when every column fits.
+size_t dual_parity_left_spill_doubles(int nh, int ldh, long long max_grid) {
+    return (size_t)max_grid * 2 * (size_t)(nh - dual_parity_left_kc(nh)) * ldh;
+}
+
+bool launch_dual_parity_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cudaStream_t s) {
     const DualArgs& a = pa.d;
     if (pa.nh > LT || pa.MA[0] > LMAXMA || pa.MA[1] > LMAXMA) return false;
-    const size_t smem = 2 * lt_team_bytes(pa.nh, pa.ldh) + ((size_t)a.R * a.M + 2 * (size_t)a.R) * 8;
+    pa.kc = dual_parity_left_kc(pa.nh);
+    const size_t smem = 2 * lt_team_bytes(pa.nh, pa.ldh, pa.kc) + ((size_t)a.R * a.M + 2 * (size_t)a.R) * 8;
     if (smem > (size_t)max_smem) return false;
     if (cudaFuncSetAttribute(dual_parity_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return false;
@@ -247,6 +285,11 @@ bool launch_dual_parity_left(const DualParityArgs& pa, int max_smem, cudaStream_
     long long grid = a.E;
     const long long cap = (long long)sm_count() * per_sm;
     if (grid > cap) grid = cap;
+    pa.spill = nullptr;
+    if (pa.kc < pa.nh) {
+        pa.spill = plan_scratch(plan, s, dual_parity_left_spill_doubles(pa.nh, pa.ldh, grid) * sizeof(double));
+        if (pa.spill == nullptr) return false;
+    }
     dual_parity_left_kernel<<<(unsigned)grid, 2 * LT, smem, s>>>(pa);
     return true;
 }

@@ -9,9 +9,11 @@ ks = torch.arange(1, R + 1, dtype=torch.float64, device='cuda')
 u = batch.fem_p1_solve_multi(nodes, ks, coarse_solver='flux')
 for M in Ms:
     fn = lambda: batch.lssvr_dual_multi(nodes, u, ks, M, 1e4, N=128, F=32, want_coef=False, want_fine=True)
-    fn(); torch.cuda.synchronize()
-    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(3): fn()
-    b.record(); torch.cuda.synchronize()
-    print('M=%d  %.4f ms' % (M, a.elapsed_time(b) / 3))
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    ts.sort()
+    print('M=%d  best %.4f ms  median %.4f ms' % (M, ts[0], ts[len(ts) // 2]))
