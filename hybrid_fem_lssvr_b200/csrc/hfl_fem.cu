@@ -209,15 +209,18 @@ __device__ __forceinline__ void thomas_step(double l, double sg, double r, doubl
 }
 
 // Top level: solve the system of tile heads.  One CTA of TOPT threads, chunk of S heads per thread.
-// ws: rows l, sigma, r, b [4][cnt] followed by Thomas scratch c', b' [2][cnt].
+// SMEM_ROWS: the rows (l, sigma, r, b) [4][cnt] live in shared memory behind the 8 * TOPT doubles of PCR buffers
+// (small meshes, see the launch); otherwise in the workspace (wsrows).  The chunk sweeps walk their rows with
+// dependent loads, so the shared-memory variant removes ~4 S L2 round trips from this serial kernel.
+template <bool SMEM_ROWS>
 __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict__ rec, int cnt, int S,
                                                        double* __restrict__ wsrows, double* __restrict__ utop,
                                                        long long ws_stride) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
     rec += (size_t)blockIdx.y * ws_stride; wsrows += (size_t)blockIdx.y * ws_stride; utop += (size_t)blockIdx.y * ws_stride;
-    double* rl = wsrows; double* rs = wsrows + cnt; double* rr = wsrows + 2 * (size_t)cnt; double* rb = wsrows + 3 * (size_t)cnt;
-    double* tc = wsrows + 4 * (size_t)cnt; double* tb = wsrows + 5 * (size_t)cnt;
+    double* rowbase = SMEM_ROWS ? sm + 8 * TOPT : wsrows;
+    double* rl = rowbase; double* rs = rowbase + cnt; double* rr = rowbase + 2 * (size_t)cnt; double* rb = rowbase + 3 * (size_t)cnt;
     for (int c = t; c < cnt; c += TOPT) {
         const double* rc = rec + (size_t)c * REC;
         double l = 0.0, sg = rc[1], b = rc[3];
@@ -240,8 +243,8 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
     chunk_reduce(rows, t * S, S, e8);
     double lp, sp, rp, bp;
     rows.get(t * S, lp, sp, rp, bp);
-    double* ex = sm;                 // 3 * TOPT
-    double* pcr = sm + 3 * TOPT;     // 2 * 4 * TOPT
+    double* pcr = sm;                // 2 * 4 * TOPT
+    double* ex = sm + 4 * TOPT;      // 3 * TOPT, inside the second PCR buffer: consumed before PCR first writes there
     ex[0 * TOPT + t] = e8[4]; ex[1 * TOPT + t] = e8[5]; ex[2 * TOPT + t] = e8[7];
     __syncthreads();
     double l = 0.0, sg = 1.0, r = 0.0, rhs[1] = {0.0}, x[1];
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
         head_equation(0.0, sp - lp, rp, bp, 0.0, 0.0, 0.0, e8, l, sg, r, rhs[0]);
     }
     pcr_solve<1, TOPT>(pcr, t, 0, TOPT - 1, l, sg, r, rhs, x);
-    double* uh = ex;   // head values, reuse
+    double* uh = sm;   // head values; the PCR buffers are dead
     __syncthreads();
     uh[t] = x[0];
     __syncthreads();
@@ -261,19 +264,20 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
     if (S >= 2 && m0 + 1 < cnt) {
         const double ua = x[0];
         const double ub = (t + 1 < TOPT) ? uh[t + 1] : 0.0;
-        // Thomas on rows m0+1 .. m0+S-1 with known neighbours
+        // Thomas on rows m0+1 .. m0+S-1 with known neighbours; c', b' stay thread-private
+        double tc[TOP_MAX_CHUNK], tb[TOP_MAX_CHUNK];
         double lo, so, ro, bo, q = 1.0, cp = 0.0, bpv = ua;     // "previous row" = the known head: x = ua
         for (int i = 1; i < S; ++i) {
             rows.get(m0 + i, lo, so, ro, bo);
             if (i == S - 1) bo = fma(-ro, ub, bo);
             thomas_step(lo, so, ro, bo, q, cp, bpv);
-            if (m0 + i < cnt) { tc[m0 + i] = cp; tb[m0 + i] = bpv; }
+            tc[i] = cp; tb[i] = bpv;
         }
         double xv = bpv;
         if (m0 + S - 1 < cnt) utop[m0 + S - 1] = xv;
         for (int i = S - 2; i >= 1; --i) {
             if (m0 + i < cnt) {
-                xv = tb[m0 + i] - tc[m0 + i] * xv;
+                xv = tb[i] - tc[i] * xv;
                 utop[m0 + i] = xv;
             } else {
                 xv = 0.0;   // padded identity rows
@@ -437,21 +441,33 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
         double* yvw = wsrows + 6 * (size_t)nt;
         const int S = (int)((nt + TOPT - 1) / TOPT);
         const dim3 grid((unsigned)nt, (unsigned)R);
-        HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(11 * TOPT * sizeof(double))));
+        // top level: rows in shared memory while the CTA stays within the shared-memory carve-out the level-0 kernels
+        // already use (<= 96 KB, ~1000 tiles = 2e6 nodes).  Asking for more (220 KB would hold 1e7 nodes) costs more
+        // in the carve-out switch between kernels than the saved L2 round trips: measured +17 us at 1e7 nodes.
+        const size_t top_small = 8 * TOPT * sizeof(double), top_rows = top_small + 4 * (size_t)nt * sizeof(double);
+        const bool top_in_smem = top_rows <= 96 * 1024;
+        const size_t top_smem = top_in_smem ? top_rows : top_small;
+        if (top_in_smem)
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_smem));
+        else
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_smem));
+        auto launch_top = [&]() {
+            if (top_in_smem) fem_top_kernel<true><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+            else fem_top_kernel<false><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+        };
         if (a.aq != nullptr) {
             const size_t smem0 = (size_t)sm_total(true) * sizeof(double);
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             fem_reduce_kernel<true><<<grid, FT, smem0, s>>>(a, rec, yvw);
-            fem_top_kernel<<<dim3(1, R), TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+            launch_top();
             fem_backsub_kernel<true><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
         } else {
             const size_t smem0 = (size_t)sm_total(false) * sizeof(double);
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
             fem_reduce_kernel<false><<<grid, FT, smem0, s>>>(a, rec, yvw);
-            fem_top_kernel<<<dim3(1, R), TOPT, 11 * TOPT * sizeof(double), s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+            launch_top();
             fem_backsub_kernel<false><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
         }
         count_launch(3);
