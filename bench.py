@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--elements', type=int, default=10 ** 7, help='elements per GPU')
     ap.add_argument('--error', default='fused', choices=['fused', 'separate', 'none'])
-    ap.add_argument('--coarse', default='assembled', choices=['assembled', 'flux'])
+    ap.add_argument('--coarse', default='assembled', choices=['assembled', 'assembled_exact', 'flux'])
     ap.add_argument('--store', type=int, default=0, help='primal store path: 0 auto, 1 direct, 2 smem, 3 tma')
     ap.add_argument('--cpu-sample', type=int, default=0, help='elements in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu', action='store_true')
@@ -213,10 +213,13 @@ def run_ours(args):
     results = {}
     err_all = torch.empty((world, 3), dtype=torch.float64, device=dev)
 
+    # partitioned solve: same partition + PCR kernels on the unrounded diagonal (include/hfl.h, HFL_COARSE_ASSEMBLED_EXACT)
+    coarse_dist = 'assembled_exact' if args.coarse == 'assembled' else args.coarse
+
     def step():
         err3.zero_()
         if world > 1:
-            _, bc2 = hdist.fem_p1_solve_distributed(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u)
+            _, bc2 = hdist.fem_p1_solve_distributed(nodes, k_freq=KFREQ, coarse_solver=coarse_dist, out=u)
         else:
             batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u)
             bc2 = None
@@ -392,7 +395,7 @@ def run_ours(args):
             'config': {'workload': 'BASELINE configs[2]: primal LSSVR, %d elements/GPU, M=9 (degree 8), N=12, F=32, '
                                    'uniform mesh on [-1,1], forcing pi^2 sin(pi x) on device; step = K1 coarse solve '
                                    '(%s) + K2/K3 element solves with fine grid + K5 error norms (%s)'
-                                   % (E, args.coarse, args.error),
+                                   % (E, args.coarse if world == 1 else coarse_dist + ' + SPIKE interface exchange', args.error),
                        'elements_per_gpu': E, 'elements_total': E_global, 'M': M, 'N_colloc': NCOL, 'F': F, 'gamma': GAMMA,
                        'parallelism': 'contiguous element ranges x%d' % world,
                        'l2_policy': 'inputs (160 MB) + outputs (2.56 GB) per step exceed the 126 MB L2; no explicit flush',

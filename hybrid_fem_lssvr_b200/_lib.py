@@ -13,6 +13,7 @@ FORCING_SINE = 0
 FORCING_SAMPLES = 1
 COARSE_ASSEMBLED_PCR = 0
 COARSE_FLUX_SCAN = 1
+COARSE_ASSEMBLED_EXACT = 2
 MAX_M, MAX_N, MAX_F = 32, 256, 256
 
 

@@ -78,6 +78,12 @@ def _workspace(nbytes, device):
     return ws
 
 
+# 'assembled': the reference's rounded tridiagonal system (partition + PCR); 'assembled_exact': the same kernels on the
+# unrounded diagonal (zero row sums); 'flux': first-order form by prefix sums.  See include/hfl.h.
+COARSE_MODES = {'assembled': _lib.COARSE_ASSEMBLED_PCR, 'pcr': _lib.COARSE_ASSEMBLED_PCR,
+                'flux': _lib.COARSE_FLUX_SCAN, 'assembled_exact': _lib.COARSE_ASSEMBLED_EXACT}
+
+
 def fem_p1_solve(nodes, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='assembled', out=None,
                  want_reaction=False):
     """K1: nodal values of the coarse P1 FEM solve (P:117-145) for -u'' = (k pi)^2 sin(k pi x).
@@ -88,8 +94,7 @@ def fem_p1_solve(nodes, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='asse
     _require_cuda_f64(nodes, 'nodes')
     n = nodes.numel()
     lib = _lib.load()
-    mode = {'assembled': _lib.COARSE_ASSEMBLED_PCR, 'pcr': _lib.COARSE_ASSEMBLED_PCR,
-            'flux': _lib.COARSE_FLUX_SCAN}[coarse_solver]
+    mode = COARSE_MODES[coarse_solver]
     u = out if out is not None else torch.empty(n, dtype=torch.float64, device=nodes.device)
     _require_cuda_f64(u, 'out', n)
     nbytes = int(lib.hfl_fem_p1_workspace_bytes(n))
@@ -108,8 +113,7 @@ def fem_p1_solve_multi(nodes, k_freqs, u_left=0.0, u_right=0.0, coarse_solver='a
     R = k_freqs.numel()
     _require_cuda_f64(k_freqs, 'k_freqs', R)
     lib = _lib.load()
-    mode = {'assembled': _lib.COARSE_ASSEMBLED_PCR, 'pcr': _lib.COARSE_ASSEMBLED_PCR,
-            'flux': _lib.COARSE_FLUX_SCAN}[coarse_solver]
+    mode = COARSE_MODES[coarse_solver]
     u = out if out is not None else torch.empty((R, n), dtype=torch.float64, device=nodes.device)
     _require_cuda_f64(u, 'out', R * n)
     ws = _workspace(int(lib.hfl_fem_p1_multi_workspace_bytes(n, R)), nodes.device)

@@ -138,7 +138,7 @@ __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __rest
                                                 double* sm) {
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
-    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
+    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR, a.exact_rowsum != 0};
     double e8[8];
     chunk_reduce(rows, t * FS, FS, e8);
     double lp, sp, rp, bp;
@@ -302,7 +302,7 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
         if (t == 0) uh[FT] = uQ;
     }
     __syncthreads();
-    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
+    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR, a.exact_rowsum != 0};
     const double ua = uh[t], ub = uh[t + 1];
     // Thomas on the chunk interior, compile-time length FS - 1 (row-sum form, see thomas_step)
     double cpv[FS], bpv[FS], xs[FS];
@@ -344,16 +344,19 @@ __global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_backsub_kernel(const 
     else fem_backsub_body<false, GENERAL>(a, utop, ntile, yvw, u, sm);
 }
 
-// End-node residuals for the multi-GPU interface system (see hfl.h).
-__global__ void fem_reaction_kernel(const FemArgs a, const double* __restrict__ u, double* __restrict__ out4) {
+// End-node residuals for the multi-GPU interface system (see hfl.h).  flux2 = {q_0, B_{n-2}} from the flux scan
+// (NULL for the assembled solvers): the end fluxes q_0 and q_{n-2} = q_0 - B_{n-2} are then used as they are instead of
+// k (u_1 - u_0), which amplifies the rounding of u by k ~ 1/h (3e-9 at h = 1e-7).
+__global__ void fem_reaction_kernel(const FemArgs a, const double* __restrict__ u, const double* __restrict__ flux2,
+                                    double* __restrict__ out4) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double k, Ls, Rs;
         out4[0] = a.nodes[0];
         out4[1] = a.nodes[a.n - 1];
         element_terms(a, a.nodes[0], a.nodes[1], k, Ls, Rs);
-        out4[2] = Ls + k * (u[1] - u[0]);
+        out4[2] = Ls + (flux2 ? flux2[0] : k * (u[1] - u[0]));
         element_terms(a, a.nodes[a.n - 2], a.nodes[a.n - 1], k, Ls, Rs);
-        out4[3] = Rs + k * (u[a.n - 2] - u[a.n - 1]);
+        out4[3] = Rs + (flux2 ? flux2[1] - flux2[0] : k * (u[a.n - 2] - u[a.n - 1]));
     }
 }
 
@@ -425,6 +428,7 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
     const long long n = a.n;
     a.gx0 = 0.5 * (-0.5773502691896257) + 0.5;   // 0.5 * leggauss(2) + 0.5
     a.gx1 = 0.5 * (0.5773502691896257) + 0.5;
+    a.exact_rowsum = (coarse_solver == HFL_COARSE_ASSEMBLED_EXACT) ? 1 : 0;
     if (coarse_solver == HFL_COARSE_FLUX_SCAN) {
         int rc = hfl_fem_flux_scan(a, R, d_u, d_ws, ws_bytes, s);
         if (rc != HFL_OK) return rc;
@@ -474,7 +478,10 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
         HFL_CUDA_CHECK(cudaGetLastError());
     }
     if (d_iface4 != nullptr) {
-        fem_reaction_kernel<<<1, 32, 0, s>>>(a, d_u, d_iface4);
+        const double* flux2 = nullptr;
+        if (coarse_solver == HFL_COARSE_FLUX_SCAN)
+            flux2 = reinterpret_cast<const double*>(d_ws) + 6 * (size_t)((n - 1 + FTS - 1) / FTS);   // after the tile prefixes (hfl_flux.cu)
+        fem_reaction_kernel<<<1, 32, 0, s>>>(a, d_u, flux2, d_iface4);
         count_launch();
         HFL_CUDA_CHECK(cudaGetLastError());
     }
@@ -486,7 +493,8 @@ extern "C" int hfl_fem_p1_solve(int64_t n, const double* d_nodes, double k_freq,
                                 void* stream) {
     HFL_REQUIRE(n >= 2, "hfl_fem_p1_solve: need at least 2 nodes (got %lld)", (long long)n);
     HFL_REQUIRE(d_nodes != nullptr && d_u != nullptr, "hfl_fem_p1_solve: d_nodes / d_u is NULL");
-    HFL_REQUIRE(coarse_solver == HFL_COARSE_ASSEMBLED_PCR || coarse_solver == HFL_COARSE_FLUX_SCAN,
+    HFL_REQUIRE(coarse_solver == HFL_COARSE_ASSEMBLED_PCR || coarse_solver == HFL_COARSE_FLUX_SCAN ||
+                    coarse_solver == HFL_COARSE_ASSEMBLED_EXACT,
                 "hfl_fem_p1_solve: unknown coarse_solver %d", coarse_solver);
     HFL_REQUIRE(d_ws != nullptr && ws_bytes >= hfl_fem_p1_workspace_bytes(n),
                 "hfl_fem_p1_solve: workspace too small (%zu < %zu)", ws_bytes, hfl_fem_p1_workspace_bytes(n));
@@ -504,7 +512,8 @@ extern "C" int hfl_fem_p1_solve_multi(int64_t n, const double* d_nodes, int R, c
     HFL_REQUIRE(n >= 2, "hfl_fem_p1_solve_multi: need at least 2 nodes (got %lld)", (long long)n);
     HFL_REQUIRE(R >= 1 && R <= 65535, "hfl_fem_p1_solve_multi: R = %d outside 1..65535", R);
     HFL_REQUIRE(d_nodes != nullptr && d_u != nullptr && d_k_freq != nullptr, "hfl_fem_p1_solve_multi: d_nodes / d_u / d_k_freq is NULL");
-    HFL_REQUIRE(coarse_solver == HFL_COARSE_ASSEMBLED_PCR || coarse_solver == HFL_COARSE_FLUX_SCAN,
+    HFL_REQUIRE(coarse_solver == HFL_COARSE_ASSEMBLED_PCR || coarse_solver == HFL_COARSE_FLUX_SCAN ||
+                    coarse_solver == HFL_COARSE_ASSEMBLED_EXACT,
                 "hfl_fem_p1_solve_multi: unknown coarse_solver %d", coarse_solver);
     HFL_REQUIRE(d_ws != nullptr && ws_bytes >= hfl_fem_p1_multi_workspace_bytes(n, R),
                 "hfl_fem_p1_solve_multi: workspace too small (%zu < %zu)", ws_bytes, hfl_fem_p1_multi_workspace_bytes(n, R));

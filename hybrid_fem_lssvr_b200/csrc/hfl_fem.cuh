@@ -27,6 +27,7 @@ struct FemArgs {
     // several right-hand sides of the same mesh in one launch (hfl_fem_p1_solve_multi): grid.y = R, right-hand side
     // r = blockIdx.y uses forcing frequency kfreqs[r], workspace slice r * ws_stride (doubles) and output row r * n
     const double* kfreqs; long long ws_stride;
+    int exact_rowsum;   // HFL_COARSE_ASSEMBLED_EXACT: interior rows have row sum 0 (unrounded diagonal)
 };
 
 // The launch arguments specialised to this CTA's right-hand side (no-op for a single solve).
@@ -52,7 +53,7 @@ __device__ __forceinline__ FemArgs select_rhs(FemArgs a) {
 template <bool SPECIAL, bool GENERAL = false>
 struct MeshRows {
     const double* k; const double* b; const double* s;    // s: row sums per node (general operator only)
-    long long P, n; double uL, uR;
+    long long P, n; double uL, uR; bool exact;
     __device__ __forceinline__ void get(int m, double& l, double& sg, double& r, double& bo) const {
         if (SPECIAL) {
             const long long g = P + m;
@@ -67,7 +68,7 @@ struct MeshRows {
         // d = fl(kl + kr) is the reference's assembled diagonal; kl + kr = d + err exactly (TwoSum), so sigma = -err
         const double d = __dadd_rn(kl, kr);
         const double t = __dsub_rn(d, kl);
-        sg = -__dadd_rn(__dsub_rn(kl, __dsub_rn(d, t)), __dsub_rn(kr, t));
+        sg = exact ? 0.0 : -__dadd_rn(__dsub_rn(kl, __dsub_rn(d, t)), __dsub_rn(kr, t));
     }
 };
 

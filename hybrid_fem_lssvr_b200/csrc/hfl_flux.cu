@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(FT, 4) flux_tile_kernel(const FemArgs a_in, do
     }
 }
 
-// One CTA: exclusive scan of the tile aggregates; out: prefix per tile [3 * nt], q0 at prefix[3 * nt].
+// One CTA: exclusive scan of the tile aggregates; out: prefix per tile [3 * nt], then q_0 and the sum of all loads.
 __global__ void __launch_bounds__(TOPT) flux_top_kernel(const double* __restrict__ agg3, int nt, int S, double uL,
                                                         double uR, double* __restrict__ prefix, long long ws_stride) {
     extern __shared__ double sm[];
@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(TOPT) flux_top_kernel(const double* __restrict
             run = tri_op(run, Tri{agg3[3 * (size_t)c], agg3[3 * (size_t)c + 1], agg3[3 * (size_t)c + 2]});
         }
     }
-    if (t == 0) prefix[3 * (size_t)nt] = (uR - uL + total.d) / total.c;
+    if (t == 0) {
+        prefix[3 * (size_t)nt] = (uR - uL + total.d) / total.c;      // q_0
+        prefix[3 * (size_t)nt + 1] = total.b;                         // B_{n-2}: q_{n-2} = q_0 - B_{n-2} (end-node reactions)
+    }
 }
 
 __global__ void __launch_bounds__(FT, 4) flux_apply_kernel(const FemArgs a_in, const double* __restrict__ prefix, int nt,
@@ -143,7 +146,7 @@ int hfl_fem_flux_scan(const FemArgs& a, int R, double* d_u, void* d_ws, size_t w
     }
     double* agg3 = reinterpret_cast<double*>(d_ws);
     double* prefix = agg3 + 3 * (size_t)nt;
-    if ((size_t)(6 * nt + 1) * sizeof(double) > ws_bytes) {
+    if ((size_t)(6 * nt + 2) * sizeof(double) > ws_bytes) {
         set_error("hfl_fem_p1_solve: workspace too small for the flux scan");
         return HFL_ERR_ARG;
     }

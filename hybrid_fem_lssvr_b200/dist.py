@@ -35,11 +35,16 @@ def _device_local_solve(nodes, k_freq, coarse_solver, out=None):
                               out=out, want_reaction=True)
 
 
-def fem_p1_solve_distributed(nodes_local, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='assembled',
+def fem_p1_solve_distributed(nodes_local, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='assembled_exact',
                              group=None, local_solve=None, device_interface=True, out=None):
     """SPIKE coarse solve.  Returns (y_local, bc2): the local zero-Dirichlet solve and the two
     interface values {U_rank, U_rank+1} as a 2-vector on the same device as `nodes_local`;
     u_local = y_local + linear correction (see hfl_fem_apply_bc).
+
+    coarse_solver: 'assembled_exact' (default) or 'flux'.  The interface system takes the correction to be linear on
+    each range, which holds for these two; the reference's rounded diagonal ('assembled') adds a spurious reaction term
+    eps k_i u_i whose discrete harmonic functions are not linear - harmless up to ~1e5 nodes per range (1e-10 parity,
+    tests), 1e-3 at 1e7 nodes per range.
 
     `local_solve(nodes, k_freq, coarse_solver, out) -> (y, iface4)` defaults to the CUDA kernels; the
     CPU tests inject a stand-in to exercise the exchange logic over gloo.

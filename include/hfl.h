@@ -39,6 +39,13 @@ extern "C" {
 /* coarse_solver */
 #define HFL_COARSE_ASSEMBLED_PCR 0  /* the reference's assembled tridiagonal system, partition + parallel cyclic reduction */
 #define HFL_COARSE_FLUX_SCAN 1      /* same equations in first-order (flux) form by two prefix sums; better conditioned */
+#define HFL_COARSE_ASSEMBLED_EXACT 2 /* the assembled system with the UNROUNDED diagonal k_l + k_r (zero row sums), same
+                                        partition + PCR kernels.  The reference's rounded diagonal fl(k_l + k_r) acts as a
+                                        spurious reaction term eps k_i u_i: invisible at the reference's sizes (both
+                                        modes are within 1e-10 of it up to ~1e4 nodes), 3e-6 at 1e6 nodes and 1e-3 at 1e7
+                                        nodes on unlucky meshes.  Mode 0 reproduces that system faithfully; mode 2 (and
+                                        mode 1) solve what it was meant to be.  The multi-GPU split uses mode 2 (or 1):
+                                        its interface system relies on discrete harmonic functions being linear. */
 
 typedef struct hfl_plan hfl_plan_t;
 
