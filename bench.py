@@ -37,6 +37,8 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--elements', type=int, default=10 ** 7, help='elements per GPU')
     ap.add_argument('--error', default='fused', choices=['fused', 'separate', 'none'])
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'nccl', 'peer'],
+                    help='N > 1: the two small all-gathers through NVLink peer memory (csrc/hfl_peer.cu) or NCCL')
     ap.add_argument('--coarse', default='assembled', choices=['assembled', 'assembled_exact', 'flux'])
     ap.add_argument('--store', type=int, default=0, help='primal store path: 0 auto, 1 direct, 2 smem, 3 tma')
     ap.add_argument('--cpu-sample', type=int, default=0, help='elements in the CPU baseline sample (0 = auto)')
@@ -213,13 +215,21 @@ def run_ours(args):
     results = {}
     err_all = torch.empty((world, 3), dtype=torch.float64, device=dev)
 
+    exchange = None
+    if world > 1 and args.exchange != 'nccl':
+        try:
+            exchange = hdist.PeerExchange(device=dev)
+        except Exception as exc:                      # no peer memory here: NCCL carries the two all-gathers
+            if args.exchange == 'peer':
+                raise
+            sys.stderr.write('bench: peer-memory exchange unavailable (%s); using NCCL\n' % exc)
     # partitioned solve: same partition + PCR kernels on the unrounded diagonal (include/hfl.h, HFL_COARSE_ASSEMBLED_EXACT)
     coarse_dist = 'assembled_exact' if args.coarse == 'assembled' else args.coarse
 
     def step():
         err3.zero_()
         if world > 1:
-            _, bc2 = hdist.fem_p1_solve_distributed(nodes, k_freq=KFREQ, coarse_solver=coarse_dist, out=u)
+            _, bc2 = hdist.fem_p1_solve_distributed(nodes, k_freq=KFREQ, coarse_solver=coarse_dist, out=u, exchange=exchange)
         else:
             batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u)
             bc2 = None
@@ -229,7 +239,7 @@ def run_ours(args):
         if args.error == 'separate':
             batch.error_fine(nodes, fine, KFREQ, err3)
         if world > 1 and args.error != 'none':
-            results['err_gathered'] = hdist.gather_error(err3, out=err_all)     # stream-ordered, no host sync
+            results['err_gathered'] = hdist.gather_error(err3, out=err_all, exchange=exchange)     # stream-ordered, no host sync
 
     def barrier():
         if world > 1:
@@ -239,6 +249,17 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if exchange is not None:       # a receive spin that expired on any rank: fall back to NCCL on all of them
+        bad = exchange.status.to(torch.float64)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if bad.item() > 0:
+            if args.exchange == 'peer':
+                raise RuntimeError('peer-memory exchange timed out')
+            sys.stderr.write('bench: peer-memory exchange timed out during warm-up; using NCCL\n')
+            exchange = None
+            for _ in range(max(args.warmup, 3)):
+                step()
+            barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -398,6 +419,8 @@ def run_ours(args):
                                    % (E, args.coarse if world == 1 else coarse_dist + ' + SPIKE interface exchange', args.error),
                        'elements_per_gpu': E, 'elements_total': E_global, 'M': M, 'N_colloc': NCOL, 'F': F, 'gamma': GAMMA,
                        'parallelism': 'contiguous element ranges x%d' % world,
+                       'exchange': ('none (single GPU)' if world == 1 else
+                                    'NVLink peer-memory all-gather (hfl_peer_allgather)' if exchange is not None else 'NCCL all-gather'),
                        'l2_policy': 'inputs (160 MB) + outputs (2.56 GB) per step exceed the 126 MB L2; no explicit flush',
                        'store_path': args.store},
             'fine_points_per_s': value * F,

@@ -38,6 +38,13 @@ SIGNATURES = {
     'hfl_fem_p1_solve_general': (_i32, [_i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _sz, _vp]),
     'hfl_spike_interface_solve': (_i32, [_i32, C.POINTER(_f64), _f64, _f64, C.POINTER(_f64)]),
     'hfl_spike_interface_solve_device': (_i32, [_i32, _vp, _f64, _f64, _i32, _vp, _vp]),
+    'hfl_peer_buffer_bytes': (_sz, []),
+    'hfl_peer_buffer_create': (_i32, [C.POINTER(_vp), C.POINTER(C.c_ubyte)]),
+    'hfl_peer_buffer_open': (_i32, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
+    'hfl_peer_buffer_close': (_i32, [_vp]),
+    'hfl_peer_buffer_destroy': (_i32, [_vp]),
+    'hfl_peer_allgather': (_i32, [_i32, _i32, _i32, _vp, _vp, C.c_uint32, _i32, _vp, _vp, _vp]),
+    'hfl_peer_spike_exchange': (_i32, [_i32, _i32, _vp, _vp, C.c_uint32, _i32, _f64, _f64, _vp, _vp, _vp, _vp]),
     'hfl_fem_apply_bc': (_i32, [_i64, _vp, _vp, _f64, _f64, _vp]),
     'hfl_lssvr_primal_batch': (_i32, [_vp, _i64, _vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'hfl_lssvr_dual_batch': (_i32, [_vp, _i64, _vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

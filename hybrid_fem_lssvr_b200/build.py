@@ -18,7 +18,7 @@ VARIANT = os.environ.get('HFL_VARIANT', '')
 OBJ = os.path.join(HERE, 'build' + ('_' + VARIANT if VARIANT else ''))
 LIB = os.path.join(HERE, 'libhfl%s.so' % ('_' + VARIANT if VARIANT else ''))
 SOURCES = ['hfl_abi.cu', 'hfl_primal.cu', 'hfl_fem.cu', 'hfl_flux.cu', 'hfl_eval.cu', 'hfl_dual.cu',
-           'hfl_dual_small.cu', 'hfl_dual_parity.cu', 'hfl_general.cu', 'hfl_primal_f16.cu', 'hfl_primal_f64.cu']
+           'hfl_dual_small.cu', 'hfl_dual_parity.cu', 'hfl_peer.cu', 'hfl_general.cu', 'hfl_primal_f16.cu', 'hfl_primal_f64.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('HFL_EXTRA_NVCC_FLAGS', '').split()

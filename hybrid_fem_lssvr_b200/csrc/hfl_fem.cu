@@ -370,33 +370,11 @@ __global__ void fem_apply_bc_kernel(long long n, const double* __restrict__ node
     }
 }
 
-// Device version of the interface solve (G <= 64): keeps the multi-GPU step stream-ordered.
-// gathered[4 r + {0,1,2,3}] = {x_first, x_last, r_left, r_right}; writes bc2 = {U_rank, U_rank+1}.
+// Device version of the interface solve (G <= 64): keeps the multi-GPU step stream-ordered (body in hfl_fem.cuh).
 __global__ void spike_iface_kernel(int G, const double* __restrict__ g, double uL, double uR, int rank,
                                    double* __restrict__ bc2) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double dl[64], dd[64], du[64], rb[64], U[66];
-    U[0] = uL; U[G] = uR;
-    const int m = G - 1;
-    for (int r = 1; r < G; ++r) {
-        const double Ll = g[4 * (r - 1) + 1] - g[4 * (r - 1) + 0];
-        const double Lr = g[4 * r + 1] - g[4 * r + 0];
-        dl[r - 1] = -1.0 / Ll; du[r - 1] = -1.0 / Lr; dd[r - 1] = 1.0 / Ll + 1.0 / Lr;
-        rb[r - 1] = g[4 * (r - 1) + 3] + g[4 * r + 2];
-    }
-    if (m >= 1) {
-        rb[0] -= dl[0] * uL;
-        rb[m - 1] -= du[m - 1] * uR;
-        for (int i = 1; i < m; ++i) {
-            const double w = dl[i] / dd[i - 1];
-            dd[i] -= w * du[i - 1];
-            rb[i] -= w * rb[i - 1];
-        }
-        U[m] = rb[m - 1] / dd[m - 1];
-        for (int i = m - 2; i >= 0; --i) U[i + 1] = (rb[i] - du[i] * U[i + 2]) / dd[i];
-    }
-    bc2[0] = U[rank];
-    bc2[1] = U[rank + 1];
+    spike_iface_solve(G, g, uL, uR, rank, bc2);
 }
 
 }  // namespace hfl

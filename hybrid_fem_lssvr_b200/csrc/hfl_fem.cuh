@@ -173,4 +173,32 @@ __device__ __forceinline__ void load_tile_elements(const FemArgs& a, long long P
     __syncthreads();
 }
 
+// Interface (SPIKE) system of G contiguous ranges on one thread: gathered[4 r + {0,1,2,3}] = {x_first, x_last, r_left,
+// r_right}; writes bc2 = {U_rank, U_rank+1}.  Used by spike_iface_kernel (hfl_fem.cu) and by the fused exchange kernel
+// (hfl_peer.cu).
+__device__ __forceinline__ void spike_iface_solve(int G, const double* g, double uL, double uR, int rank, double* bc2) {
+    double dl[64], dd[64], du[64], rb[64], U[66];
+    U[0] = uL; U[G] = uR;
+    const int m = G - 1;
+    for (int r = 1; r < G; ++r) {
+        const double Ll = g[4 * (r - 1) + 1] - g[4 * (r - 1) + 0];
+        const double Lr = g[4 * r + 1] - g[4 * r + 0];
+        dl[r - 1] = -1.0 / Ll; du[r - 1] = -1.0 / Lr; dd[r - 1] = 1.0 / Ll + 1.0 / Lr;
+        rb[r - 1] = g[4 * (r - 1) + 3] + g[4 * r + 2];
+    }
+    if (m >= 1) {
+        rb[0] -= dl[0] * uL;
+        rb[m - 1] -= du[m - 1] * uR;
+        for (int i = 1; i < m; ++i) {
+            const double w = dl[i] / dd[i - 1];
+            dd[i] -= w * du[i - 1];
+            rb[i] -= w * rb[i - 1];
+        }
+        U[m] = rb[m - 1] / dd[m - 1];
+        for (int i = m - 2; i >= 0; --i) U[i + 1] = (rb[i] - du[i] * U[i + 2]) / dd[i];
+    }
+    bc2[0] = U[rank];
+    bc2[1] = U[rank + 1];
+}
+
 }  // namespace hfl

@@ -107,6 +107,27 @@ int hfl_spike_interface_solve(int G, const double* gathered, double u_left, doub
 int hfl_spike_interface_solve_device(int G, const double* d_gathered, double u_left, double u_right,
                                      int rank, double* d_bc2, void* stream);
 
+/* ---- exchange of a few doubles per rank over NVLink peer memory (one process per GPU, one node): the two
+ * collectives of the partitioned path (4 doubles per rank for the interface system, 3 for the error norms) without
+ * NCCL's per-call latency.  Every rank creates one buffer, the 64-byte IPC handles are swapped by the host (any
+ * transport), every rank opens its peers' buffers and keeps the G device pointers in a device array d_bufs[G]
+ * (its own buffer at [rank]).  hfl_peer_allgather: d_out[G][W] <- every rank's d_src[W] (W <= 4), stream-ordered;
+ * all ranks must call it with the same (epoch, channel, W); epoch != 0 increases by one per call on a channel
+ * (channel < 4 separates call sites).  The receive spin is bounded (~2 s); *d_status (optional) becomes 1 on expiry.
+ * Replaces the dist.all_gather_into_tensor calls a torch.distributed port of P:117-145 / K5 would make. */
+size_t hfl_peer_buffer_bytes(void);
+int hfl_peer_buffer_create(void** d_buf, unsigned char* ipc_handle64);
+int hfl_peer_buffer_open(const unsigned char* ipc_handle64, void** d_peer);
+int hfl_peer_buffer_close(void* d_peer);
+int hfl_peer_buffer_destroy(void* d_buf);
+int hfl_peer_allgather(int G, int rank, int W, const double* d_src, void* const* d_bufs, uint32_t epoch,
+                       int channel, double* d_out, int32_t* d_status, void* stream);
+/* The interface exchange of the partitioned coarse solve in one launch: all-gather of the 4-double records
+ * (d_iface4 from hfl_fem_p1_solve) into d_gathered[4 G], then hfl_spike_interface_solve_device's solve -> d_bc2. */
+int hfl_peer_spike_exchange(int G, int rank, const double* d_iface4, void* const* d_bufs, uint32_t epoch,
+                            int channel, double u_left, double u_right, double* d_gathered, double* d_bc2,
+                            int32_t* d_status, void* stream);
+
 /* d_u[i] += bc_left * (x_last - x_i) / L + bc_right * (x_i - x_first) / L  (discrete-harmonic
  * correction of a local solve; the element kernels can apply it on the fly through d_bc2). */
 int hfl_fem_apply_bc(int64_t n_nodes, const double* d_nodes, double* d_u,

@@ -168,3 +168,42 @@ def test_nodal_error_norms():
     w = np.zeros(n); w[1:-1] = 0.5 * (nodes[2:] - nodes[:-2]); w[0] = 0.5 * (nodes[1] - nodes[0]); w[-1] = w[0]
     assert mx > 1e-7 and abs(mx - np.max(np.abs(d))) <= 1e-9 * mx
     assert abs(l2 - np.sqrt(np.sum(w * d * d))) <= 1e-9 * l2
+
+
+def test_peer_allgather_protocol_on_one_gpu():
+    """hfl_peer_allgather with three "ranks" in one process: three buffers on one device, one stream per rank (the
+    kernels wait for each other, so they must be able to run concurrently).  Several epochs on two channels, both
+    widths used by the partitioned path; every rank must see every rank's doubles bit for bit."""
+    import ctypes as C
+    from hybrid_fem_lssvr_b200 import _lib, dist as hdist
+    lib = _lib.load()
+    G = 3
+    nbytes = int(lib.hfl_peer_buffer_bytes())
+    bufs = [torch.zeros(nbytes // 8, dtype=torch.int64, device='cuda') for _ in range(G)]
+    ranks = [hdist.PeerExchange(rank=r, buffers=[b.data_ptr() for b in bufs]) for r in range(G)]
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    rng = np.random.default_rng(0)
+    torch.cuda.synchronize()
+    for epoch in range(5):
+        for channel, W in ((hdist.PeerExchange.CHANNEL_INTERFACE, 4), (hdist.PeerExchange.CHANNEL_ERROR, 3)):
+            data = rng.normal(size=(G, W)) * 10.0 ** rng.integers(-300, 300, size=(G, W))
+            outs = []
+            for r in range(G):
+                with torch.cuda.stream(streams[r]):
+                    outs.append(ranks[r].all_gather(dev(data[r]), channel))
+            torch.cuda.synchronize()
+            for r in range(G):
+                assert np.array_equal(outs[r].cpu().numpy(), data), (epoch, channel, r)
+                assert not ranks[r].timed_out()
+    # the fused exchange + interface solve against the host solve of the same records
+    xs = np.array([-1.0, -0.2, 0.3, 1.0])
+    recs = np.array([[xs[r], xs[r + 1], rng.normal(), rng.normal()] for r in range(G)])
+    expect = batch.spike_interface_solve(recs.reshape(-1).tolist(), 0.25, -0.5)
+    got = []
+    for r in range(G):
+        with torch.cuda.stream(streams[r]):
+            got.append(ranks[r].spike_exchange(dev(recs[r]), 0.25, -0.5))
+    torch.cuda.synchronize()
+    for r in range(G):
+        assert np.max(np.abs(got[r].cpu().numpy() - np.array(expect[r:r + 2]))) <= 1e-14
+        assert not ranks[r].timed_out()
