@@ -37,27 +37,43 @@ class PeerExchange:
             self.world = dist.get_world_size(group)
             self.rank = dist.get_rank(group)
             self.device = torch.device(device or ('cuda:%d' % torch.cuda.current_device()))
+            # every step that can fail on one rank only is followed by a collective agreement, so that either all ranks
+            # end up with a working exchange or all of them raise (and fall back to NCCL together)
             own = C.c_void_p()
             handle = (C.c_ubyte * 64)()
-            with torch.cuda.device(self.device):
-                _lib.check(self._lib.hfl_peer_buffer_create(C.byref(own), handle), 'hfl_peer_buffer_create')
-            self._own = own
-            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
-            allh = torch.empty(64 * self.world, dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(allh, mine, group=group)
-            allh = allh.cpu().reshape(self.world, 64)
-            ptrs = []
-            for r in range(self.world):
-                if r == self.rank:
-                    ptrs.append(own.value)
-                    continue
-                h = (C.c_ubyte * 64)(*allh[r].tolist())
-                peer = C.c_void_p()
+            err = None
+            try:
                 with torch.cuda.device(self.device):
-                    _lib.check(self._lib.hfl_peer_buffer_open(h, C.byref(peer)), 'hfl_peer_buffer_open')
-                self._peers.append(peer)
-                ptrs.append(peer.value)
-            dist.barrier(group=group)      # every rank has opened every buffer before the first store
+                    _lib.check(self._lib.hfl_peer_buffer_create(C.byref(own), handle), 'hfl_peer_buffer_create')
+                self._own = own
+            except Exception as exc:
+                err = exc
+            mine = torch.tensor([0 if err else 1] + list(handle), dtype=torch.uint8, device=self.device)
+            allh = torch.empty(65 * self.world, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu().reshape(self.world, 65)
+            if int(allh[:, 0].min()) == 0:
+                self.close()
+                raise _lib.HflError('peer-memory buffer creation failed on a rank: %s' % (err or 'another rank'))
+            ptrs = []
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        ptrs.append(own.value)
+                        continue
+                    h = (C.c_ubyte * 64)(*allh[r, 1:].tolist())
+                    peer = C.c_void_p()
+                    with torch.cuda.device(self.device):
+                        _lib.check(self._lib.hfl_peer_buffer_open(h, C.byref(peer)), 'hfl_peer_buffer_open')
+                    self._peers.append(peer)
+                    ptrs.append(peer.value)
+            except Exception as exc:
+                err = exc
+            good = torch.tensor([0.0 if err else 1.0], dtype=torch.float64, device=self.device)
+            dist.all_reduce(good, op=dist.ReduceOp.MIN, group=group)     # also: every buffer is open before the first store
+            if good.item() == 0.0:
+                self.close()
+                raise _lib.HflError('peer-memory buffer could not be opened on a rank: %s' % (err or 'another rank'))
         self.bufs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.epoch = {}
