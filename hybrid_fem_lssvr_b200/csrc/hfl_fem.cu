@@ -133,12 +133,12 @@ __device__ __forceinline__ void head_equation(double lp, double sp, double rp, d
 }
 
 // Level 0, pass 1: one record per tile = {l, sigma, r, b of the tile head, y1, v1, w1, e1, ys, vs, ws, es of the interior}.
-template <bool SPECIAL, bool GENERAL>
+template <bool SPECIAL, bool GENERAL, bool EXACT>
 __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __restrict__ rec, double* __restrict__ yvw,
                                                 double* sm) {
     const int t = threadIdx.x;
     const long long P = (long long)blockIdx.x * FTS;
-    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR, a.exact_rowsum != 0};
+    MeshRows<SPECIAL, GENERAL, EXACT> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
     double e8[8];
     chunk_reduce(rows, t * FS, FS, e8);
     double lp, sp, rp, bp;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __rest
     }
 }
 
-template <bool GENERAL>
+template <bool GENERAL, bool EXACT = false>
 __global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_reduce_kernel(const FemArgs a_in, double* __restrict__ rec,
                                                                          double* __restrict__ yvw) {
     extern __shared__ double sm[];
@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_reduce_kernel(const F
     rec += (size_t)blockIdx.y * a.ws_stride; yvw += (size_t)blockIdx.y * a.ws_stride;
     const long long P = (long long)blockIdx.x * FTS;
     load_tile_elements<GENERAL>(a, P, sm);
-    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true, GENERAL>(a, rec, yvw, sm);
-    else fem_reduce_body<false, GENERAL>(a, rec, yvw, sm);
+    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true, GENERAL, EXACT>(a, rec, yvw, sm);
+    else fem_reduce_body<false, GENERAL, EXACT>(a, rec, yvw, sm);
 }
 
 // Thomas elimination of a chunk interior between two known head values, in (l, sigma, r) form: s = row sum over
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
 
 // Level 0, pass 2: tile head values known -> chunk heads from the stored partial solutions
 // (U_t = Y_t - u_P V_t - u_Q W_t) -> chunk interiors by Thomas -> u.
-template <bool SPECIAL, bool GENERAL>
+template <bool SPECIAL, bool GENERAL, bool EXACT>
 __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double* __restrict__ utop, int ntile,
                                                  const double* __restrict__ yvw, double* __restrict__ u, double* sm) {
     const int t = threadIdx.x;
@@ -302,7 +302,7 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
         if (t == 0) uh[FT] = uQ;
     }
     __syncthreads();
-    MeshRows<SPECIAL, GENERAL> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR, a.exact_rowsum != 0};
+    MeshRows<SPECIAL, GENERAL, EXACT> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
     const double ua = uh[t], ub = uh[t + 1];
     // Thomas on the chunk interior, compile-time length FS - 1 (row-sum form, see thomas_step)
     double cpv[FS], bpv[FS], xs[FS];
@@ -331,7 +331,7 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
     }
 }
 
-template <bool GENERAL>
+template <bool GENERAL, bool EXACT = false>
 __global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_backsub_kernel(const FemArgs a_in, const double* __restrict__ utop,
                                                                           int ntile, const double* __restrict__ yvw,
                                                                           double* __restrict__ u) {
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_backsub_kernel(const 
     utop += (size_t)blockIdx.y * a.ws_stride; yvw += (size_t)blockIdx.y * a.ws_stride; u += (size_t)blockIdx.y * a.n;
     const long long P = (long long)blockIdx.x * FTS;
     load_tile_elements<GENERAL>(a, P, sm);   // recomputed: re-reading cached terms (16 B/node) measured slower than 2 sinpi
-    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true, GENERAL>(a, utop, ntile, yvw, u, sm);
-    else fem_backsub_body<false, GENERAL>(a, utop, ntile, yvw, u, sm);
+    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true, GENERAL, EXACT>(a, utop, ntile, yvw, u, sm);
+    else fem_backsub_body<false, GENERAL, EXACT>(a, utop, ntile, yvw, u, sm);
 }
 
 // End-node residuals for the multi-GPU interface system (see hfl.h).  flux2 = {q_0, B_{n-2}} from the flux scan
@@ -444,6 +444,13 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
             fem_reduce_kernel<true><<<grid, FT, smem0, s>>>(a, rec, yvw);
             launch_top();
             fem_backsub_kernel<true><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+        } else if (a.exact_rowsum) {
+            const size_t smem0 = (size_t)sm_total(false) * sizeof(double);
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+            fem_reduce_kernel<false, true><<<grid, FT, smem0, s>>>(a, rec, yvw);
+            launch_top();
+            fem_backsub_kernel<false, true><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
         } else {
             const size_t smem0 = (size_t)sm_total(false) * sizeof(double);
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));

@@ -50,10 +50,10 @@ __device__ __forceinline__ FemArgs select_rhs(FemArgs a) {
 // Rows of the level-0 system from shared memory: k[q] = stiffness entry of local element q (global element
 // P - 1 + q), b[m] = load of local node m (global node P + m).  SPECIAL = the tile contains a Dirichlet node
 // or padding past the mesh (first / last tile only); interior tiles take the branch-free path.
-template <bool SPECIAL, bool GENERAL = false>
+template <bool SPECIAL, bool GENERAL = false, bool EXACT = false>
 struct MeshRows {
     const double* k; const double* b; const double* s;    // s: row sums per node (general operator only)
-    long long P, n; double uL, uR; bool exact;
+    long long P, n; double uL, uR;
     __device__ __forceinline__ void get(int m, double& l, double& sg, double& r, double& bo) const {
         if (SPECIAL) {
             const long long g = P + m;
@@ -65,10 +65,11 @@ struct MeshRows {
         l = -kl; r = -kr;
         bo = b[padi(m)];
         if (GENERAL) { sg = s[padi(m)]; return; }          // mass-matrix row sum, assembled without cancellation
+        if (EXACT) { sg = 0.0; return; }                   // HFL_COARSE_ASSEMBLED_EXACT: unrounded diagonal kl + kr
         // d = fl(kl + kr) is the reference's assembled diagonal; kl + kr = d + err exactly (TwoSum), so sigma = -err
         const double d = __dadd_rn(kl, kr);
         const double t = __dsub_rn(d, kl);
-        sg = exact ? 0.0 : -__dadd_rn(__dsub_rn(kl, __dsub_rn(d, t)), __dsub_rn(kr, t));
+        sg = -__dadd_rn(__dsub_rn(kl, __dsub_rn(d, t)), __dsub_rn(kr, t));
     }
 };
 
