@@ -207,3 +207,17 @@ def test_peer_allgather_protocol_on_one_gpu():
     for r in range(G):
         assert np.max(np.abs(got[r].cpu().numpy() - np.array(expect[r:r + 2]))) <= 1e-14
         assert not ranks[r].timed_out()
+
+
+@pytest.mark.parametrize('n', [2048 * 300 + 5, 2048 * 6144, 2048 * 6144 + 1])
+def test_large_meshes_three_solvers(n):
+    """Meshes of 0.6e6 and 1.26e7 nodes (300 / 6144 / 6145 tiles: the top-level CTA holds the tile-head rows in shared
+    memory for the first, in the workspace for the others): the exact-row-sum mode against the flux form (both
+    well-conditioned, so they must agree to rounding) and against sin(pi x); the reference's rounded mode for sanity."""
+    nodes = batch.mesh_linspace(-1.0, 1.0, n)
+    uf = batch.fem_p1_solve(nodes, coarse_solver='flux')
+    ue = batch.fem_p1_solve(nodes, coarse_solver='assembled_exact')
+    assert torch.max(torch.abs(ue - uf)).item() <= 1e-12
+    assert torch.max(torch.abs(ue - torch.sin(np.pi * nodes))).item() <= 1e-12
+    ua = batch.fem_p1_solve(nodes, coarse_solver='assembled')
+    assert torch.max(torch.abs(ua - uf)).item() <= 1e-2 and ua[0].item() == 0.0 and ua[-1].item() == 0.0
