@@ -115,7 +115,9 @@ class FEMLSSVRPrimalSolver:
 
     Keyword-only additions (defaults reproduce the reference): ``rhs_func`` (default: the shipped
     ``poisson_rhs``, evaluated on the device), ``k_freq`` (forcing (k pi)^2 sin(k pi x) when rhs_func is
-    None), ``n_colloc`` (P:40 hard-codes 12), ``coarse_solver`` ('assembled' | 'flux'), ``form``
+    None), ``n_colloc`` (P:40 hard-codes 12), ``coarse_solver`` ('assembled': the reference's rounded
+    tridiagonal system, faithful at any size | 'assembled_exact' | 'flux': the same equations without the rounded
+    diagonal, which is what to use beyond ~1e5 nodes - see include/hfl.h), ``form``
     ('primal' | 'dual').
     """
 
