@@ -70,7 +70,11 @@ __host__ __device__ constexpr int tile_bytes(int F) {
 }
 
 // CTAs per SM the register budget is sized for: small systems fit 128 registers (4 CTAs = 16 warps)
-__host__ __device__ constexpr int min_ctas(int M, bool err) { return (M <= 10 && !err) ? 4 : 3; }
+// (fine grid only: 128 registers, 4 CTAs; with the fused error norms: 168 registers, 3 CTAs - at 2 CTAs / 184 registers it
+// runs 0.62 instead of 0.55 ms; fine grid + coefficient output: 2 CTAs, 0.60 instead of 0.63 ms at 3)
+__host__ __device__ constexpr int min_ctas(int M, bool err, bool coef) {
+    return (M <= 10 && !err && !coef) ? 4 : (err ? 3 : (coef ? 2 : 3));
+}
 
 // LDL^T of a packed-lower PSD matrix in a FIXED (plan-supplied) pivot order with a skip rule: a pivot that
 // is not above 2^-10 eps * (first pivot) is dropped (its unknown is set to zero), which gives the basic solution
@@ -119,7 +123,10 @@ __device__ __forceinline__ int ldl_solve_skip(double (&A)[n * (n + 1) / 2], doub
 // COEF: the coefficient-output path is compiled in (a separate instantiation, so that the fine-grid-only kernel
 // keeps its register budget).
 template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true>
-__global__ void __launch_bounds__(kThreads, NHD > 0 ? 3 : min_ctas(M, ERR || COEF))
+#ifndef HFL_DUAL_SMALL_MINB
+#define HFL_DUAL_SMALL_MINB 2      // 254 registers, no spills: 3 CTAs per SM (168 registers) spilled the prefetched nodal data, 1.01 -> 0.77 ms at 1e7 elements
+#endif
+__global__ void __launch_bounds__(kThreads, NHD > 0 ? HFL_DUAL_SMALL_MINB : min_ctas(M, ERR, COEF))
 lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
               const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DualSmallTables<M, NHD> dt) {
     constexpr int ME = n_even(M), MO = n_odd(M);
