@@ -27,10 +27,45 @@ __device__ __forceinline__ double legval_numpy(double x, const double* __restric
 __global__ void evaluate_points_kernel(long long E, const double* __restrict__ nodes, int M,
                                        const double* __restrict__ coef, long long P, const double* __restrict__ xq,
                                        double* __restrict__ out) {
+    const double x_first = nodes[0];
+    const double inv_len = 1.0 / (nodes[E] - x_first);
+    // Is the mesh quasi-uniform?  Warp 0 compares 32 nodes spread over the mesh with the index a uniform mesh would give
+    // them; the guess is used only when all of them land within 3 elements (otherwise the four probing loads around a
+    // wrong guess are wasted: +50 % on a random-walk mesh).
+    __shared__ int guess_ok;
+    if (threadIdx.x < 32) {
+        const long long is = (E * (long long)threadIdx.x) / 32 + (threadIdx.x & 1);
+        const double t = (nodes[is] - x_first) * inv_len * (double)E;
+        const bool near = fabs(t - (double)is) <= 3.0;
+        const unsigned all = __ballot_sync(0xffffffffu, near);
+        if (threadIdx.x == 0) guess_ok = (all == 0xffffffffu);
+    }
+    __syncthreads();
+    const bool use_guess = guess_ok != 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
         const double x = xq[i];
-        // lower bound: smallest idx with nodes[idx] >= x  (idx in [0, E+1])
+        // lower bound: smallest idx with nodes[idx] >= x  (idx in [0, E+1]).  The bracket [lo, hi] starts from the
+        // position a uniform mesh would give (the reference's meshes are linspace, P:120) and gallops outwards for at
+        // most three steps (offsets 1, 2, 4); if that does not bracket x the plain search over the whole array runs (its upper
+        // levels are shared by all threads and stay in cache, which a one-sided search from the guess would lose).
+        // Quasi-uniform mesh: 3-5 dependent loads instead of log2(E) = 24 (1e8 random points on 1e7 elements 10.2 ->
+        // 8.2 ms, sorted points 5.0 -> 2.4 ms); any monotone mesh stays correct and costs at most 4 extra loads.
         long long lo = 0, hi = E + 1;
+#ifndef HFL_EVAL_PLAIN_SEARCH
+        if (use_guess) {
+            const double t = (x - x_first) * inv_len;                 // NaN / out of range handled by the clamps
+            const long long g = (t > 0.0) ? (long long)fmin(t * (double)E, (double)E) : 0;
+            if (nodes[g] < x) {                                       // answer is to the right of g
+                long long l = g, r = g + 1;
+                for (int step = 1; step <= 4 && r <= E && nodes[r] < x; step <<= 1) { l = r; r += step; }
+                if (!(r <= E && nodes[r] < x)) { lo = l + 1; hi = (r <= E) ? r : E + 1; }   // bracketed; else full search
+            } else {                                                  // nodes[g] >= x: answer is g or to its left
+                long long r = g, l = g - 1;
+                for (int step = 1; step <= 4 && l >= 0 && !(nodes[l] < x); step <<= 1) { r = l; l -= step; }
+                if (!(l >= 0 && !(nodes[l] < x))) { hi = r; lo = (l >= 0) ? l + 1 : 0; }    // bracketed; else full search
+            }
+        }
+#endif
         while (lo < hi) {
             const long long mid = (lo + hi) >> 1;
             if (nodes[mid] < x) lo = mid + 1; else hi = mid;
