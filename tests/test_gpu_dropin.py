@@ -44,6 +44,17 @@ def test_evaluate_points_bit_exact_with_numpy_legval(golden_config1):
     xq = np.concatenate([rng.uniform(-1.2, 1.2, 5000), nodes])
     out = batch.evaluate_points(dev(nodes), dev(coef), dev(xq)).cpu().numpy()
     assert np.array_equal(out, kkt.evaluate_solution(nodes, coef, xq))
+    # uniform and nearly uniform meshes take the guess-and-gallop lookup: query points on the nodes (left element wins),
+    # a hair to either side of them, outside the mesh, and meshes of 1..40 elements
+    for E in (1, 2, 3, 31, 32, 33, 40, 2000):
+        for jitter in (0.0, 0.3):
+            nodes = np.linspace(-0.7, 1.9, E + 1)
+            if jitter:
+                nodes[1:-1] += jitter * (nodes[1] - nodes[0]) * rng.uniform(-1, 1, E - 1)
+            coef = rng.normal(size=(E, 6))
+            xq = np.concatenate([nodes, np.nextafter(nodes, -np.inf), np.nextafter(nodes, np.inf), rng.uniform(-1.0, 2.2, 3000)])
+            out = batch.evaluate_points(dev(nodes), dev(coef), dev(xq)).cpu().numpy()
+            assert np.array_equal(out, kkt.evaluate_solution(nodes, coef, xq)), (E, jitter)
 
 
 def test_lssvr_primal_signature_and_golden(golden_elements):
