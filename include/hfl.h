@@ -6,7 +6,9 @@
  * point below names the reference code it replaces.  All pointers named d_* are DEVICE pointers;
  * everything is stream-ordered on `stream` (a cudaStream_t passed as void*, NULL = legacy default
  * stream); no entry point synchronises the device or allocates device memory behind the caller's
- * back except hfl_plan_create (a few KB of tables).  Every function returns HFL_OK or an error code
+ * back except hfl_plan_create (a few KB of tables), hfl_peer_buffer_create (16 KB) and the FIRST
+ * hfl_lssvr_dual_* call of a (plan, stream) pair with N >= 48, which may grow a scratch buffer owned
+ * by the plan (cudaMalloc; released by hfl_plan_destroy).  Every function returns HFL_OK or an error code
  * and records a message readable through hfl_last_error().  There is no CPU fallback anywhere.
  *
  * Conventions: E elements, n = E + 1 nodes, M Legendre coefficients (degree M - 1), N equispaced
