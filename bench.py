@@ -94,32 +94,6 @@ def cpu_slsqp_sample(n_elements=8):
     return n_elements / (time.perf_counter() - t0)
 
 
-def _slsqp_worker(i):
-    import numpy as np
-    from oracle import fem_p1, slsqp_port
-    nodes = np.linspace(-1.0, 1.0, 25)
-    u = fem_p1.solve_fem_p1(nodes)
-    e = i % 24
-    slsqp_port.lssvr_primal_slsqp(lambda x: np.pi ** 2 * np.sin(np.pi * x), [nodes[e], nodes[e + 1]], u[e], u[e + 1], 8, GAMMA)
-    return 1
-
-
-def cpu_slsqp_pool(per_core=4):
-    """The same SLSQP formulation on every host core at once (multiprocessing pool, per_core elements each):
-    whole-host solves/s of the algorithm the reference runs."""
-    try:
-        import multiprocessing as mp
-        from oracle import slsqp_port  # noqa: F401
-        cores = os.cpu_count() or 1
-        with mp.get_context('fork').Pool(cores) as pool:
-            pool.map(_slsqp_worker, range(cores))                 # warm the workers (imports, first call)
-            t0 = time.perf_counter()
-            n = sum(pool.map(_slsqp_worker, range(cores * per_core)))
-            return n / (time.perf_counter() - t0), cores
-    except Exception:
-        return None
-
-
 def run_cpu_baseline_c(sample, steps=1):
     """The C / OpenMP restatement (oracle/c/hfl_oracle.c): coarse solve + element solves + fine grid + max error
     on `sample` elements of the benchmark's mesh family, all host threads."""
@@ -497,10 +471,6 @@ def cpu_baseline_record(sample_arg, steps):
     s = cpu_slsqp_sample()
     if s is not None:
         rec['reference_formulation_slsqp_solves_per_s_per_core'] = s
-    sp = cpu_slsqp_pool()
-    if sp is not None:
-        rec['reference_formulation_slsqp_solves_per_s_all_cores'] = sp[0]
-        rec['reference_formulation_slsqp_cores'] = sp[1]
     return rec
 
 
