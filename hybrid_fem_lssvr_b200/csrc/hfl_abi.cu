@@ -12,6 +12,7 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_opt_store{0};
 static std::atomic<int> g_opt_debug{0};
 static std::atomic<int> g_opt_dual_team{0};
+static std::atomic<int> g_opt_top_smem_kb{227};
 static std::atomic<int> g_sm_count{0};
 
 void set_error(const char* fmt, ...) {
@@ -24,6 +25,7 @@ void count_launch(int n) { g_launches.fetch_add(n); }
 int get_option_store() { return g_opt_store.load(); }
 int get_option_debug() { return g_opt_debug.load(); }
 int get_option_dual_team() { return g_opt_dual_team.load(); }
+int get_option_top_smem_kb() { return g_opt_top_smem_kb.load(); }
 
 int sm_count() {
     int v = g_sm_count.load();
@@ -84,6 +86,12 @@ extern "C" int hfl_set_option(const char* key, int value) {
     if (strcmp(key, "dual_team") == 0) {
         HFL_REQUIRE(value >= 0 && value <= 3, "dual_team must be 0..3");
         g_opt_dual_team.store(value);
+        return HFL_OK;
+    }
+    // K1 top level: tile-head rows live in shared memory while 64 KB + 32 B per tile fit in this many KB
+    if (strcmp(key, "fem_top_smem_kb") == 0) {
+        HFL_REQUIRE(value >= 64 && value <= 227, "fem_top_smem_kb must be 64..227");
+        g_opt_top_smem_kb.store(value);
         return HFL_OK;
     }
     if (strcmp(key, "primal_debug") == 0) {

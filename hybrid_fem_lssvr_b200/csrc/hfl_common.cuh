@@ -17,6 +17,7 @@ void count_launch(int n = 1);
 int get_option_store();
 int get_option_debug();
 int get_option_dual_team();
+int get_option_top_smem_kb();
 int sm_count();
 
 #define HFL_CUDA_CHECK(expr)                                                            \

@@ -11,6 +11,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // 1/d to ~1 ulp: hardware seed (MUFU.RCP64H, ~2^-20) + two Newton steps on the FP64 pipe.
 // Used for pivots, which are well inside the normal range (no denormal / inf handling needed).
 __device__ __forceinline__ double fast_rcp(double d) {
+#ifdef HFL_EXACT_RCP
+    return __drcp_rn(d);
+#endif
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
     double e = fma(-d, r, 1.0);

@@ -1,30 +1,258 @@
 // K1: coarse P1 FEM nodal solve, replaces FEMLSSVRPrimalSolver.solve_fem (P:117-145).
 //
 // The reference assembles the P1 stiffness and a 2-point-Gauss load with scikit-fem, turns the two
-// boundary rows into identity rows and calls a sparse direct solver.  Here the same rounded entries
-// (k_e = fl(1/h)^2 * (h/2) summed over the two Gauss points, d_i = fl(k_{i-1} + k_i), load by the same
-// two-point rule) are formed on the fly from the node array and the tridiagonal system is solved by a
-// two-level partition method whose reduced systems are solved by parallel cyclic reduction (PCR):
+// boundary rows into identity rows and calls a sparse direct solver.  Here the same rounded matrix entries
+// (k_e = fl(1/h)^2 * (h/2) summed over the two Gauss points, d_i = fl(k_{i-1} + k_i)) and the same two-point
+// load are formed on the fly from the node array and the tridiagonal system is solved by a two-level
+// partition method:
 //
-//   level 0  tiles of T*S = 2048 nodes, one CTA each.  Every thread eliminates the S-1 interior nodes
-//            of its chunk (two sweeps give the first/last entries of T^-1 b, T^-1 l e_1, T^-1 r e_s and of
-//            the "leak" 1 + v + w), the T-1 chunk heads form a tridiagonal system solved by PCR in shared
-//            memory (4 right-hand sides in the reduce pass; the back-substitution pass reuses the stored
-//            head solutions).
-//   top      one CTA solves the system of tile heads the same way (chunk per thread + PCR).
+//   level 0  tiles of FT * FS = 2048 nodes, one CTA each; thread t owns the chunk of FS = 8 consecutive nodes
+//            8 t .. 8 t + 7 (head + 7 interior) and keeps its rows in REGISTERS: it loads its nine nodes with
+//            vector loads, forms its eight elements itself (the element left of the head comes from the
+//            neighbouring thread through shared memory) and never stages a row in shared memory.
+//            pass 1 (fem_reduce_kernel): two interleaved sweeps eliminate the chunk interior (first / last
+//            entries of T^-1 b, T^-1 l e_1, T^-1 r e_s and of the "leak" 1 + v + w), the 255 chunk heads form a
+//            tridiagonal system reduced by CYCLIC REDUCTION in shared memory (7 levels, active rows compacted
+//            onto the first warps: 247 row updates per tile instead of the 255 x 8 of a parallel cyclic
+//            reduction with four right-hand sides); every head keeps its final row (L/d, R/d, B/d) for pass 2, and
+//            two threads walk the two root-to-leaf paths of the reduction tree to express the tile's first and last
+//            interior node through the two tile heads: the 12-number tile record.
+//   top      one CTA solves the system of tile heads (chunk per thread + parallel cyclic reduction).
+//            pass 2 (fem_backsub_kernel): tile heads known -> chunk heads by the back-substitution of the cyclic
+//            reduction (8 levels, one fused multiply-add pair per head) -> chunk interiors by Thomas in
+//            registers -> u with 16-byte stores.
 //
+// The load uses sin(k pi x_q) = S cos(theta) + C sin(theta), (S, C) = sincospi of the chunk's head node and
+// theta = k pi (x_q - x_head) by a short Taylor polynomial when the chunk spans less than 1/16 rad (any mesh of
+// more than ~800 k nodes), the library sinpi otherwise: ~12 FP64 instructions per Gauss point instead of ~45.
 // Every elimination runs in row-sum form (l, sigma, r), d = sigma - l - r (hfl_fem.cuh): no cancellation,
 // ~1e-14 from the exact solution of the rounded system where LU-type solvers lose cond * eps.
-// Kernels: fem_reduce_kernel -> fem_top_kernel -> fem_backsub_kernel.  Node traffic: the node array
-// is read twice and u written once (24 B/node) plus 3 B/node of head solutions; the load is recomputed
-// in the second pass instead of stored (re-reading it measured slower than two sinpi per element).
+// Node traffic: the node array is read twice and u written once (24 B/node) plus 3 B/node of head rows; the
+// element terms are recomputed in the second pass instead of stored (16 B/node each way would cost more).
+#include <type_traits>
 #include "hfl_fem.cuh"
 
 namespace hfl {
 
-// Interior of a chunk (rows m0+1 .. m0+S-1): first / last entries of the three partial solutions
-// x = y - u_head v - u_next w and the "leaks" e = 1 + v + w, all formed without cancellation.
-// out = {y1, v1, w1, e1, ys, vs, ws, es}.
+// ---------------------------------------------------------------------------------------------------------
+// Element terms.
+
+// Taylor polynomial of the forcing about the chunk's head node: (k pi)^2 sin(k pi (x_ref + dx)) = sum_j tc[j] dx^j,
+// tc[j] = ta[j] * (sin | cos)(k pi x_ref).  TIER 1: degree 9, |k pi dx| <= 2^-4 (truncation < 3e-19 of the amplitude);
+// TIER 2: degree 4, |k pi dx| <= 2^-10 (truncation < 1e-17).
+template <int TIER>
+struct ForcingPoly {
+    static constexpr int DEG = (TIER == 2) ? 4 : 9;
+    double tc[DEG + 1];
+    __device__ __forceinline__ void init(const FemArgs& a, double S, double C) {
+#pragma unroll
+        for (int j = 0; j <= DEG; ++j) tc[j] = a.ta[j] * ((j & 1) ? C : S);
+    }
+    __device__ __forceinline__ double eval(double dx) const {
+        double p = tc[DEG];
+#pragma unroll
+        for (int j = DEG - 1; j >= 0; --j) p = fma(p, dx, tc[j]);
+        return p;
+    }
+};
+template <>
+struct ForcingPoly<0> {
+    __device__ __forceinline__ void init(const FemArgs&, double, double) {}
+    __device__ __forceinline__ double eval(double) const { return 0.0; }
+};
+
+// Stiffness entry and load shares of one element of the reference's Poisson problem.  k carries the reference's
+// rounding (P:125-136 through scikit-fem's quadrature loop: fl(fl(1/h)^2 * (h W_q)) twice) because the row-sum
+// residues of the assembled diagonal depend on its last bit; the load (2-point Gauss, P:129-136) is formed with
+// fused multiply-adds.  TIER 0: library sinpi at the Gauss points; TIER 1, 2: the chunk's Taylor polynomial.
+template <int TIER>
+__device__ __forceinline__ void element_terms_fast(const FemArgs& a, double x0, double x1, double xref,
+                                                   const ForcingPoly<TIER>& fp, double& k, double& Ls, double& Rs) {
+    const double h = x1 - x0;
+    const double invh = __drcp_rn(h);                // = fl(1 / h), the same bits as __ddiv_rn(1.0, h)
+    const double gg = __dmul_rn(invh, invh);
+    const double hw = 0.5 * h;                       // |detDF| * W_q
+    const double kq = __dmul_rn(gg, hw);
+    k = __dadd_rn(kq, kq);
+    double f0, f1;
+    if (TIER == 0) {
+        const double xq0 = __dadd_rn(__dmul_rn(h, a.gx0), x0), xq1 = __dadd_rn(__dmul_rn(h, a.gx1), x0);
+        f0 = a.kp2 * sinpi(__dmul_rn(a.k, xq0));     // sin(k pi x) without the argument-reduction slow path
+        f1 = a.kp2 * sinpi(__dmul_rn(a.k, xq1));
+    } else {
+        const double d0 = x0 - xref;
+        f0 = fp.eval(fma(h, a.gx0, d0));
+        f1 = fp.eval(fma(h, a.gx1, d0));
+    }
+    Ls = hw * fma(f0, 1.0 - a.gx0, f1 * (1.0 - a.gx1));
+    Rs = hw * fma(f0, a.gx0, f1 * a.gx1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-thread chunk: local nodes m0 .. m0 + FS - 1 of the tile, global nodes g0 .. g0 + FS - 1.
+template <bool GENERAL>
+struct Chunk {
+    double k[FS + 1];             // k[j] = stiffness of the element LEFT of node g0 + j (global element g0 - 1 + j)
+    double b[FS];                 // load of node g0 + i
+    double s[GENERAL ? FS : 1];   // general operator: mass-matrix row sum of node g0 + i
+};
+
+constexpr int EXW = 3;            // doubles per thread in the element exchange: k, Rs, sR of the thread's last element
+
+// First half: loads the chunk's nodes, forms elements j = 1 .. FS (left of nodes g0 + 1 .. g0 + FS), publishes the last
+// one for the next thread; thread 0 forms the element left of its head itself.  Call __syncthreads(), then
+// chunk_build_finish.  SPECIAL = the tile holds a Dirichlet node or padding past the mesh.
+template <bool SPECIAL, bool GENERAL>
+__device__ __forceinline__ void chunk_build_start(const FemArgs& a, long long g0, double* __restrict__ ex, Chunk<GENERAL>& c,
+                                                  double& k0, double& r0, double& s0) {
+    const int t = threadIdx.x;
+    double x[FS + 1];
+    if (!SPECIAL) {
+        const double* p = a.nodes + g0;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < FS; i += 2) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(p + i));
+                x[i] = v.x; x[i + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < FS; ++i) x[i] = __ldg(p + i);
+        }
+        x[FS] = __ldg(p + FS);
+    } else {
+#pragma unroll
+        for (int i = 0; i <= FS; ++i) x[i] = __ldg(a.nodes + min(g0 + i, a.n - 1));
+    }
+    int tier = 0;
+    double S = 0.0, C = 0.0;
+    if (!SPECIAL && !GENERAL) {
+        const double span = fabs(a.kpi * (x[FS] - x[0]));
+        tier = (span <= 0.0009765625) ? 2 : ((span <= 0.0625) ? 1 : 0);
+#ifdef HFL_FEM_NO_TAYLOR
+        tier = 0;
+#endif
+        if (tier != 0) sincospi(__dmul_rn(a.k, x[0]), &S, &C);
+    }
+    double Ls[FS + 1], Rs[FS + 1], sL[GENERAL ? FS + 1 : 1], sR[GENERAL ? FS + 1 : 1];
+    auto elements = [&](auto tier_tag) {
+        constexpr int TIER = decltype(tier_tag)::value;
+        ForcingPoly<TIER> fp;
+        fp.init(a, S, C);
+#pragma unroll
+        for (int j = 1; j <= FS; ++j) {
+            const bool valid = !SPECIAL || (g0 + j <= a.n - 1);
+            double k = 0.0, l = 0.0, r = 0.0, sl = 0.0, sr = 0.0;
+            if (valid) {
+                if (GENERAL) element_terms_general(a, g0 - 1 + j, x[j - 1], x[j], k, sl, sr, l, r);
+                else element_terms_fast<TIER>(a, x[j - 1], x[j], x[0], fp, k, l, r);
+            }
+            c.k[j] = k; Ls[j] = l; Rs[j] = r;
+            if (GENERAL) { sL[j] = sl; sR[j] = sr; }
+        }
+    };
+    if (tier == 2) elements(std::integral_constant<int, 2>{});
+    else if (tier == 1) elements(std::integral_constant<int, 1>{});
+    else elements(std::integral_constant<int, 0>{});
+#pragma unroll
+    for (int i = 0; i < FS; ++i) {
+        c.b[i] = Ls[i + 1] + ((i >= 1) ? Rs[i] : 0.0);
+        if (GENERAL) c.s[i] = sL[i + 1] + ((i >= 1) ? sR[i] : 0.0);
+    }
+    ex[0 * FT + t] = c.k[FS];
+    ex[1 * FT + t] = Rs[FS];
+    if (GENERAL) ex[2 * FT + t] = sR[FS];
+    k0 = 0.0; r0 = 0.0; s0 = 0.0;
+    if (t == 0 && g0 >= 1 && g0 <= a.n - 1) {      // element left of the tile head: nobody in this CTA owns it
+        const double xm = __ldg(a.nodes + g0 - 1);
+        double l, sl = 0.0;
+        if (GENERAL) element_terms_general(a, g0 - 1, xm, x[0], k0, sl, s0, l, r0);
+        else element_terms_fast<0>(a, xm, x[0], 0.0, ForcingPoly<0>{}, k0, l, r0);
+    }
+}
+
+template <bool GENERAL>
+__device__ __forceinline__ void chunk_build_finish(const double* __restrict__ ex, Chunk<GENERAL>& c, double k0, double r0,
+                                                   double s0) {
+    const int t = threadIdx.x;
+    if (t >= 1) {
+        k0 = ex[0 * FT + t - 1];
+        r0 = ex[1 * FT + t - 1];
+        if (GENERAL) s0 = ex[2 * FT + t - 1];
+    }
+    c.k[0] = k0;
+    c.b[0] += r0;
+    if (GENERAL) c.s[0] += s0;
+}
+
+// Row i of the chunk in (l, sigma, r, b) form (hfl_fem.cuh explains the row-sum form).
+template <bool SPECIAL, bool GENERAL, bool EXACT>
+__device__ __forceinline__ void chunk_row(const Chunk<GENERAL>& c, int i, long long g0, const FemArgs& a, double& l,
+                                          double& sg, double& r, double& b) {
+    if (SPECIAL) {
+        const long long g = g0 + i;
+        if (g >= a.n) { l = 0.0; sg = 1.0; r = 0.0; b = 0.0; return; }
+        if (g == 0) { l = 0.0; sg = 1.0; r = 0.0; b = a.uL; return; }
+        if (g == a.n - 1) { l = 0.0; sg = 1.0; r = 0.0; b = a.uR; return; }
+    }
+    const double kl = c.k[i], kr = c.k[i + 1];
+    l = -kl; r = -kr;
+    b = c.b[i];
+    if (GENERAL) { sg = c.s[i]; return; }              // mass-matrix row sum, assembled without cancellation
+    if (EXACT) { sg = 0.0; return; }                   // HFL_COARSE_ASSEMBLED_EXACT: unrounded diagonal kl + kr
+    // d = fl(kl + kr) is the reference's assembled diagonal; kl + kr = d + err exactly (TwoSum), so sigma = -err
+    const double d = __dadd_rn(kl, kr);
+    const double tt = __dsub_rn(d, kl);
+    sg = -__dadd_rn(__dsub_rn(kl, __dsub_rn(d, tt)), __dsub_rn(kr, tt));
+}
+
+// Diagonal of a row from its row sum and its two off-diagonal entries, d = sigma - (p + q): a sum of same-signed terms,
+// and bitwise symmetric in (p, q).  Every elimination below forms its left / right quantities by mirror-image
+// operations with explicitly rounded products (no fused contraction chosen by the compiler): on a (nearly) uniform mesh
+// the roundings of the two directions then agree instead of differing by a systematic fraction of an ulp - the
+// reduction tree doubles such a left / right bias at every level (2^17 from the chunk to the top of a 1e7-node mesh),
+// which showed up as 1e-11 instead of 1e-14.
+__device__ __forceinline__ double diag_of(double sg, double p, double q) { return __dsub_rn(sg, __dadd_rn(p, q)); }
+
+// Interior of the chunk (rows 1 .. FS-1): first / last entries of the three partial solutions
+// x = y - u_head v - u_next w and the "leaks" e = 1 + v + w, all formed without cancellation; the forward and the
+// backward sweep are independent chains and run interleaved.  out = {y1, v1, w1, e1, ys, vs, ws, es}.
+template <bool SPECIAL, bool GENERAL, bool EXACT>
+__device__ __forceinline__ void chunk_reduce_reg(const Chunk<GENERAL>& c, long long g0, const FemArgs& a, double (&out)[8]) {
+    double l, sg, r, b;
+    // forward: transformed row i has entries (head: v, i: d, i+1: r); tp = v + d + r is its row sum
+    chunk_row<SPECIAL, GENERAL, EXACT>(c, 1, g0, a, l, sg, r, b);
+    double tpf = sg, vpf = l, rpf = r, bpf = b, dpf = diag_of(tpf, vpf, rpf);
+    // backward: entries (i-1: l, i: d, next head: w)
+    chunk_row<SPECIAL, GENERAL, EXACT>(c, FS - 1, g0, a, l, sg, r, b);
+    double tpb = sg, bpb = b, wpb = r, lpb = l, dpb = diag_of(tpb, wpb, lpb);
+    // division-free elimination: row_i <- d_prev row_i - l_i row_prev (every product keeps its sign, so the row sums stay
+    // sums of same-signed terms); the rows grow by ~d per step, 7 steps stay far inside the double range, and the only
+    // reciprocals are the two at the end.  The two sweeps are exact mirror images of each other, operation by operation
+    // and rounding by rounding (no compiler contraction): see diag_of.
+#pragma unroll
+    for (int s = 2; s < FS; ++s) {
+        chunk_row<SPECIAL, GENERAL, EXACT>(c, s, g0, a, l, sg, r, b);
+        tpf = __fma_rn(dpf, sg, __dmul_rn(-l, tpf));
+        vpf = __dmul_rn(-l, vpf);
+        bpf = fma(dpf, b, -l * bpf);
+        rpf = __dmul_rn(dpf, r);
+        dpf = diag_of(tpf, vpf, rpf);
+        chunk_row<SPECIAL, GENERAL, EXACT>(c, FS - s, g0, a, l, sg, r, b);
+        tpb = __fma_rn(dpb, sg, __dmul_rn(-r, tpb));
+        wpb = __dmul_rn(-r, wpb);
+        bpb = fma(dpb, b, -r * bpb);
+        lpb = __dmul_rn(dpb, l);
+        dpb = diag_of(tpb, wpb, lpb);
+    }
+    const double invf = fast_rcp(dpf), invb = fast_rcp(dpb);
+    out[4] = bpf * invf; out[5] = __dmul_rn(vpf, invf); out[6] = __dmul_rn(rpf, invf); out[7] = __dmul_rn(tpf, invf);
+    out[0] = bpb * invb; out[1] = __dmul_rn(lpb, invb); out[2] = __dmul_rn(wpb, invb); out[3] = __dmul_rn(tpb, invb);
+}
+
+// Chunk interior of the top level: rows through a getter with run-time indices (the rows live in shared or global
+// memory), chunk length S up to TOP_MAX_CHUNK.  Same partial solutions as chunk_reduce_reg, with a reciprocal per row
+// (a division-free sweep would overflow on long chunks); the two sweeps run interleaved.
 template <class Rows>
 __device__ __forceinline__ void chunk_reduce(const Rows& rows, int m0, int S, double (&out)[8]) {
     if (S < 2) {   // no interior: neighbouring heads couple directly (x_first = u_next, x_last = u_head)
@@ -33,92 +261,29 @@ __device__ __forceinline__ void chunk_reduce(const Rows& rows, int m0, int S, do
         return;
     }
     double l, sg, r, b;
-    // forward: transformed row i has entries (head: v, i: d, i+1: r); tp = v + d + r is its row sum
     rows.get(m0 + 1, l, sg, r, b);
-    double tp = sg, vp = l, rp = r, bp = b;
-    double dp = tp - vp - rp;
-    for (int i = 2; i < S; ++i) {
-        rows.get(m0 + i, l, sg, r, b);
-        const double m = l * fast_rcp(dp);        // <= 0
-        tp = fma(-m, tp, sg);
-        vp = -m * vp;
-        bp = fma(-m, bp, b);
-        rp = r;
-        dp = tp - vp - rp;
-    }
-    double inv = fast_rcp(dp);
-    out[4] = bp * inv; out[5] = vp * inv; out[6] = rp * inv; out[7] = tp * inv;
-    // backward: entries (i-1: l, i: d, next head: w)
+    double tpf = sg, vpf = l, rpf = r, bpf = b, dpf = diag_of(tpf, vpf, rpf);
     rows.get(m0 + S - 1, l, sg, r, b);
-    tp = sg; bp = b;
-    double wp = r, lp = l;
-    dp = tp - lp - wp;
-    for (int i = S - 2; i >= 1; --i) {
+    double tpb = sg, bpb = b, wpb = r, lpb = l, dpb = diag_of(tpb, wpb, lpb);
+    for (int i = 2; i < S; ++i) {          // the two sweeps mirror each other rounding by rounding (see diag_of)
         rows.get(m0 + i, l, sg, r, b);
-        const double m = r * fast_rcp(dp);
-        tp = fma(-m, tp, sg);
-        wp = -m * wp;
-        bp = fma(-m, bp, b);
-        lp = l;
-        dp = tp - lp - wp;
+        const double mf = __dmul_rn(l, fast_rcp(dpf));
+        tpf = __fma_rn(-mf, tpf, sg);
+        vpf = __dmul_rn(-mf, vpf);
+        bpf = fma(-mf, bpf, b);
+        rpf = r;
+        dpf = diag_of(tpf, vpf, rpf);
+        rows.get(m0 + S - i, l, sg, r, b);
+        const double mb = __dmul_rn(r, fast_rcp(dpb));
+        tpb = __fma_rn(-mb, tpb, sg);
+        wpb = __dmul_rn(-mb, wpb);
+        bpb = fma(-mb, bpb, b);
+        lpb = l;
+        dpb = diag_of(tpb, wpb, lpb);
     }
-    inv = fast_rcp(dp);
-    out[0] = bp * inv; out[1] = lp * inv; out[2] = wp * inv; out[3] = tp * inv;
-}
-
-// Parallel cyclic reduction over equations first..last (one per thread, index = thread id), NR right-hand
-// sides, rows as (l, sigma, r).  sm holds 2 * (3 + NR) * T doubles.  Every thread of the CTA must call this.
-template <int NR, int T>
-__device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last, double l, double sg, double r,
-                                          double (&rhs)[NR], double (&x)[NR]) {
-    constexpr int W = 3 + NR;
-    int cur = 0;
-    const bool active = (t >= first && t <= last);
-    {
-        double* bufw = sm + cur * W * T;
-        bufw[0 * T + t] = l; bufw[1 * T + t] = sg; bufw[2 * T + t] = r;
-#pragma unroll
-        for (int q = 0; q < NR; ++q) bufw[(3 + q) * T + t] = rhs[q];
-    }
-    __syncthreads();
-    const int count = last - first + 1;
-    for (int delta = 1; delta < count; delta <<= 1) {
-        const double* bufr = sm + cur * W * T;
-        double* bufw = sm + (cur ^ 1) * W * T;
-        if (active) {
-            const int im = t - delta, ip = t + delta;
-            double sn = sg, ln = 0.0, rn = 0.0;
-            if (im >= first) {
-                const double lm = bufr[0 * T + im], sm_ = bufr[1 * T + im], rm = bufr[2 * T + im];
-                const double al = -l * fast_rcp(sm_ - lm - rm);      // >= 0
-                sn = fma(al, sm_, sn);
-                ln = al * lm;
-#pragma unroll
-                for (int q = 0; q < NR; ++q) rhs[q] = fma(al, bufr[(3 + q) * T + im], rhs[q]);
-            } else {
-                sn -= l;          // no such neighbour: l is 0 here by construction
-            }
-            if (ip <= last) {
-                const double lq = bufr[0 * T + ip], sq = bufr[1 * T + ip], rq = bufr[2 * T + ip];
-                const double be = -r * fast_rcp(sq - lq - rq);
-                sn = fma(be, sq, sn);
-                rn = be * rq;
-#pragma unroll
-                for (int q = 0; q < NR; ++q) rhs[q] = fma(be, bufr[(3 + q) * T + ip], rhs[q]);
-            } else {
-                sn -= r;
-            }
-            l = ln; sg = sn; r = rn;
-        }
-        bufw[0 * T + t] = l; bufw[1 * T + t] = sg; bufw[2 * T + t] = r;
-#pragma unroll
-        for (int q = 0; q < NR; ++q) bufw[(3 + q) * T + t] = rhs[q];
-        __syncthreads();
-        cur ^= 1;
-    }
-    const double inv = fast_rcp(sg - l - r);
-#pragma unroll
-    for (int q = 0; q < NR; ++q) x[q] = rhs[q] * inv;
+    const double invf = fast_rcp(dpf), invb = fast_rcp(dpb);
+    out[4] = bpf * invf; out[5] = __dmul_rn(vpf, invf); out[6] = __dmul_rn(rpf, invf); out[7] = __dmul_rn(tpf, invf);
+    out[0] = bpb * invb; out[1] = __dmul_rn(lpb, invb); out[2] = __dmul_rn(wpb, invb); out[3] = __dmul_rn(tpb, invb);
 }
 
 // Reduced equation of a chunk head from its own row (lp, sp, rp, bp), the previous chunk's {ys, vs, ws, es} and
@@ -126,75 +291,141 @@ __device__ __forceinline__ void pcr_solve(double* sm, int t, int first, int last
 __device__ __forceinline__ void head_equation(double lp, double sp, double rp, double bp, double ys_prev,
                                               double vs_prev, double es_prev, const double (&e8)[8], double& L,
                                               double& S, double& R, double& B) {
-    L = -lp * vs_prev;
-    R = -rp * e8[2];
-    S = fma(-rp, e8[3], fma(-lp, es_prev, sp));
+    L = __dmul_rn(-lp, vs_prev);
+    R = __dmul_rn(-rp, e8[2]);
+    S = __dadd_rn(sp, __dadd_rn(__dmul_rn(-lp, es_prev), __dmul_rn(-rp, e8[3])));      // mirror-symmetric (see diag_of)
     B = fma(-rp, e8[0], fma(-lp, ys_prev, bp));
 }
 
-// Level 0, pass 1: one record per tile = {l, sigma, r, b of the tile head, y1, v1, w1, e1, ys, vs, ws, es of the interior}.
+// Shared-memory index of chunk head i (0 .. FT; index FT = the next tile's head): one pad per 16 doubles keeps the
+// strided accesses of the cyclic reduction (stride 2, 4, ..., 128 heads) free of bank conflicts.
+__host__ __device__ constexpr int cp(int i) { return i + (i >> 4); }
+constexpr int CRLEN = cp(FT) + 1;
+
+// Forward cyclic reduction over rows 1 .. N-1 (rows as (l, sigma, r, b) at padded index cp(i); index 0 and index N are
+// unknown columns without rows of their own).  Level delta updates the rows at multiples of 2 delta from their
+// neighbours at distance delta; the active rows are compacted onto the first threads, and once a level fits one warp
+// the remaining levels run on warp 0 alone behind __syncwarp (no CTA barrier, nobody else executes the loop).
+// Every thread of the CTA must call this; ends with a CTA barrier.  Afterwards the row of index i is final for its level
+// (it couples to i -+ lowbit(i)).
+template <int N>
+__device__ __forceinline__ void cr_forward(double* sL, double* sS, double* sR, double* sB, int t) {
+    auto update = [&](int lv) {
+        const int delta = 1 << lv, i = (t + 1) << (lv + 1);
+        const int im = cp(i - delta), ip = cp(i + delta), ii = cp(i);
+        const double lm = sL[im], sm_ = sS[im], rm = sR[im], bm = sB[im];
+        const double lq = sL[ip], sq = sS[ip], rq = sR[ip], bq = sB[ip];
+        const double al = __dmul_rn(-sL[ii], fast_rcp(diag_of(sm_, lm, rm)));      // >= 0
+        const double be = __dmul_rn(-sR[ii], fast_rcp(diag_of(sq, lq, rq)));
+        sL[ii] = __dmul_rn(al, lm);
+        sR[ii] = __dmul_rn(be, rq);
+        sS[ii] = __dadd_rn(sS[ii], __dadd_rn(__dmul_rn(al, sm_), __dmul_rn(be, sq)));  // mirror-symmetric (see diag_of)
+        sB[ii] = fma(be, bq, fma(al, bm, sB[ii]));
+    };
+    int lv = 0;
+#pragma unroll 1
+    for (; (N >> (lv + 1)) - 1 > 32; ++lv) {
+        if (t < (N >> (lv + 1)) - 1) update(lv);
+        __syncthreads();
+    }
+    if (t < 32) {
+#pragma unroll 1
+        for (; (2 << lv) < N; ++lv) {
+            if (t < (N >> (lv + 1)) - 1) update(lv);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+
+// Level 0, pass 1.  Tile record (SoA, rec[f * ntile + tile]): f = 0..3 {l, sigma, r, b} of the tile head's row,
+// 4..7 {y, v, w, e} of the tile's first interior node, 8..11 of its last one (x = y - v u_P - w u_Q, e = 1 + v + w).
+// heads[tile][3][FT]: final cyclic-reduction row {L/d, R/d, B/d} of every chunk head.
 template <bool SPECIAL, bool GENERAL, bool EXACT>
-__device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __restrict__ rec, double* __restrict__ yvw,
-                                                double* sm) {
+__device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __restrict__ rec, double* __restrict__ heads,
+                                                double* s_ex, double* s_ex2, double* s_cr) {
     const int t = threadIdx.x;
-    const long long P = (long long)blockIdx.x * FTS;
-    MeshRows<SPECIAL, GENERAL, EXACT> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
+    const long long g0 = (long long)blockIdx.x * FTS + (long long)t * FS;
+    Chunk<GENERAL> c;
+    double k0, r0, s0;
+    chunk_build_start<SPECIAL, GENERAL>(a, g0, s_ex, c, k0, r0, s0);
+    __syncthreads();
+    chunk_build_finish<GENERAL>(s_ex, c, k0, r0, s0);
     double e8[8];
-    chunk_reduce(rows, t * FS, FS, e8);
+    chunk_reduce_reg<SPECIAL, GENERAL, EXACT>(c, g0, a, e8);
     double lp, sp, rp, bp;
-    rows.get(t * FS, lp, sp, rp, bp);
-    __syncthreads();                 // the element arrays are dead from here: exchange / PCR buffers alias them
-    double* ex = sm + SM_EX;
-    ex[0 * FT + t] = e8[4]; ex[1 * FT + t] = e8[5]; ex[2 * FT + t] = e8[7];     // ys, vs, es of this chunk
+    chunk_row<SPECIAL, GENERAL, EXACT>(c, 0, g0, a, lp, sp, rp, bp);
+    s_ex2[0 * FT + t] = e8[4]; s_ex2[1 * FT + t] = e8[5]; s_ex2[2 * FT + t] = e8[7];     // ys, vs, es of this chunk
     __syncthreads();
-    double l = 0.0, sg = 1.0, r = 0.0, rhs[4] = {0.0, 0.0, 0.0, 0.0}, x[4];
+    double* sL = s_cr; double* sS = s_cr + CRLEN; double* sR = s_cr + 2 * CRLEN; double* sB = s_cr + 3 * CRLEN;
     if (t >= 1) {
-        double B;
-        head_equation(lp, sp, rp, bp, ex[0 * FT + t - 1], ex[1 * FT + t - 1], ex[2 * FT + t - 1], e8, l, sg, r, B);
-        rhs[0] = B;
-        rhs[3] = sg;                                       // T (1 + V + W) = full row sums  ->  E = 1 + V + W
-        if (t == 1) { rhs[1] = l; sg -= l; l = 0.0; }      // coupling to the tile head moves to the right-hand side
-        if (t == FT - 1) { rhs[2] = r; sg -= r; r = 0.0; } // ... and the one to the next tile's head
+        double L, S, R, B;
+        head_equation(lp, sp, rp, bp, s_ex2[0 * FT + t - 1], s_ex2[1 * FT + t - 1], s_ex2[2 * FT + t - 1], e8, L, S, R, B);
+        sL[cp(t)] = L; sS[cp(t)] = S; sR[cp(t)] = R; sB[cp(t)] = B;
     }
-    __syncthreads();                 // ex is consumed; the PCR buffers alias it
-    pcr_solve<4, FT>(sm + SM_PCR, t, 1, FT - 1, l, sg, r, rhs, x);
-    {   // chunk-head partial solutions, read back by the back-substitution pass
-        double* o = yvw + (size_t)blockIdx.x * 3 * FT;
-        o[t] = x[0]; o[FT + t] = x[1]; o[2 * FT + t] = x[2];
-    }
-    // x = {Y, V, W, E} of head t.  The tile's first interior node belongs to chunk 0 (it needs head 1's
-    // solution), its last interior node to chunk T-1.
     __syncthreads();
-    double* xb = sm;                 // 4 doubles: head 1's solution for thread 0
-    if (t == 1) { xb[0] = x[0]; xb[1] = x[1]; xb[2] = x[2]; xb[3] = x[3]; }
-    __syncthreads();
-    double* out = rec + (long long)blockIdx.x * REC;
-    if (t == 0) {
-        const double Y1 = xb[0], V1 = xb[1], W1 = xb[2], E1 = xb[3];
-        out[0] = lp; out[1] = sp; out[2] = rp; out[3] = bp;
-        out[4] = fma(-e8[2], Y1, e8[0]);
-        out[5] = fma(-e8[2], V1, e8[1]);
-        out[6] = -e8[2] * W1;
-        out[7] = fma(-e8[2], E1, e8[3]);
+    // cyclic reduction over heads 1 .. FT-1; heads 0 (this tile's) and FT (the next tile's) stay as unknown columns
+    cr_forward<FT>(sL, sS, sR, sB, t);
+    if (t >= 1) {        // every head's row is final: scale by its diagonal, keep it for the back-substitution pass
+        const int ii = cp(t);
+        const double L = sL[ii], S = sS[ii], R = sR[ii], B = sB[ii];
+        const double inv = fast_rcp(diag_of(S, L, R));
+        const double Ld = __dmul_rn(L, inv), Rd = __dmul_rn(R, inv), Bd = B * inv;
+        sL[ii] = Ld; sR[ii] = Rd; sB[ii] = Bd; sS[ii] = __dmul_rn(S, inv);
+        double* o = heads + (size_t)blockIdx.x * 3 * FT;
+        o[t] = Ld; o[FT + t] = Rd; o[2 * FT + t] = Bd;
+    } else {             // slot 0 is the tile head itself (solved at the top level)
+        double* o = heads + (size_t)blockIdx.x * 3 * FT;
+        o[0] = 0.0; o[FT] = 0.0; o[2 * FT] = 0.0;
     }
-    if (t == FT - 1) {
-        out[8] = fma(-e8[5], x[0], e8[4]);
-        out[9] = -e8[5] * x[1];
-        out[10] = fma(-e8[5], x[2], e8[6]);
-        out[11] = fma(-e8[5], x[3], e8[7]);
+    __syncthreads();
+    const long long nt = gridDim.x;
+    double* out = rec + blockIdx.x;
+    if (t == 0 || t == FT - 1) {
+        // head FT/2 through the two tile heads, then down the tree to head 1 (t = 0) or head FT-1 (t = FT-1):
+        // u = Y - V u_P - W u_Q, E = 1 + V + W
+        int i = cp(FT / 2);
+        double Y = sB[i], V = sL[i], W = sR[i], E = sS[i];
+        if (t == 0) {
+#pragma unroll 1
+            for (int delta = FT / 4; delta >= 1; delta >>= 1) {        // node delta: left neighbour 0, right neighbour 2 delta
+                i = cp(delta);
+                const double Rd = sR[i];
+                Y = fma(-Rd, Y, sB[i]); V = __fma_rn(-Rd, V, sL[i]); W = __dmul_rn(-Rd, W); E = __fma_rn(-Rd, E, sS[i]);
+            }
+            out[0 * nt] = lp; out[1 * nt] = sp; out[2 * nt] = rp; out[3 * nt] = bp;
+            out[4 * nt] = fma(-e8[2], Y, e8[0]);
+            out[5 * nt] = __fma_rn(-e8[2], V, e8[1]);
+            out[6 * nt] = __dmul_rn(-e8[2], W);
+            out[7 * nt] = __fma_rn(-e8[2], E, e8[3]);
+        } else {
+#pragma unroll 1
+            for (int delta = FT / 4; delta >= 1; delta >>= 1) {        // node FT - delta: left neighbour FT - 2 delta, right FT
+                i = cp(FT - delta);
+                const double Ld = sL[i];
+                Y = fma(-Ld, Y, sB[i]); V = __dmul_rn(-Ld, V); W = __fma_rn(-Ld, W, sR[i]); E = __fma_rn(-Ld, E, sS[i]);
+            }
+            out[8 * nt] = fma(-e8[5], Y, e8[4]);
+            out[9 * nt] = __dmul_rn(-e8[5], V);
+            out[10 * nt] = __fma_rn(-e8[5], W, e8[6]);
+            out[11 * nt] = __fma_rn(-e8[5], E, e8[7]);
+        }
     }
 }
 
 template <bool GENERAL, bool EXACT = false>
-__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_reduce_kernel(const FemArgs a_in, double* __restrict__ rec,
-                                                                         double* __restrict__ yvw) {
-    extern __shared__ double sm[];
+#ifndef HFL_FEM_MINB
+#define HFL_FEM_MINB 3
+#endif
+__global__ void __launch_bounds__(FT, HFL_FEM_MINB) fem_reduce_kernel(const FemArgs a_in, double* __restrict__ rec,
+                                                           double* __restrict__ heads) {
+    __shared__ double s_ex[EXW * FT], s_ex2[3 * FT], s_cr[4 * CRLEN];
     const FemArgs a = select_rhs(a_in);
-    rec += (size_t)blockIdx.y * a.ws_stride; yvw += (size_t)blockIdx.y * a.ws_stride;
+    rec += (size_t)blockIdx.y * a.ws_stride; heads += (size_t)blockIdx.y * a.ws_stride;
     const long long P = (long long)blockIdx.x * FTS;
-    load_tile_elements<GENERAL>(a, P, sm);
-    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true, GENERAL, EXACT>(a, rec, yvw, sm);
-    else fem_reduce_body<false, GENERAL, EXACT>(a, rec, yvw, sm);
+    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true, GENERAL, EXACT>(a, rec, heads, s_ex, s_ex2, s_cr);
+    else fem_reduce_body<false, GENERAL, EXACT>(a, rec, heads, s_ex, s_ex2, s_cr);
 }
 
 // Thomas elimination of a chunk interior between two known head values, in (l, sigma, r) form: s = row sum over
@@ -208,10 +439,15 @@ __device__ __forceinline__ void thomas_step(double l, double sg, double r, doubl
     q = s * inv;
 }
 
-// Top level: solve the system of tile heads.  One CTA of TOPT threads, chunk of S heads per thread.
-// SMEM_ROWS: the rows (l, sigma, r, b) [4][cnt] live in shared memory behind the 8 * TOPT doubles of PCR buffers
-// (small meshes, see the launch); otherwise in the workspace (wsrows).  The chunk sweeps walk their rows with
-// dependent loads, so the shared-memory variant removes ~4 S L2 round trips from this serial kernel.
+// Top level: solve the system of tile heads.  One CTA of TOPT threads, chunk of S heads per thread: chunk interiors
+// by two interleaved sweeps, the TOPT chunk heads by cyclic reduction (forward with compacted levels, then the
+// back-substitution tree), chunk interiors by Thomas.  Head 0 is global node 0, always a Dirichlet (identity) row, so it
+// enters the reduction as a known column.  SMEM_ROWS: the rows (l, sigma, r, b) [4][cnt] live in shared memory behind
+// the reduction arrays; otherwise in the workspace (wsrows).  The tile records are SoA: the row build reads them
+// coalesced.
+constexpr int CRT = cp(TOPT) + 1;
+constexpr int TOP_SMEM_DOUBLES = 4 * CRT + 3 * TOPT;     // reduction arrays + head exchange
+
 template <bool SMEM_ROWS>
 __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict__ rec, int cnt, int S,
                                                        double* __restrict__ wsrows, double* __restrict__ utop,
@@ -219,22 +455,24 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
     extern __shared__ double sm[];
     const int t = threadIdx.x;
     rec += (size_t)blockIdx.y * ws_stride; wsrows += (size_t)blockIdx.y * ws_stride; utop += (size_t)blockIdx.y * ws_stride;
-    double* rowbase = SMEM_ROWS ? sm + 8 * TOPT : wsrows;
+    double* sL = sm; double* sS = sm + CRT; double* sR = sm + 2 * CRT; double* sB = sm + 3 * CRT;
+    double* ex = sm + 4 * CRT;
+    double* rowbase = SMEM_ROWS ? sm + TOP_SMEM_DOUBLES : wsrows;
     double* rl = rowbase; double* rs = rowbase + cnt; double* rr = rowbase + 2 * (size_t)cnt; double* rb = rowbase + 3 * (size_t)cnt;
+    const size_t nt = (size_t)cnt;
     for (int c = t; c < cnt; c += TOPT) {
-        const double* rc = rec + (size_t)c * REC;
-        double l = 0.0, sg = rc[1], b = rc[3];
+        const double* rc = rec + c;
+        const double hl = rc[0], hr = rc[2 * nt];
+        double l = 0.0, sg = rc[1 * nt], b = rc[3 * nt];
+        double leak_l = -hl;      // no tile to the left: the coupling stays in the row sum (hl is 0 for the Dirichlet head anyway)
         if (c > 0) {
-            const double* rp = rec + (size_t)(c - 1) * REC;
-            l = -rc[0] * rp[9];
-            sg = fma(-rc[0], rp[11], sg);
-            b = fma(-rc[0], rp[8], b);
-        } else {
-            sg -= rc[0];          // no tile to the left (rc[0] is 0 for the Dirichlet head anyway)
+            l = __dmul_rn(-hl, rc[9 * nt - 1]);
+            leak_l = __dmul_rn(-hl, rc[11 * nt - 1]);
+            b = fma(-hl, rc[8 * nt - 1], b);
         }
-        sg = fma(-rc[2], rc[7], sg);
-        const double r = -rc[2] * rc[6];
-        b = fma(-rc[2], rc[4], b);
+        sg = __dadd_rn(sg, __dadd_rn(leak_l, __dmul_rn(-hr, rc[7 * nt])));      // mirror-symmetric (see diag_of)
+        const double r = __dmul_rn(-hr, rc[6 * nt]);
+        b = fma(-hr, rc[4 * nt], b);
         rl[c] = l; rs[c] = sg; rr[c] = r; rb[c] = b;
     }
     __syncthreads();
@@ -243,35 +481,61 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
     chunk_reduce(rows, t * S, S, e8);
     double lp, sp, rp, bp;
     rows.get(t * S, lp, sp, rp, bp);
-    double* pcr = sm;                // 2 * 4 * TOPT
-    double* ex = sm + 4 * TOPT;      // 3 * TOPT, inside the second PCR buffer: consumed before PCR first writes there
     ex[0 * TOPT + t] = e8[4]; ex[1 * TOPT + t] = e8[5]; ex[2 * TOPT + t] = e8[7];
     __syncthreads();
-    double l = 0.0, sg = 1.0, r = 0.0, rhs[1] = {0.0}, x[1];
-    if (t >= 1) {
-        head_equation(lp, sp, rp, bp, ex[0 * TOPT + t - 1], ex[1 * TOPT + t - 1], ex[2 * TOPT + t - 1], e8, l, sg, r, rhs[0]);
-    } else {
-        // head 0 is global node 0 (identity row); its equation still carries the coupling to chunk 0's interior
-        head_equation(0.0, sp - lp, rp, bp, 0.0, 0.0, 0.0, e8, l, sg, r, rhs[0]);
+    {
+        double L, Sg, R, B;
+        if (t >= 1) {
+            head_equation(lp, sp, rp, bp, ex[0 * TOPT + t - 1], ex[1 * TOPT + t - 1], ex[2 * TOPT + t - 1], e8, L, Sg, R, B);
+            sL[cp(t)] = L; sS[cp(t)] = Sg; sR[cp(t)] = R; sB[cp(t)] = B;
+        } else {
+            // head 0 = global node 0 (identity row, no coupling to its right): its value is its right-hand side
+            head_equation(0.0, sp - lp, rp, bp, 0.0, 0.0, 0.0, e8, L, Sg, R, B);
+            sB[cp(0)] = B * fast_rcp(diag_of(Sg, L, R));
+        }
     }
-    pcr_solve<1, TOPT>(pcr, t, 0, TOPT - 1, l, sg, r, rhs, x);
-    double* uh = sm;   // head values; the PCR buffers are dead
     __syncthreads();
-    uh[t] = x[0];
+    cr_forward<TOPT>(sL, sS, sR, sB, t);
+    if (t >= 1) {
+        const int ii = cp(t);
+        const double L = sL[ii], R = sR[ii];
+        const double inv = fast_rcp(diag_of(sS[ii], L, R));
+        sL[ii] = __dmul_rn(L, inv); sR[ii] = __dmul_rn(R, inv); sB[ii] = sB[ii] * inv;
+    }
     __syncthreads();
+    // back-substitution tree; the head values overwrite the (now unused) row sums
+    double* su = sS;
+    if (t == 0) { su[cp(0)] = sB[cp(0)]; su[cp(TOPT)] = 0.0; }
+    auto level = [&](int q) {
+        const int delta = (TOPT / 2) >> q;
+        if (t < (1 << q)) {
+            const int i = delta * (2 * t + 1), ii = cp(i);
+            su[ii] = fma(-sR[ii], su[cp(i + delta)], fma(-sL[ii], su[cp(i - delta)], sB[ii]));
+        }
+    };
+    int q = 0;
+    if (t < 32) {
+        __syncwarp();
+#pragma unroll 1
+        for (; q <= 5; ++q) { level(q); __syncwarp(); }
+    }
+    q = 6;
+    __syncthreads();
+#pragma unroll 1
+    for (; (1 << q) < TOPT; ++q) { level(q); __syncthreads(); }
     const int m0 = t * S;
-    if (m0 < cnt) utop[m0] = x[0];
+    const double ua = su[cp(t)];
+    if (m0 < cnt) utop[m0] = ua;
     if (S >= 2 && m0 + 1 < cnt) {
-        const double ua = x[0];
-        const double ub = (t + 1 < TOPT) ? uh[t + 1] : 0.0;
+        const double ub = su[cp(t + 1)];
         // Thomas on rows m0+1 .. m0+S-1 with known neighbours; c', b' stay thread-private
         double tc[TOP_MAX_CHUNK], tb[TOP_MAX_CHUNK];
-        double lo, so, ro, bo, q = 1.0, cp = 0.0, bpv = ua;     // "previous row" = the known head: x = ua
+        double lo, so, ro, bo, qq = 1.0, cpv = 0.0, bpv = ua;     // "previous row" = the known head: x = ua
         for (int i = 1; i < S; ++i) {
             rows.get(m0 + i, lo, so, ro, bo);
             if (i == S - 1) bo = fma(-ro, ub, bo);
-            thomas_step(lo, so, ro, bo, q, cp, bpv);
-            tc[i] = cp; tb[i] = bpv;
+            thomas_step(lo, so, ro, bo, qq, cpv, bpv);
+            tc[i] = cpv; tb[i] = bpv;
         }
         double xv = bpv;
         if (m0 + S - 1 < cnt) utop[m0 + S - 1] = xv;
@@ -286,62 +550,132 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
     }
 }
 
-// Level 0, pass 2: tile head values known -> chunk heads from the stored partial solutions
-// (U_t = Y_t - u_P V_t - u_Q W_t) -> chunk interiors by Thomas -> u.
+// Level 0, pass 2: tile head values known -> chunk heads by the back-substitution of the cyclic reduction ->
+// chunk interiors by Thomas in registers -> u.  iface4 (optional): the end-node residuals of the multi-GPU
+// interface system (hfl.h), written by the two threads that own nodes 0 and n - 2.
 template <bool SPECIAL, bool GENERAL, bool EXACT>
 __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double* __restrict__ utop, int ntile,
-                                                 const double* __restrict__ yvw, double* __restrict__ u, double* sm) {
+                                                 const double* __restrict__ heads, double* __restrict__ u,
+                                                 double* __restrict__ iface4, double* s_ex, double* s_u) {
     const int t = threadIdx.x;
-    const long long P = (long long)blockIdx.x * FTS;
-    const double uP = utop[blockIdx.x];
-    const double uQ = ((int)blockIdx.x + 1 < ntile) ? utop[blockIdx.x + 1] : 0.0;
-    double* uh = sm + sm_uh(GENERAL);    // FT head values (+1 for the next tile's head)
-    {
-        const double* o = yvw + (size_t)blockIdx.x * 3 * FT;
-        uh[t] = (t == 0) ? uP : (o[t] - uP * o[FT + t] - uQ * o[2 * FT + t]);
-        if (t == 0) uh[FT] = uQ;
+    const long long g0 = (long long)blockIdx.x * FTS + (long long)t * FS;
+    const double* o = heads + (size_t)blockIdx.x * 3 * FT;
+    // chunk heads from the two tile heads: back-substitution of the cyclic reduction, u_i = B_i - L_i u_{i-d} - R_i u_{i+d}
+    // with d = lowbit(i).  Levels d >= 4 (the 63 heads at multiples of 4) run on warp 0 while the other warps form their
+    // elements; after the one CTA barrier every thread evaluates the two rows (d = 2, d = 1) its own u_t, u_{t+1} need.
+    const int od = t | 1;                                  // the odd one of {t, t + 1}
+    const int m2 = (od & 2) ? (od - 1) : (od + 1);      // its neighbour that is 2 mod 4 (the other one is 0 mod 4)
+    const double oL = o[od], oR = o[FT + od], oB = o[2 * FT + od];
+    const double mL = o[m2], mR = o[FT + m2], mB = o[2 * FT + m2];
+    if (t < 32) {
+        constexpr int NLV = 6;                             // d = FT/2 .. 4
+        static_assert(FT == 256, "level count of the warp-0 tree");
+        double rl[NLV], rr[NLV], rb[NLV];
+#pragma unroll
+        for (int q = 0; q < NLV; ++q) {
+            const int delta = (FT / 2) >> q, cnt = 1 << q;
+            const int i = (t < cnt) ? delta * (2 * t + 1) : delta;
+            rl[q] = o[i]; rr[q] = o[FT + i]; rb[q] = o[2 * FT + i];
+        }
+        if (t == 0) {
+            s_u[cp(0)] = utop[blockIdx.x];
+            s_u[cp(FT)] = ((int)blockIdx.x + 1 < ntile) ? utop[blockIdx.x + 1] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NLV; ++q) {
+            const int delta = (FT / 2) >> q, cnt = 1 << q;
+            if (t < cnt) {
+                const int i = delta * (2 * t + 1);
+                s_u[cp(i)] = fma(-rr[q], s_u[cp(i + delta)], fma(-rl[q], s_u[cp(i - delta)], rb[q]));
+            }
+            __syncwarp();
+        }
     }
+    Chunk<GENERAL> c;
+    double k0, r0, s0;
+    chunk_build_start<SPECIAL, GENERAL>(a, g0, s_ex, c, k0, r0, s0);
     __syncthreads();
-    MeshRows<SPECIAL, GENERAL, EXACT> rows{sm + SM_K, sm + SM_B, sm + SM_S, P, a.n, a.uL, a.uR};
-    const double ua = uh[t], ub = uh[t + 1];
-    // Thomas on the chunk interior, compile-time length FS - 1 (row-sum form, see thomas_step)
-    double cpv[FS], bpv[FS], xs[FS];
+    chunk_build_finish<GENERAL>(s_ex, c, k0, r0, s0);
+    double ua, ub;
     {
-        double lo, so, ro, bo, q = 1.0, cp = 0.0, bv = ua;      // "previous row" = the known head: x = ua
+        const double um2 = fma(-mR, s_u[cp(m2 + 2)], fma(-mL, s_u[cp(m2 - 2)], mB));      // level d = 2
+        const int z4 = 2 * od - m2;                                                         // the neighbour that is 0 mod 4
+        const double uz4 = s_u[cp(z4)];
+        const double ulo = (m2 < od) ? um2 : uz4, uhi = (m2 < od) ? uz4 : um2;
+        const double uod = fma(-oR, uhi, fma(-oL, ulo, oB));                                 // level d = 1
+        ua = (t & 1) ? uod : ulo;
+        ub = (t & 1) ? uhi : uod;
+    }
+    // Thomas on the chunk interior between the two known heads, division-free forward sweep in row-sum form:
+    // transformed row i is dN x_i + rN x_{i+1} = bN with sP = dN + rN formed as a sum of same-signed terms
+    // (row_i <- d_prev row_i - l_i row_prev); the reciprocals of the 7 pivots are independent of each other
+    double cq[FS], bq[FS], xs[FS];
+    {
+        double lo, so, ro, bo, dP = 1.0, sP = 1.0, bP = ua;     // "previous row" = the known head: x = ua
 #pragma unroll
         for (int i = 1; i < FS; ++i) {
-            rows.get(t * FS + i, lo, so, ro, bo);
+            chunk_row<SPECIAL, GENERAL, EXACT>(c, i, g0, a, lo, so, ro, bo);
             if (i == FS - 1) bo = fma(-ro, ub, bo);
-            thomas_step(lo, so, ro, bo, q, cp, bv);
-            cpv[i] = cp; bpv[i] = bv;
+            double sN = fma(dP, so, -lo * sP);
+            double rN = dP * ro;
+            double bN = fma(dP, bo, -lo * bP);
+            if (SPECIAL && lo == 0.0 && ro == 0.0) { sN = so; rN = 0.0; bN = bo; }   // identity row: value reproduced exactly
+            const double dN = sN - rN;
+            const double inv = fast_rcp(dN);
+            cq[i] = rN * inv; bq[i] = bN * inv;
+            dP = dN; sP = sN; bP = bN;
         }
-        xs[FS - 1] = bpv[FS - 1];
+        xs[FS - 1] = bq[FS - 1];
 #pragma unroll
-        for (int i = FS - 2; i >= 1; --i) xs[i] = bpv[i] - cpv[i] * xs[i + 1];
+        for (int i = FS - 2; i >= 1; --i) xs[i] = fma(-cq[i], xs[i + 1], bq[i]);
         xs[0] = ua;
     }
-    __syncthreads();               // everyone is done reading the element arrays
-    double* stage = sm + SM_K;     // reuse as padded output staging
+    double* p = u + g0;
+    if (!SPECIAL && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
-    for (int i = 0; i < FS; ++i) stage[padi(t * FS + i)] = xs[i];
-    __syncthreads();
-    for (int m = t; m < FTS; m += FT) {
-        const long long g = P + m;
-        if (g < a.n) u[g] = stage[padi(m)];
+        for (int i = 0; i < FS; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(xs[i], xs[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < FS; ++i)
+            if (g0 + i < a.n) p[i] = xs[i];
+    }
+    if (SPECIAL && !GENERAL && iface4 != nullptr) {
+        if (g0 == 0) {                                   // node 0: r_left = load_0 + k_0 (u_1 - u_0)
+            const double x0 = __ldg(a.nodes), x1 = __ldg(a.nodes + 1);
+            double k, Ls, Rs;
+            element_terms_fast<0>(a, x0, x1, 0.0, ForcingPoly<0>{}, k, Ls, Rs);
+            iface4[0] = x0;
+            iface4[2] = Ls + k * (xs[1] - xs[0]);
+        }
+        const long long gm = a.n - 2;                    // node n - 2 and the element right of it
+        if (gm >= g0 && gm < g0 + FS) {
+            const int i = (int)(gm - g0);
+            double um = xs[0], up = ub;
+#pragma unroll
+            for (int q = 0; q < FS; ++q) {
+                if (q == i) um = xs[q];
+                if (q == i + 1) up = xs[q];
+            }
+            const double x0 = __ldg(a.nodes + gm), x1 = __ldg(a.nodes + gm + 1);
+            double k, Ls, Rs;
+            element_terms_fast<0>(a, x0, x1, 0.0, ForcingPoly<0>{}, k, Ls, Rs);
+            iface4[1] = x1;
+            iface4[3] = Rs + k * (um - up);
+        }
     }
 }
 
 template <bool GENERAL, bool EXACT = false>
-__global__ void __launch_bounds__(FT, GENERAL ? 3 : 4) fem_backsub_kernel(const FemArgs a_in, const double* __restrict__ utop,
-                                                                          int ntile, const double* __restrict__ yvw,
-                                                                          double* __restrict__ u) {
-    extern __shared__ double sm[];
+__global__ void __launch_bounds__(FT, HFL_FEM_MINB) fem_backsub_kernel(const FemArgs a_in, const double* __restrict__ utop,
+                                                            int ntile, const double* __restrict__ heads,
+                                                            double* __restrict__ u, double* __restrict__ iface4) {
+    __shared__ double s_ex[EXW * FT], s_u[CRLEN];
     const FemArgs a = select_rhs(a_in);
-    utop += (size_t)blockIdx.y * a.ws_stride; yvw += (size_t)blockIdx.y * a.ws_stride; u += (size_t)blockIdx.y * a.n;
+    utop += (size_t)blockIdx.y * a.ws_stride; heads += (size_t)blockIdx.y * a.ws_stride; u += (size_t)blockIdx.y * a.n;
     const long long P = (long long)blockIdx.x * FTS;
-    load_tile_elements<GENERAL>(a, P, sm);   // recomputed: re-reading cached terms (16 B/node) measured slower than 2 sinpi
-    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true, GENERAL, EXACT>(a, utop, ntile, yvw, u, sm);
-    else fem_backsub_body<false, GENERAL, EXACT>(a, utop, ntile, yvw, u, sm);
+    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true, GENERAL, EXACT>(a, utop, ntile, heads, u, iface4, s_ex, s_u);
+    else fem_backsub_body<false, GENERAL, EXACT>(a, utop, ntile, heads, u, iface4, s_ex, s_u);
 }
 
 // End-node residuals for the multi-GPU interface system (see hfl.h).  flux2 = {q_0, B_{n-2}} from the flux scan
@@ -407,6 +741,7 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
     a.gx0 = 0.5 * (-0.5773502691896257) + 0.5;   // 0.5 * leggauss(2) + 0.5
     a.gx1 = 0.5 * (0.5773502691896257) + 0.5;
     a.exact_rowsum = (coarse_solver == HFL_COARSE_ASSEMBLED_EXACT) ? 1 : 0;
+    fem_taylor_table(a);
     if (coarse_solver == HFL_COARSE_FLUX_SCAN) {
         int rc = hfl_fem_flux_scan(a, R, d_u, d_ws, ws_bytes, s);
         if (rc != HFL_OK) return rc;
@@ -420,14 +755,13 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
         double* rec = reinterpret_cast<double*>(d_ws);
         double* utop = rec + (size_t)REC * nt;
         double* wsrows = utop + nt;
-        double* yvw = wsrows + 6 * (size_t)nt;
+        double* heads = wsrows + 6 * (size_t)nt;
         const int S = (int)((nt + TOPT - 1) / TOPT);
         const dim3 grid((unsigned)nt, (unsigned)R);
-        // top level: rows in shared memory while the CTA stays within the shared-memory carve-out the level-0 kernels
-        // already use (<= 96 KB, ~1000 tiles = 2e6 nodes).  Asking for more (220 KB would hold 1e7 nodes) costs more
-        // in the carve-out switch between kernels than the saved L2 round trips: measured +17 us at 1e7 nodes.
-        const size_t top_small = 8 * TOPT * sizeof(double), top_rows = top_small + 4 * (size_t)nt * sizeof(double);
-        const bool top_in_smem = top_rows <= 96 * 1024;
+        // top level: rows in shared memory while they fit (fem_top_smem_kb option, default 200 KB: 1.2e7 nodes), else in
+        // the workspace
+        const size_t top_small = (size_t)TOP_SMEM_DOUBLES * sizeof(double), top_rows = top_small + 4 * (size_t)nt * sizeof(double);
+        const bool top_in_smem = top_rows <= (size_t)get_option_top_smem_kb() * 1024;
         const size_t top_smem = top_in_smem ? top_rows : top_small;
         if (top_in_smem)
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_smem));
@@ -438,34 +772,23 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
             else fem_top_kernel<false><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
         };
         if (a.aq != nullptr) {
-            const size_t smem0 = (size_t)sm_total(true) * sizeof(double);
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            fem_reduce_kernel<true><<<grid, FT, smem0, s>>>(a, rec, yvw);
+            fem_reduce_kernel<true><<<grid, FT, 0, s>>>(a, rec, heads);
             launch_top();
-            fem_backsub_kernel<true><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+            fem_backsub_kernel<true><<<grid, FT, 0, s>>>(a, utop, (int)nt, heads, d_u, nullptr);
         } else if (a.exact_rowsum) {
-            const size_t smem0 = (size_t)sm_total(false) * sizeof(double);
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            fem_reduce_kernel<false, true><<<grid, FT, smem0, s>>>(a, rec, yvw);
+            fem_reduce_kernel<false, true><<<grid, FT, 0, s>>>(a, rec, heads);
             launch_top();
-            fem_backsub_kernel<false, true><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+            fem_backsub_kernel<false, true><<<grid, FT, 0, s>>>(a, utop, (int)nt, heads, d_u, d_iface4);
         } else {
-            const size_t smem0 = (size_t)sm_total(false) * sizeof(double);
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            fem_reduce_kernel<false><<<grid, FT, smem0, s>>>(a, rec, yvw);
+            fem_reduce_kernel<false><<<grid, FT, 0, s>>>(a, rec, heads);
             launch_top();
-            fem_backsub_kernel<false><<<grid, FT, smem0, s>>>(a, utop, (int)nt, yvw, d_u);
+            fem_backsub_kernel<false><<<grid, FT, 0, s>>>(a, utop, (int)nt, heads, d_u, d_iface4);
         }
         count_launch(3);
         HFL_CUDA_CHECK(cudaGetLastError());
     }
-    if (d_iface4 != nullptr) {
-        const double* flux2 = nullptr;
-        if (coarse_solver == HFL_COARSE_FLUX_SCAN)
-            flux2 = reinterpret_cast<const double*>(d_ws) + 6 * (size_t)((n - 1 + FTS - 1) / FTS);   // after the tile prefixes (hfl_flux.cu)
+    if (d_iface4 != nullptr && coarse_solver == HFL_COARSE_FLUX_SCAN) {   // the assembled solvers write it in pass 2
+        const double* flux2 = reinterpret_cast<const double*>(d_ws) + 6 * (size_t)((n - 1 + FTS - 1) / FTS);   // after the tile prefixes (hfl_flux.cu)
         fem_reaction_kernel<<<1, 32, 0, s>>>(a, d_u, flux2, d_iface4);
         count_launch();
         HFL_CUDA_CHECK(cudaGetLastError());

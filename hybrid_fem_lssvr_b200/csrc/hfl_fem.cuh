@@ -28,7 +28,18 @@ struct FemArgs {
     // r = blockIdx.y uses forcing frequency kfreqs[r], workspace slice r * ws_stride (doubles) and output row r * n
     const double* kfreqs; long long ws_stride;
     int exact_rowsum;   // HFL_COARSE_ASSEMBLED_EXACT: interior rows have row sum 0 (unrounded diagonal)
+    // Taylor coefficients of the forcing about a reference point: (k pi)^2 sin(k pi (x_ref + dx)) = sum_j ta[j] dx^j T_j,
+    // T_j = sin(k pi x_ref) for even j, cos(k pi x_ref) for odd j; ta[j] = (k pi)^(2 + j) * (+, +, -, -, ...) / j!
+    double ta[10];
 };
+
+__host__ __device__ inline void fem_taylor_table(FemArgs& a) {
+    double p = a.kp2, f = 1.0;
+    for (int j = 0; j < 10; ++j) {
+        if (j > 0) { p *= a.kpi; f *= (double)j; }
+        a.ta[j] = ((j & 2) ? -p : p) / f;
+    }
+}
 
 // The launch arguments specialised to this CTA's right-hand side (no-op for a single solve).
 __device__ __forceinline__ FemArgs select_rhs(FemArgs a) {
@@ -36,6 +47,7 @@ __device__ __forceinline__ FemArgs select_rhs(FemArgs a) {
         a.k = __ldg(a.kfreqs + blockIdx.y);
         a.kpi = __dmul_rn(a.k, 3.14159265358979323846);      // the same two roundings as the host does for one solve
         a.kp2 = __dmul_rn(a.kpi, a.kpi);
+        fem_taylor_table(a);
     }
     return a;
 }
