@@ -6,29 +6,30 @@
 // load are formed on the fly from the node array and the tridiagonal system is solved by a two-level
 // partition method:
 //
-//   level 0  tiles of FT * FS = 2048 nodes, one CTA each; thread t owns the chunk of FS = 8 consecutive nodes
-//            8 t .. 8 t + 7 (head + 7 interior) and keeps its rows in REGISTERS: it loads its nine nodes with
-//            vector loads, forms its eight elements itself (the element left of the head comes from the
-//            neighbouring thread through shared memory) and never stages a row in shared memory.
-//            pass 1 (fem_reduce_kernel): two interleaved sweeps eliminate the chunk interior (first / last
-//            entries of T^-1 b, T^-1 l e_1, T^-1 r e_s and of the "leak" 1 + v + w), the 255 chunk heads form a
-//            tridiagonal system reduced by CYCLIC REDUCTION in shared memory (7 levels, active rows compacted
-//            onto the first warps: 247 row updates per tile instead of the 255 x 8 of a parallel cyclic
-//            reduction with four right-hand sides); every head keeps its final row (L/d, R/d, B/d) for pass 2, and
-//            two threads walk the two root-to-leaf paths of the reduction tree to express the tile's first and last
-//            interior node through the two tile heads: the 12-number tile record.
-//   top      one CTA solves the system of tile heads (chunk per thread + parallel cyclic reduction).
-//            pass 2 (fem_backsub_kernel): tile heads known -> chunk heads by the back-substitution of the cyclic
-//            reduction (8 levels, one fused multiply-add pair per head) -> chunk interiors by Thomas in
-//            registers -> u with 16-byte stores.
+//   level 0  chunks of FS = 8 consecutive nodes (head + 7 interior), one per thread, FT = 256 threads per CTA; the
+//            thread loads its nine nodes with vector loads, forms its eight elements itself and keeps the rows in
+//            REGISTERS.  fem_chunk_reduce_kernel: two interleaved division-free sweeps eliminate the chunk interior
+//            (first / last entries of T^-1 b, T^-1 l e_1, T^-1 r e_s and of the "leak" 1 + v + w) and give the reduced
+//            row of every chunk head among the heads.  fem_chunk_backsub_kernel: heads known -> chunk interiors by
+//            Thomas in registers -> u with 16-byte stores.  Both are streaming kernels without a serial phase.
+//   level 1  the same once more on the heads (every 8th node): chunks of 8 heads per thread, rows from the workspace,
+//            2048 heads = 16384 nodes per CTA (a tile).  fem_heads_reduce_kernel: chunk sweeps, then the 255 super heads
+//            of the tile are reduced by CYCLIC REDUCTION in shared memory (7 levels, active rows compacted onto the first
+//            warps, single-warp levels without CTA barriers: 247 row updates per tile), every super head keeps its final
+//            row (L/d, R/d, B/d), and two threads walk the two root-to-leaf paths of the reduction tree to express the
+//            tile's first and last interior head through the two tile heads: the 12-number tile record.
+//            fem_heads_backsub_kernel: tile heads known -> super heads by the back-substitution tree -> heads by Thomas.
+//   top      fem_top_kernel, one CTA: the tile heads (every 16384th node; 611 at 1e7 nodes), chunk per thread + cyclic
+//            reduction.
 //
 // The load uses sin(k pi x_q) = S cos(theta) + C sin(theta), (S, C) = sincospi of the chunk's head node and
 // theta = k pi (x_q - x_head) by a short Taylor polynomial when the chunk spans less than 1/16 rad (any mesh of
 // more than ~800 k nodes), the library sinpi otherwise: ~12 FP64 instructions per Gauss point instead of ~45.
 // Every elimination runs in row-sum form (l, sigma, r), d = sigma - l - r (hfl_fem.cuh): no cancellation,
 // ~1e-14 from the exact solution of the rounded system where LU-type solvers lose cond * eps.
-// Node traffic: the node array is read twice and u written once (24 B/node) plus 3 B/node of head rows; the
-// element terms are recomputed in the second pass instead of stored (16 B/node each way would cost more).
+// Node traffic: the node array is read twice and u written once (24 B/node) plus ~10 B/node of head rows and head values
+// (mostly L2 hits); the element terms are recomputed in the second pass instead of stored (16 B/node each way would
+// cost more).
 #include <type_traits>
 #include "hfl_fem.cuh"
 
@@ -39,10 +40,10 @@ namespace hfl {
 
 // Taylor polynomial of the forcing about the chunk's head node: (k pi)^2 sin(k pi (x_ref + dx)) = sum_j tc[j] dx^j,
 // tc[j] = ta[j] * (sin | cos)(k pi x_ref).  TIER 1: degree 9, |k pi dx| <= 2^-4 (truncation < 3e-19 of the amplitude);
-// TIER 2: degree 4, |k pi dx| <= 2^-10 (truncation < 1e-17).
+// TIER 2: degree 4, |k pi dx| <= 2^-10 (truncation < 1e-17); TIER 3: degree 2, |k pi dx| <= 2^-17.5 (truncation < 4e-17).
 template <int TIER>
 struct ForcingPoly {
-    static constexpr int DEG = (TIER == 2) ? 4 : 9;
+    static constexpr int DEG = (TIER == 3) ? 2 : ((TIER == 2) ? 4 : 9);
     double tc[DEG + 1];
     __device__ __forceinline__ void init(const FemArgs& a, double S, double C) {
 #pragma unroll
@@ -97,12 +98,12 @@ struct Chunk {
     double s[GENERAL ? FS : 1];   // general operator: mass-matrix row sum of node g0 + i
 };
 
-constexpr int EXW = 3;            // doubles per thread in the element exchange: k, Rs, sR of the thread's last element
+
 
 // First half: loads the chunk's nodes, forms elements j = 1 .. FS (left of nodes g0 + 1 .. g0 + FS), publishes the last
 // one for the next thread; thread 0 forms the element left of its head itself.  Call __syncthreads(), then
 // chunk_build_finish.  SPECIAL = the tile holds a Dirichlet node or padding past the mesh.
-template <bool SPECIAL, bool GENERAL>
+template <bool SPECIAL, bool GENERAL, bool EXCH = true>
 __device__ __forceinline__ void chunk_build_start(const FemArgs& a, long long g0, double* __restrict__ ex, Chunk<GENERAL>& c,
                                                   double& k0, double& r0, double& s0) {
     const int t = threadIdx.x;
@@ -128,7 +129,7 @@ __device__ __forceinline__ void chunk_build_start(const FemArgs& a, long long g0
     double S = 0.0, C = 0.0;
     if (!SPECIAL && !GENERAL) {
         const double span = fabs(a.kpi * (x[FS] - x[0]));
-        tier = (span <= 0.0009765625) ? 2 : ((span <= 0.0625) ? 1 : 0);
+        tier = (span <= 5.3e-6) ? 3 : ((span <= 0.0009765625) ? 2 : ((span <= 0.0625) ? 1 : 0));
 #ifdef HFL_FEM_NO_TAYLOR
         tier = 0;
 #endif
@@ -151,7 +152,8 @@ __device__ __forceinline__ void chunk_build_start(const FemArgs& a, long long g0
             if (GENERAL) { sL[j] = sl; sR[j] = sr; }
         }
     };
-    if (tier == 2) elements(std::integral_constant<int, 2>{});
+    if (tier == 3) elements(std::integral_constant<int, 3>{});
+    else if (tier == 2) elements(std::integral_constant<int, 2>{});
     else if (tier == 1) elements(std::integral_constant<int, 1>{});
     else elements(std::integral_constant<int, 0>{});
 #pragma unroll
@@ -159,10 +161,11 @@ __device__ __forceinline__ void chunk_build_start(const FemArgs& a, long long g0
         c.b[i] = Ls[i + 1] + ((i >= 1) ? Rs[i] : 0.0);
         if (GENERAL) c.s[i] = sL[i + 1] + ((i >= 1) ? sR[i] : 0.0);
     }
+    k0 = 0.0; r0 = 0.0; s0 = 0.0;
+    if (!EXCH) return;        // the caller only needs rows 1 .. FS-1
     ex[0 * FT + t] = c.k[FS];
     ex[1 * FT + t] = Rs[FS];
     if (GENERAL) ex[2 * FT + t] = sR[FS];
-    k0 = 0.0; r0 = 0.0; s0 = 0.0;
     if (t == 0 && g0 >= 1 && g0 <= a.n - 1) {      // element left of the tile head: nobody in this CTA owns it
         const double xm = __ldg(a.nodes + g0 - 1);
         double l, sl = 0.0;
@@ -214,17 +217,18 @@ __device__ __forceinline__ void chunk_row(const Chunk<GENERAL>& c, int i, long l
 // which showed up as 1e-11 instead of 1e-14.
 __device__ __forceinline__ double diag_of(double sg, double p, double q) { return __dsub_rn(sg, __dadd_rn(p, q)); }
 
-// Interior of the chunk (rows 1 .. FS-1): first / last entries of the three partial solutions
-// x = y - u_head v - u_next w and the "leaks" e = 1 + v + w, all formed without cancellation; the forward and the
-// backward sweep are independent chains and run interleaved.  out = {y1, v1, w1, e1, ys, vs, ws, es}.
-template <bool SPECIAL, bool GENERAL, bool EXACT>
-__device__ __forceinline__ void chunk_reduce_reg(const Chunk<GENERAL>& c, long long g0, const FemArgs& a, double (&out)[8]) {
+// Interior of a chunk of FS rows (rows 1 .. FS-1; row(i, l, sg, r, b) with compile-time i after unrolling): first / last
+// entries of the three partial solutions x = y - u_head v - u_next w and the "leaks" e = 1 + v + w, all formed without
+// cancellation; the forward and the backward sweep are independent chains and run interleaved.
+// out = {y1, v1, w1, e1, ys, vs, ws, es}.
+template <class RowFn>
+__device__ __forceinline__ void chunk_sweeps(RowFn&& row, double (&out)[8]) {
     double l, sg, r, b;
     // forward: transformed row i has entries (head: v, i: d, i+1: r); tp = v + d + r is its row sum
-    chunk_row<SPECIAL, GENERAL, EXACT>(c, 1, g0, a, l, sg, r, b);
+    row(1, l, sg, r, b);
     double tpf = sg, vpf = l, rpf = r, bpf = b, dpf = diag_of(tpf, vpf, rpf);
     // backward: entries (i-1: l, i: d, next head: w)
-    chunk_row<SPECIAL, GENERAL, EXACT>(c, FS - 1, g0, a, l, sg, r, b);
+    row(FS - 1, l, sg, r, b);
     double tpb = sg, bpb = b, wpb = r, lpb = l, dpb = diag_of(tpb, wpb, lpb);
     // division-free elimination: row_i <- d_prev row_i - l_i row_prev (every product keeps its sign, so the row sums stay
     // sums of same-signed terms); the rows grow by ~d per step, 7 steps stay far inside the double range, and the only
@@ -232,13 +236,13 @@ __device__ __forceinline__ void chunk_reduce_reg(const Chunk<GENERAL>& c, long l
     // and rounding by rounding (no compiler contraction): see diag_of.
 #pragma unroll
     for (int s = 2; s < FS; ++s) {
-        chunk_row<SPECIAL, GENERAL, EXACT>(c, s, g0, a, l, sg, r, b);
+        row(s, l, sg, r, b);
         tpf = __fma_rn(dpf, sg, __dmul_rn(-l, tpf));
         vpf = __dmul_rn(-l, vpf);
         bpf = fma(dpf, b, -l * bpf);
         rpf = __dmul_rn(dpf, r);
         dpf = diag_of(tpf, vpf, rpf);
-        chunk_row<SPECIAL, GENERAL, EXACT>(c, FS - s, g0, a, l, sg, r, b);
+        row(FS - s, l, sg, r, b);
         tpb = __fma_rn(dpb, sg, __dmul_rn(-r, tpb));
         wpb = __dmul_rn(-r, wpb);
         bpb = fma(dpb, b, -r * bpb);
@@ -248,6 +252,33 @@ __device__ __forceinline__ void chunk_reduce_reg(const Chunk<GENERAL>& c, long l
     const double invf = fast_rcp(dpf), invb = fast_rcp(dpb);
     out[4] = bpf * invf; out[5] = __dmul_rn(vpf, invf); out[6] = __dmul_rn(rpf, invf); out[7] = __dmul_rn(tpf, invf);
     out[0] = bpb * invb; out[1] = __dmul_rn(lpb, invb); out[2] = __dmul_rn(wpb, invb); out[3] = __dmul_rn(tpb, invb);
+}
+
+// Thomas on a chunk interior (rows 1 .. FS-1) between the two known heads ua (row 0) and ub (the next chunk's head),
+// division-free forward sweep in row-sum form: transformed row i is dN x_i + rN x_{i+1} = bN with sP = dN + rN formed as
+// a sum of same-signed terms (row_i <- d_prev row_i - l_i row_prev); the reciprocals of the 7 pivots are independent of
+// each other.  IDENT: identity rows (Dirichlet nodes, padding) reproduce their value bit for bit.
+template <bool IDENT, class RowFn>
+__device__ __forceinline__ void chunk_thomas(RowFn&& row, double ua, double ub, double (&xs)[FS]) {
+    double cq[FS], bq[FS];
+    double lo, so, ro, bo, dP = 1.0, sP = 1.0, bP = ua;     // "previous row" = the known head: x = ua
+#pragma unroll
+    for (int i = 1; i < FS; ++i) {
+        row(i, lo, so, ro, bo);
+        if (i == FS - 1) bo = fma(-ro, ub, bo);
+        double sN = fma(dP, so, -lo * sP);
+        double rN = dP * ro;
+        double bN = fma(dP, bo, -lo * bP);
+        if (IDENT && lo == 0.0 && ro == 0.0) { sN = so; rN = 0.0; bN = bo; }
+        const double dN = sN - rN;
+        const double inv = fast_rcp(dN);
+        cq[i] = rN * inv; bq[i] = bN * inv;
+        dP = dN; sP = sN; bP = bN;
+    }
+    xs[FS - 1] = bq[FS - 1];
+#pragma unroll
+    for (int i = FS - 2; i >= 1; --i) xs[i] = fma(-cq[i], xs[i + 1], bq[i]);
+    xs[0] = ua;
 }
 
 // Chunk interior of the top level: rows through a getter with run-time indices (the rows live in shared or global
@@ -339,23 +370,118 @@ __device__ __forceinline__ void cr_forward(double* sL, double* sS, double* sR, d
 }
 
 
-// Level 0, pass 1.  Tile record (SoA, rec[f * ntile + tile]): f = 0..3 {l, sigma, r, b} of the tile head's row,
-// 4..7 {y, v, w, e} of the tile's first interior node, 8..11 of its last one (x = y - v u_P - w u_Q, e = 1 + v + w).
-// heads[tile][3][FT]: final cyclic-reduction row {L/d, R/d, B/d} of every chunk head.
+// ---------------------------------------------------------------------------------------------------------
+// Three levels.  Level 0: chunks of FS = 8 nodes, one per thread (FT = 256 threads = 2048 nodes per CTA), rows formed
+// from the node array and kept in registers.  Level 1: the chunk heads (every 8th node) form a tridiagonal system of
+// their own; chunks of 8 heads, one per thread, FT threads = 2048 heads = 16384 nodes per CTA (a "tile"), rows read
+// from the workspace; the 256 "super heads" of a tile are reduced by cyclic reduction in shared memory.  Top: the
+// tile heads (every 16384th node), one CTA.  The two level-0 kernels are streaming kernels without a serial phase; the
+// reduction trees, which are latency-bound, run in the two light level-1 kernels (1/8 of the unknowns, 4 doubles each).
+//
+// Workspace per right-hand side (doubles): rec [12][ntile] | utop [ntile] | top rows [6 ntile] | sheads [ntile][3][FT] |
+// hrow [4][NH] | edge [8 nchunkcta] | uh [NH + 8], NH = FT * nchunkcta heads.
+
+// Level 0, pass 1: head equations.  hrow[f * NH + h], f = 0..3: reduced row {L, sigma, R, B} of head h among the heads
+// (h - 1, h, h + 1).  The head of a CTA's first chunk needs the previous CTA's last chunk, so its row is finished by the
+// level-1 kernel from edge[cta][0..4] = {l, sigma, -r e1, -r w1, b - r y1} of that head and edge[cta - 1][5..7] =
+// {ys, vs, es} of the chunk before it.
 template <bool SPECIAL, bool GENERAL, bool EXACT>
-__device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __restrict__ rec, double* __restrict__ heads,
-                                                double* s_ex, double* s_ex2, double* s_cr) {
+__device__ __forceinline__ void fem_chunk_reduce_body(const FemArgs& a, double* __restrict__ hrow, double* __restrict__ edge,
+                                                      double* s_ex) {
     const int t = threadIdx.x;
     const long long g0 = (long long)blockIdx.x * FTS + (long long)t * FS;
+    const long long NH = (long long)gridDim.x * FT, h = (long long)blockIdx.x * FT + t;
     Chunk<GENERAL> c;
     double k0, r0, s0;
     chunk_build_start<SPECIAL, GENERAL>(a, g0, s_ex, c, k0, r0, s0);
+    double e8[8];
+    chunk_sweeps([&](int i, double& l, double& sg, double& r, double& b) { chunk_row<SPECIAL, GENERAL, EXACT>(c, i, g0, a, l, sg, r, b); },
+                 e8);      // rows 1 .. FS-1 do not involve the element left of the head
+    s_ex[3 * FT + t] = e8[4]; s_ex[4 * FT + t] = e8[5]; s_ex[5 * FT + t] = e8[7];     // ys, vs, es of this chunk
     __syncthreads();
     chunk_build_finish<GENERAL>(s_ex, c, k0, r0, s0);
-    double e8[8];
-    chunk_reduce_reg<SPECIAL, GENERAL, EXACT>(c, g0, a, e8);
     double lp, sp, rp, bp;
     chunk_row<SPECIAL, GENERAL, EXACT>(c, 0, g0, a, lp, sp, rp, bp);
+    if (t >= 1) {
+        double L, S, R, B;
+        head_equation(lp, sp, rp, bp, s_ex[3 * FT + t - 1], s_ex[4 * FT + t - 1], s_ex[5 * FT + t - 1], e8, L, S, R, B);
+        hrow[h] = L; hrow[NH + h] = S; hrow[2 * NH + h] = R; hrow[3 * NH + h] = B;
+    } else {
+        double* eo = edge + (size_t)blockIdx.x * 8;
+        eo[0] = lp; eo[1] = sp; eo[2] = __dmul_rn(-rp, e8[3]); eo[3] = __dmul_rn(-rp, e8[2]); eo[4] = fma(-rp, e8[0], bp);
+        hrow[h] = 0.0; hrow[NH + h] = 1.0; hrow[2 * NH + h] = 0.0; hrow[3 * NH + h] = 0.0;      // finished at level 1
+    }
+    if (t == FT - 1) {
+        double* eo = edge + (size_t)blockIdx.x * 8;
+        eo[5] = e8[4]; eo[6] = e8[5]; eo[7] = e8[7];
+    }
+}
+
+#ifndef HFL_FEM_MINB
+#define HFL_FEM_MINB 3
+#endif
+template <bool GENERAL, bool EXACT = false>
+__global__ void __launch_bounds__(FT, HFL_FEM_MINB) fem_chunk_reduce_kernel(const FemArgs a_in, double* __restrict__ hrow,
+                                                                            double* __restrict__ edge) {
+    __shared__ double s_ex[6 * FT];
+    const FemArgs a = select_rhs(a_in);
+    hrow += (size_t)blockIdx.y * a.ws_stride; edge += (size_t)blockIdx.y * a.ws_stride;
+    const long long P = (long long)blockIdx.x * FTS;
+    if (P == 0 || P + FTS >= a.n - 1) fem_chunk_reduce_body<true, GENERAL, EXACT>(a, hrow, edge, s_ex);
+    else fem_chunk_reduce_body<false, GENERAL, EXACT>(a, hrow, edge, s_ex);
+}
+
+// The 8 head rows of a level-1 chunk (heads H0 .. H0 + 7), heads past NH padded with identity rows.
+struct HeadRows {
+    double l[FS], s[FS], r[FS], b[FS];
+    __device__ __forceinline__ void load(const double* __restrict__ hrow, long long NH, long long H0) {
+        if (H0 + FS <= NH) {
+#pragma unroll
+            for (int i = 0; i < FS; i += 2) {
+                const double2 vl = *reinterpret_cast<const double2*>(hrow + H0 + i);
+                const double2 vs = *reinterpret_cast<const double2*>(hrow + NH + H0 + i);
+                const double2 vr = *reinterpret_cast<const double2*>(hrow + 2 * NH + H0 + i);
+                const double2 vb = *reinterpret_cast<const double2*>(hrow + 3 * NH + H0 + i);
+                l[i] = vl.x; l[i + 1] = vl.y; s[i] = vs.x; s[i + 1] = vs.y;
+                r[i] = vr.x; r[i + 1] = vr.y; b[i] = vb.x; b[i + 1] = vb.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < FS; ++i) { l[i] = 0.0; s[i] = 1.0; r[i] = 0.0; b[i] = 0.0; }
+        }
+    }
+    __device__ __forceinline__ void get(int i, double& lo, double& so, double& ro, double& bo) const {
+        lo = l[i]; so = s[i]; ro = r[i]; bo = b[i];
+    }
+};
+
+// Level 1, pass 1.  Tile record (SoA, rec[f * ntile + tile]): f = 0..3 {l, sigma, r, b} of the tile head's row,
+// 4..7 {y, v, w, e} of the tile's first interior head, 8..11 of its last one (x = y - v u_P - w u_Q, e = 1 + v + w).
+// sheads[tile][3][FT]: final cyclic-reduction row {L/d, R/d, B/d} of every super head.
+__global__ void __launch_bounds__(FT, 3) fem_heads_reduce_kernel(const double* __restrict__ hrow, const double* __restrict__ edge,
+                                                              long long NH, double* __restrict__ rec,
+                                                              double* __restrict__ sheads, long long ws_stride) {
+    __shared__ double s_ex2[3 * FT], s_cr[4 * CRLEN];
+    hrow += (size_t)blockIdx.y * ws_stride; edge += (size_t)blockIdx.y * ws_stride;
+    rec += (size_t)blockIdx.y * ws_stride; sheads += (size_t)blockIdx.y * ws_stride;
+    const int t = threadIdx.x;
+    const long long H0 = (long long)blockIdx.x * FTS + (long long)t * FS;
+    HeadRows hr;
+    hr.load(hrow, NH, H0);
+    if ((t & (FT / FS - 1)) == 0 && H0 < NH) {            // first head of a level-0 CTA: finish its row from the edge records
+        const long long cta = H0 / FT;
+        const double* eo = edge + (size_t)cta * 8;
+        const double lp = eo[0], sp = eo[1];
+        double ysp = 0.0, vsp = 0.0, esp = 0.0;
+        if (cta > 0) { ysp = eo[5 - 8]; vsp = eo[6 - 8]; esp = eo[7 - 8]; }
+        hr.l[0] = __dmul_rn(-lp, vsp);
+        hr.r[0] = eo[3];
+        hr.s[0] = __dadd_rn(sp, __dadd_rn(__dmul_rn(-lp, esp), eo[2]));          // the sum head_equation forms
+        hr.b[0] = fma(-lp, ysp, eo[4]);
+    }
+    double e8[8];
+    chunk_sweeps([&](int i, double& l, double& sg, double& r, double& b) { hr.get(i, l, sg, r, b); }, e8);
+    const double lp = hr.l[0], sp = hr.s[0], rp = hr.r[0], bp = hr.b[0];
     s_ex2[0 * FT + t] = e8[4]; s_ex2[1 * FT + t] = e8[5]; s_ex2[2 * FT + t] = e8[7];     // ys, vs, es of this chunk
     __syncthreads();
     double* sL = s_cr; double* sS = s_cr + CRLEN; double* sR = s_cr + 2 * CRLEN; double* sB = s_cr + 3 * CRLEN;
@@ -365,30 +491,30 @@ __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __rest
         sL[cp(t)] = L; sS[cp(t)] = S; sR[cp(t)] = R; sB[cp(t)] = B;
     }
     __syncthreads();
-    // cyclic reduction over heads 1 .. FT-1; heads 0 (this tile's) and FT (the next tile's) stay as unknown columns
+    // cyclic reduction over super heads 1 .. FT-1; heads 0 (this tile's) and FT (the next tile's) stay as unknown columns
     cr_forward<FT>(sL, sS, sR, sB, t);
-    if (t >= 1) {        // every head's row is final: scale by its diagonal, keep it for the back-substitution pass
+    if (t >= 1) {        // every row is final: scale by its diagonal, keep it for the back-substitution pass
         const int ii = cp(t);
         const double L = sL[ii], S = sS[ii], R = sR[ii], B = sB[ii];
         const double inv = fast_rcp(diag_of(S, L, R));
         const double Ld = __dmul_rn(L, inv), Rd = __dmul_rn(R, inv), Bd = B * inv;
         sL[ii] = Ld; sR[ii] = Rd; sB[ii] = Bd; sS[ii] = __dmul_rn(S, inv);
-        double* o = heads + (size_t)blockIdx.x * 3 * FT;
+        double* o = sheads + (size_t)blockIdx.x * 3 * FT;
         o[t] = Ld; o[FT + t] = Rd; o[2 * FT + t] = Bd;
     } else {             // slot 0 is the tile head itself (solved at the top level)
-        double* o = heads + (size_t)blockIdx.x * 3 * FT;
+        double* o = sheads + (size_t)blockIdx.x * 3 * FT;
         o[0] = 0.0; o[FT] = 0.0; o[2 * FT] = 0.0;
     }
     __syncthreads();
     const long long nt = gridDim.x;
     double* out = rec + blockIdx.x;
     if (t == 0 || t == FT - 1) {
-        // head FT/2 through the two tile heads, then down the tree to head 1 (t = 0) or head FT-1 (t = FT-1):
+        // super head FT/2 through the two tile heads, then down the tree to super head 1 (t = 0) or FT-1 (t = FT-1):
         // u = Y - V u_P - W u_Q, E = 1 + V + W
         int i = cp(FT / 2);
         double Y = sB[i], V = sL[i], W = sR[i], E = sS[i];
         if (t == 0) {
-#pragma unroll 1
+#pragma unroll
             for (int delta = FT / 4; delta >= 1; delta >>= 1) {        // node delta: left neighbour 0, right neighbour 2 delta
                 i = cp(delta);
                 const double Rd = sR[i];
@@ -400,7 +526,7 @@ __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __rest
             out[6 * nt] = __dmul_rn(-e8[2], W);
             out[7 * nt] = __fma_rn(-e8[2], E, e8[3]);
         } else {
-#pragma unroll 1
+#pragma unroll
             for (int delta = FT / 4; delta >= 1; delta >>= 1) {        // node FT - delta: left neighbour FT - 2 delta, right FT
                 i = cp(FT - delta);
                 const double Ld = sL[i];
@@ -412,20 +538,6 @@ __device__ __forceinline__ void fem_reduce_body(const FemArgs& a, double* __rest
             out[11 * nt] = __fma_rn(-e8[5], E, e8[7]);
         }
     }
-}
-
-template <bool GENERAL, bool EXACT = false>
-#ifndef HFL_FEM_MINB
-#define HFL_FEM_MINB 3
-#endif
-__global__ void __launch_bounds__(FT, HFL_FEM_MINB) fem_reduce_kernel(const FemArgs a_in, double* __restrict__ rec,
-                                                           double* __restrict__ heads) {
-    __shared__ double s_ex[EXW * FT], s_ex2[3 * FT], s_cr[4 * CRLEN];
-    const FemArgs a = select_rhs(a_in);
-    rec += (size_t)blockIdx.y * a.ws_stride; heads += (size_t)blockIdx.y * a.ws_stride;
-    const long long P = (long long)blockIdx.x * FTS;
-    if (P == 0 || P + FTS >= a.n - 1) fem_reduce_body<true, GENERAL, EXACT>(a, rec, heads, s_ex, s_ex2, s_cr);
-    else fem_reduce_body<false, GENERAL, EXACT>(a, rec, heads, s_ex, s_ex2, s_cr);
 }
 
 // Thomas elimination of a chunk interior between two known head values, in (l, sigma, r) form: s = row sum over
@@ -550,23 +662,26 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
     }
 }
 
-// Level 0, pass 2: tile head values known -> chunk heads by the back-substitution of the cyclic reduction ->
-// chunk interiors by Thomas in registers -> u.  iface4 (optional): the end-node residuals of the multi-GPU
-// interface system (hfl.h), written by the two threads that own nodes 0 and n - 2.
-template <bool SPECIAL, bool GENERAL, bool EXACT>
-__device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double* __restrict__ utop, int ntile,
-                                                 const double* __restrict__ heads, double* __restrict__ u,
-                                                 double* __restrict__ iface4, double* s_ex, double* s_u) {
+// Level 1, pass 2: tile head values known -> super heads by the back-substitution of the cyclic reduction,
+// u_i = B_i - L_i u_{i-d} - R_i u_{i+d} with d = lowbit(i): levels d >= 4 (the 63 super heads at multiples of 4) on warp
+// 0, then every thread evaluates the two rows (d = 2, d = 1) its own u_t, u_{t+1} need -> the 7 interior heads of every
+// level-1 chunk by Thomas in registers -> uh[h] for every head h.
+__global__ void __launch_bounds__(FT) fem_heads_backsub_kernel(const double* __restrict__ hrow, long long NH,
+                                                               const double* __restrict__ utop, int ntile,
+                                                               const double* __restrict__ sheads, double* __restrict__ uh,
+                                                               long long ws_stride) {
+    __shared__ double s_u[CRLEN];
+    hrow += (size_t)blockIdx.y * ws_stride; utop += (size_t)blockIdx.y * ws_stride;
+    sheads += (size_t)blockIdx.y * ws_stride; uh += (size_t)blockIdx.y * ws_stride;
     const int t = threadIdx.x;
-    const long long g0 = (long long)blockIdx.x * FTS + (long long)t * FS;
-    const double* o = heads + (size_t)blockIdx.x * 3 * FT;
-    // chunk heads from the two tile heads: back-substitution of the cyclic reduction, u_i = B_i - L_i u_{i-d} - R_i u_{i+d}
-    // with d = lowbit(i).  Levels d >= 4 (the 63 heads at multiples of 4) run on warp 0 while the other warps form their
-    // elements; after the one CTA barrier every thread evaluates the two rows (d = 2, d = 1) its own u_t, u_{t+1} need.
+    const long long H0 = (long long)blockIdx.x * FTS + (long long)t * FS;
+    const double* o = sheads + (size_t)blockIdx.x * 3 * FT;
     const int od = t | 1;                                  // the odd one of {t, t + 1}
-    const int m2 = (od & 2) ? (od - 1) : (od + 1);      // its neighbour that is 2 mod 4 (the other one is 0 mod 4)
+    const int m2 = (od & 2) ? (od - 1) : (od + 1);         // its neighbour that is 2 mod 4 (the other one is 0 mod 4)
     const double oL = o[od], oR = o[FT + od], oB = o[2 * FT + od];
     const double mL = o[m2], mR = o[FT + m2], mB = o[2 * FT + m2];
+    HeadRows hr;
+    hr.load(hrow, NH, H0);                                 // rows 1 .. 7 are never the first head of a level-0 CTA
     if (t < 32) {
         constexpr int NLV = 6;                             // d = FT/2 .. 4
         static_assert(FT == 256, "level count of the warp-0 tree");
@@ -592,11 +707,7 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
             __syncwarp();
         }
     }
-    Chunk<GENERAL> c;
-    double k0, r0, s0;
-    chunk_build_start<SPECIAL, GENERAL>(a, g0, s_ex, c, k0, r0, s0);
     __syncthreads();
-    chunk_build_finish<GENERAL>(s_ex, c, k0, r0, s0);
     double ua, ub;
     {
         const double um2 = fma(-mR, s_u[cp(m2 + 2)], fma(-mL, s_u[cp(m2 - 2)], mB));      // level d = 2
@@ -607,30 +718,30 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
         ua = (t & 1) ? uod : ulo;
         ub = (t & 1) ? uhi : uod;
     }
-    // Thomas on the chunk interior between the two known heads, division-free forward sweep in row-sum form:
-    // transformed row i is dN x_i + rN x_{i+1} = bN with sP = dN + rN formed as a sum of same-signed terms
-    // (row_i <- d_prev row_i - l_i row_prev); the reciprocals of the 7 pivots are independent of each other
-    double cq[FS], bq[FS], xs[FS];
-    {
-        double lo, so, ro, bo, dP = 1.0, sP = 1.0, bP = ua;     // "previous row" = the known head: x = ua
+    double xs[FS];
+    chunk_thomas<true>([&](int i, double& l, double& sg, double& r, double& b) { hr.get(i, l, sg, r, b); }, ua, ub, xs);
+    if (H0 + FS <= NH) {
 #pragma unroll
-        for (int i = 1; i < FS; ++i) {
-            chunk_row<SPECIAL, GENERAL, EXACT>(c, i, g0, a, lo, so, ro, bo);
-            if (i == FS - 1) bo = fma(-ro, ub, bo);
-            double sN = fma(dP, so, -lo * sP);
-            double rN = dP * ro;
-            double bN = fma(dP, bo, -lo * bP);
-            if (SPECIAL && lo == 0.0 && ro == 0.0) { sN = so; rN = 0.0; bN = bo; }   // identity row: value reproduced exactly
-            const double dN = sN - rN;
-            const double inv = fast_rcp(dN);
-            cq[i] = rN * inv; bq[i] = bN * inv;
-            dP = dN; sP = sN; bP = bN;
-        }
-        xs[FS - 1] = bq[FS - 1];
-#pragma unroll
-        for (int i = FS - 2; i >= 1; --i) xs[i] = fma(-cq[i], xs[i + 1], bq[i]);
-        xs[0] = ua;
+        for (int i = 0; i < FS; i += 2) *reinterpret_cast<double2*>(uh + H0 + i) = make_double2(xs[i], xs[i + 1]);
     }
+}
+
+// Level 0, pass 2: head values known -> chunk interiors by Thomas in registers -> u with 16-byte stores.  No shared
+// memory, no barrier.  iface4 (optional): the end-node residuals of the multi-GPU interface system (hfl.h), written by the
+// two threads that own nodes 0 and n - 2.
+template <bool SPECIAL, bool GENERAL, bool EXACT>
+__device__ __forceinline__ void fem_chunk_backsub_body(const FemArgs& a, const double* __restrict__ uh, double* __restrict__ u,
+                                                       double* __restrict__ iface4) {
+    const int t = threadIdx.x;
+    const long long g0 = (long long)blockIdx.x * FTS + (long long)t * FS;
+    const long long NH = (long long)gridDim.x * FT, h = (long long)blockIdx.x * FT + t;
+    const double ua = uh[h], ub = (h + 1 < NH) ? uh[h + 1] : 0.0;
+    Chunk<GENERAL> c;
+    double k0, r0, s0;
+    chunk_build_start<SPECIAL, GENERAL, false>(a, g0, nullptr, c, k0, r0, s0);      // rows 1 .. FS-1 only: no exchange
+    double xs[FS];
+    chunk_thomas<SPECIAL>([&](int i, double& l, double& sg, double& r, double& b) { chunk_row<SPECIAL, GENERAL, EXACT>(c, i, g0, a, l, sg, r, b); },
+                          ua, ub, xs);
     double* p = u + g0;
     if (!SPECIAL && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
@@ -667,15 +778,13 @@ __device__ __forceinline__ void fem_backsub_body(const FemArgs& a, const double*
 }
 
 template <bool GENERAL, bool EXACT = false>
-__global__ void __launch_bounds__(FT, HFL_FEM_MINB) fem_backsub_kernel(const FemArgs a_in, const double* __restrict__ utop,
-                                                            int ntile, const double* __restrict__ heads,
-                                                            double* __restrict__ u, double* __restrict__ iface4) {
-    __shared__ double s_ex[EXW * FT], s_u[CRLEN];
+__global__ void __launch_bounds__(FT, HFL_FEM_MINB) fem_chunk_backsub_kernel(const FemArgs a_in, const double* __restrict__ uh,
+                                                                             double* __restrict__ u, double* __restrict__ iface4) {
     const FemArgs a = select_rhs(a_in);
-    utop += (size_t)blockIdx.y * a.ws_stride; heads += (size_t)blockIdx.y * a.ws_stride; u += (size_t)blockIdx.y * a.n;
+    uh += (size_t)blockIdx.y * a.ws_stride; u += (size_t)blockIdx.y * a.n;
     const long long P = (long long)blockIdx.x * FTS;
-    if (P == 0 || P + FTS >= a.n - 1) fem_backsub_body<true, GENERAL, EXACT>(a, utop, ntile, heads, u, iface4, s_ex, s_u);
-    else fem_backsub_body<false, GENERAL, EXACT>(a, utop, ntile, heads, u, iface4, s_ex, s_u);
+    if (P == 0 || P + FTS >= a.n - 1) fem_chunk_backsub_body<true, GENERAL, EXACT>(a, uh, u, iface4);
+    else fem_chunk_backsub_body<false, GENERAL, EXACT>(a, uh, u, iface4);
 }
 
 // End-node residuals for the multi-GPU interface system (see hfl.h).  flux2 = {q_0, B_{n-2}} from the flux scan
@@ -715,13 +824,20 @@ __global__ void spike_iface_kernel(int G, const double* __restrict__ g, double u
 
 using namespace hfl;
 
-static inline long long fem_ntile(long long n) { return (n + FTS - 1) / FTS; }
-static size_t fem_ws_doubles(long long nt) { return (size_t)(REC + 1 + 6 + 3 * FT) * (size_t)nt; }
+static inline long long fem_nchunkcta(long long n) { return (n + FTS - 1) / FTS; }                  // level-0 CTAs (2048 nodes each)
+static inline long long fem_ntile(long long n) { return (fem_nchunkcta(n) * FT + FTS - 1) / FTS; }    // level-1 CTAs (2048 heads each)
+// rec | utop | top rows | sheads | hrow | edge | uh (see the layout comment above fem_chunk_reduce_body); every block
+// starts on a 16-byte boundary
+static size_t fem_ws_doubles(long long n) {
+    const size_t nc = (size_t)fem_nchunkcta(n), nt = (size_t)fem_ntile(n), NH = nc * FT;
+    size_t top = (REC + 1 + 6 + 3 * FT) * nt;
+    top += top & 1;
+    return top + 4 * NH + 8 * nc + NH + 8;
+}
 
 extern "C" size_t hfl_fem_p1_workspace_bytes(int64_t n_nodes) {
     if (n_nodes < 2) return 256;
-    const long long nt = fem_ntile(n_nodes);
-    return fem_ws_doubles(nt) * sizeof(double) + 256;
+    return fem_ws_doubles(n_nodes) * sizeof(double) + 256;
 }
 
 // per right-hand side: the single-solve layout rounded up to 256 bytes
@@ -746,20 +862,24 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
         int rc = hfl_fem_flux_scan(a, R, d_u, d_ws, ws_bytes, s);
         if (rc != HFL_OK) return rc;
     } else {
-        const long long nt = fem_ntile(n);
+        const long long nc = fem_nchunkcta(n), nt = fem_ntile(n), NH = nc * FT;
         if (nt > (long long)TOPT * TOP_MAX_CHUNK) {
             set_error("hfl_fem_p1_solve: %lld nodes exceed the single-call limit of %lld; split the mesh across GPUs",
-                      (long long)n, (long long)TOPT * TOP_MAX_CHUNK * FTS);
+                      (long long)n, (long long)TOPT * TOP_MAX_CHUNK * FTS * FS);
             return HFL_ERR_UNSUPPORTED;
         }
         double* rec = reinterpret_cast<double*>(d_ws);
         double* utop = rec + (size_t)REC * nt;
         double* wsrows = utop + nt;
-        double* heads = wsrows + 6 * (size_t)nt;
+        double* sheads = wsrows + 6 * (size_t)nt;
+        size_t top = (size_t)(REC + 1 + 6 + 3 * FT) * nt;
+        top += top & 1;
+        double* hrow = rec + top;
+        double* edge = hrow + 4 * (size_t)NH;
+        double* uh = edge + 8 * (size_t)nc;
         const int S = (int)((nt + TOPT - 1) / TOPT);
-        const dim3 grid((unsigned)nt, (unsigned)R);
-        // top level: rows in shared memory while they fit (fem_top_smem_kb option, default 200 KB: 1.2e7 nodes), else in
-        // the workspace
+        const dim3 grid0((unsigned)nc, (unsigned)R), grid1((unsigned)nt, (unsigned)R);
+        // top level: rows in shared memory while they fit (fem_top_smem_kb option), else in the workspace
         const size_t top_small = (size_t)TOP_SMEM_DOUBLES * sizeof(double), top_rows = top_small + 4 * (size_t)nt * sizeof(double);
         const bool top_in_smem = top_rows <= (size_t)get_option_top_smem_kb() * 1024;
         const size_t top_smem = top_in_smem ? top_rows : top_small;
@@ -767,24 +887,17 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_smem));
         else
             HFL_CUDA_CHECK(cudaFuncSetAttribute(fem_top_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_smem));
-        auto launch_top = [&]() {
-            if (top_in_smem) fem_top_kernel<true><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
-            else fem_top_kernel<false><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
-        };
-        if (a.aq != nullptr) {
-            fem_reduce_kernel<true><<<grid, FT, 0, s>>>(a, rec, heads);
-            launch_top();
-            fem_backsub_kernel<true><<<grid, FT, 0, s>>>(a, utop, (int)nt, heads, d_u, nullptr);
-        } else if (a.exact_rowsum) {
-            fem_reduce_kernel<false, true><<<grid, FT, 0, s>>>(a, rec, heads);
-            launch_top();
-            fem_backsub_kernel<false, true><<<grid, FT, 0, s>>>(a, utop, (int)nt, heads, d_u, d_iface4);
-        } else {
-            fem_reduce_kernel<false><<<grid, FT, 0, s>>>(a, rec, heads);
-            launch_top();
-            fem_backsub_kernel<false><<<grid, FT, 0, s>>>(a, utop, (int)nt, heads, d_u, d_iface4);
-        }
-        count_launch(3);
+        if (a.aq != nullptr) fem_chunk_reduce_kernel<true><<<grid0, FT, 0, s>>>(a, hrow, edge);
+        else if (a.exact_rowsum) fem_chunk_reduce_kernel<false, true><<<grid0, FT, 0, s>>>(a, hrow, edge);
+        else fem_chunk_reduce_kernel<false><<<grid0, FT, 0, s>>>(a, hrow, edge);
+        fem_heads_reduce_kernel<<<grid1, FT, 0, s>>>(hrow, edge, NH, rec, sheads, a.ws_stride);
+        if (top_in_smem) fem_top_kernel<true><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+        else fem_top_kernel<false><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
+        fem_heads_backsub_kernel<<<grid1, FT, 0, s>>>(hrow, NH, utop, (int)nt, sheads, uh, a.ws_stride);
+        if (a.aq != nullptr) fem_chunk_backsub_kernel<true><<<grid0, FT, 0, s>>>(a, uh, d_u, nullptr);
+        else if (a.exact_rowsum) fem_chunk_backsub_kernel<false, true><<<grid0, FT, 0, s>>>(a, uh, d_u, d_iface4);
+        else fem_chunk_backsub_kernel<false><<<grid0, FT, 0, s>>>(a, uh, d_u, d_iface4);
+        count_launch(5);
         HFL_CUDA_CHECK(cudaGetLastError());
     }
     if (d_iface4 != nullptr && coarse_solver == HFL_COARSE_FLUX_SCAN) {   // the assembled solvers write it in pass 2

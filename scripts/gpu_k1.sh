@@ -8,6 +8,6 @@ echo "fem tests rc=$?" | tee -a gpurun_out/${tag}_tests.txt
 tail -5 gpurun_out/${tag}_tests.txt
 timeout 300 python scripts/probe_k1.py hybrid_fem_lssvr_b200/libhfl.so $EXTRA_LIBS > gpurun_out/${tag}_probe.txt 2>&1
 cat gpurun_out/${tag}_probe.txt
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:fem_ -c 3 -o gpurun_out/${tag}_ncu -f \
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:fem_ -c 5 -o gpurun_out/${tag}_ncu -f \
     env N_ROUNDS=1 python scripts/probe_k1.py hybrid_fem_lssvr_b200/libhfl.so > gpurun_out/${tag}_ncu.log 2>&1
 echo "ncu rc=$?"
