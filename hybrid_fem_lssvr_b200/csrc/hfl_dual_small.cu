@@ -97,7 +97,7 @@ int launch_dual_small(const hfl_plan* plan, long long E, const double* d_nodes, 
     a.coef = d_coef; a.fine = d_fine; a.status = d_status; a.err3 = d_err3;
     a.De = nullptr; a.Do = nullptr;
     a.N = plan->N; a.NH = plan->NH; a.F = plan->F; a.forcing = forcing_kind; a.debug = 0;
-    a.k_freq = k_freq; a.kk = (k_freq * pi) * (k_freq * pi);
+    a.k_freq = k_freq; a.kk = (k_freq * pi) * (k_freq * pi); a.hpk = 0.5 * pi * k_freq;
     a.c_tau = 1.0 / (16.0 * plan->gamma);
     a.cN = 0.5 / (double)(plan->N - 1);
     a.cF = 0.5 / (double)(plan->F - 1);

@@ -1,6 +1,7 @@
 // Element kernel template shared by the primal instantiations (hfl_primal.cu) and the parity-split dual
 // instantiations (hfl_dual_small.cu).
 #pragma once
+#include <cmath>
 #include <cstring>
 #include "hfl_device.cuh"
 
@@ -26,6 +27,7 @@ struct PrimalArgs {
     double c_tau;          // 1 / (16 gamma)
     double cN;             // 0.5 / (N - 1)
     double cF;             // 0.5 / (F - 1)
+    double hpk;            // k pi / 2: half-width angle of an element per unit h
 };
 
 // Tables of the parity-split DUAL form (hfl_dual.cu header comment): per parity block the (NHD + 1) x (NHD + 1)
@@ -49,6 +51,16 @@ struct PrimalTables {
     double Go[MO > 0 ? MO * (MO + 1) / 2 : 1];
     double fineE[FH > 0 ? FH : 1][ME];
     double fineO[FH > 0 ? FH : 1][MO + 1];
+    // Horner form of the fine-grid evaluation: the fine points xi+_i, z_i = xi_i^2 and the monomial coefficients of the
+    // basis, P_{2+2k}(xi) = sum_j TE[j][k] z^j, P_{3+2k}(xi) = xi sum_j TO[j][k] z^j (j <= k + 1): two constants per
+    // point pair instead of ME + MO + 1
+    double xi[FH > 0 ? FH : 1], z[FH > 0 ? FH : 1];
+    double TE[ME + 1][ME];
+    double TO[MO + 1][MO > 0 ? MO : 1];
+    // Moments of the collocation tables against the Taylor series of the sine forcing about the element centre:
+    // sum_j De[j][i] cos(th xi_j) = sum_m FE[m][i] th^(2m), sum_j Do[j][i] sin(th xi_j) = th sum_m FO[m][i] th^(2m)
+    double FE[3][ME];
+    double FO[3][MO > 0 ? MO : 1];
 };
 
 enum { STORE_DIRECT = 1, STORE_SMEM = 2, STORE_TMA = 3, STORE_TMA_ROWS = 4, STORE_COOP = 5 };
@@ -59,6 +71,10 @@ enum { STORE_DIRECT = 1, STORE_SMEM = 2, STORE_TMA = 3, STORE_TMA_ROWS = 4, STOR
 //   every STG.64 of the warp writes two complete 128-byte lines.  No TMA, no constant-bank operands.
 
 constexpr int kThreads = 128;
+#ifndef HFL_TMA_PER_WARP
+#define HFL_TMA_PER_WARP 0
+#endif
+constexpr bool kTmaPerWarp = HFL_TMA_PER_WARP != 0;   // STORE_TMA: one bulk store per warp (32-row boxes) instead of per CTA
 constexpr int kWarps = kThreads / 32;
 
 constexpr int kCoopPitch = 14;   // doubles per staged element row: w[0..M), h, S, C (M <= 11); 14 keeps STS.128 conflict-free
@@ -72,8 +88,11 @@ __host__ __device__ constexpr int tile_bytes(int F) {
 // CTAs per SM the register budget is sized for: small systems fit 128 registers (4 CTAs = 16 warps)
 // (fine grid only: 128 registers, 4 CTAs; with the fused error norms: 168 registers, 3 CTAs - at 2 CTAs / 184 registers it
 // runs 0.62 instead of 0.55 ms; fine grid + coefficient output: 2 CTAs, 0.60 instead of 0.63 ms at 3)
+#ifndef HFL_ERR_MINB
+#define HFL_ERR_MINB 3
+#endif
 __host__ __device__ constexpr int min_ctas(int M, bool err, bool coef) {
-    return (M <= 10 && !err && !coef) ? 4 : (err ? 3 : (coef ? 2 : 3));
+    return (M <= 10 && !err && !coef) ? 4 : (err ? HFL_ERR_MINB : (coef ? 2 : 3));
 }
 
 // LDL^T of a packed-lower PSD matrix in a FIXED (plan-supplied) pivot order with a skip rule: a pivot that
@@ -145,6 +164,7 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
     double* sCoef = sDe + (NHD > 0 ? 2 * (NHD + 1) * kThreads : a.NH * (ME + MO));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     unsigned char* tile_ptr = smem_raw + warp * TILE;
     const uint32_t tile_s = smem_u32(tile_ptr);
     const bool do_fine = (a.fine != nullptr) || ERR;
@@ -293,16 +313,29 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
         double sclE = 0.0, sclO = 0.0;
         if (a.debug == 2) {
         } else if (a.forcing == HFL_FORCING_SINE) {
-            double sb, cb;
-            sincospi_base(a.k_freq * h * a.cN, &sb, &cb);       // base angle k pi (h/2) / (N-1)
-            const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
-            double s = (a.N & 1) ? 0.0 : sb, c = (a.N & 1) ? 1.0 : cb;
-            for (int j = 0; j < a.NH; ++j) {
+            // f(x_c + (h/2) xi) = (k pi)^2 [S cos(th xi) + C sin(th xi)], th = k pi h / 2: the even part projects on De, the
+            // odd part on Do.  |th| <= 2^-10 (any mesh worth timing): the projections from the moment tables (three Taylor
+            // terms, truncation < 1e-20); otherwise the angle-addition rotation over the collocation pairs.
+            const double th = a.hpk * h;
+            if (fabs(th) <= 0.0009765625) {
+                const double z = th * th;
 #pragma unroll
-                for (int i = 0; i < ME; ++i) re[i] = fma(sDe[j * ME + i], c, re[i]);
+                for (int i = 0; i < ME; ++i) re[i] = fma(fma(t.FE[2][i], z, t.FE[1][i]), z, t.FE[0][i]);
 #pragma unroll
-                for (int i = 0; i < MO; ++i) ro[i] = fma(sDo[j * MO + i], s, ro[i]);
-                rotate(s, c, s2, c2);
+                for (int i = 0; i < MO; ++i) ro[i] = th * fma(fma(t.FO[2][i], z, t.FO[1][i]), z, t.FO[0][i]);
+            } else {
+                double sb, cb;
+                sincospi_base(a.k_freq * h * a.cN, &sb, &cb);       // base angle k pi (h/2) / (N-1)
+                const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
+                double s = (a.N & 1) ? 0.0 : sb, c = (a.N & 1) ? 1.0 : cb;
+#pragma unroll 1
+                for (int j = 0; j < a.NH; ++j) {
+#pragma unroll
+                    for (int i = 0; i < ME; ++i) re[i] = fma(sDe[j * ME + i], c, re[i]);
+#pragma unroll
+                    for (int i = 0; i < MO; ++i) ro[i] = fma(sDo[j * MO + i], s, ro[i]);
+                    rotate(s, c, s2, c2);
+                }
             }
             sclE = -isig * a.kk * S;
             sclO = -isig * a.kk * C;
@@ -441,21 +474,51 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
         } else
         // ---- fine grid: u(+-xi_i) = Ee +- Oo; rows go to shared memory (or straight to global)
         if (FH > 0 && do_fine) {
-            double sf = 0.0, cf = 1.0, s2f = 0.0, c2f = 1.0, sq = 0.0;
+            // even / odd parts as polynomials in z = xi^2: Ee = sum_j ae[j] z^j, Oo = xi sum_j ao[j] z^j (Horner)
+            double ae[ME + 1], ao[MO + 1];
+            ae[0] = w0; ao[0] = w1;
+#pragma unroll
+            for (int j = 1; j <= ME; ++j) ae[j] = 0.0;
+#pragma unroll
+            for (int j = 1; j <= MO; ++j) ao[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < ME; ++k)
+#pragma unroll
+                for (int j = 0; j <= k + 1; ++j) ae[j] = fma(t.TE[j][k], re[k], ae[j]);
+#pragma unroll
+            for (int k = 0; k < MO; ++k)
+#pragma unroll
+                for (int j = 0; j <= k + 1; ++j) ao[j] = fma(t.TO[j][k], ro[k], ao[j]);
+            // exact solution at +-xi: S cos(th xi) +- C sin(th xi), th = k pi h / 2.  |th| <= 2^-10 (any mesh worth timing):
+            // Taylor in z, truncation < 1e-17; otherwise a sincospi per point pair after the loop.
+            double ce1 = 0.0, ce2 = 0.0, co0 = 0.0, co1 = 0.0, sq = 0.0, sq_last = 0.0;
+            const double acc_mx0 = acc_mx;
+            bool taylor = false;
             if (ERR) {
-                sincospi_base(a.k_freq * h * a.cF, &sf, &cf);   // base angle k pi (h/2) / (F-1); F even
-                s2f = 2.0 * sf * cf;
-                c2f = fma(-2.0 * sf, sf, 1.0);
+                const double th = a.hpk * h;
+                taylor = fabs(th) <= 0.0009765625;
+                const double q = -th * th;
+                ce1 = 0.5 * (S * q); ce2 = (S * q) * (q * 4.1666666666666664e-02);
+                co0 = C * th; co1 = (C * th) * (q * 1.6666666666666666e-01);
             }
             const bool st = (a.fine != nullptr);
             if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && st && store_pending) {
-                // the CTA buffer is free once the issuing thread has seen its last bulk store read it
-                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncthreads();
+                if (kTmaPerWarp && STORE == STORE_TMA) {
+                    // the warp's buffer is free once its issuing lane has seen its last bulk stores read it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                } else {
+                    // the CTA buffer is free once the issuing thread has seen its last bulk store read it
+                    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncthreads();
+                }
                 store_pending = false;
             }
-            // TMA layout: F/16 boxes of [kThreads rows][128 B], row = thread, 16-byte chunks XOR-swizzled by row & 7
-            const uint32_t row_tma = smem_u32(smem_raw) + threadIdx.x * 128, sw = (uint32_t)(lane & 7) << 4;
+            // TMA layout: F/16 boxes of [rows][128 B], row = thread (CTA boxes of kThreads rows) or lane (warp boxes of 32
+            // rows, kTmaPerWarp), 16-byte chunks XOR-swizzled by row & 7
+            constexpr uint32_t kBoxBytes = (kTmaPerWarp && STORE == STORE_TMA) ? 32 * 128 : kThreads * 128;
+            const uint32_t row_tma = (kTmaPerWarp && STORE == STORE_TMA) ? tile_s + lane * 128 : smem_u32(smem_raw) + threadIdx.x * 128;
+            const uint32_t sw = (uint32_t)(lane & 7) << 4;
             const uint32_t row_sm = tile_s + lane * ((F + 2) * 8);
             double2* row_g = reinterpret_cast<double2*>(a.fine + e * F);
 #pragma unroll
@@ -463,21 +526,23 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
                 double up[2], um[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    double Ee = w0, Oo = w1 * t.fineO[i + q][0];
+                    const double z = t.z[i + q], x = t.xi[i + q];
+                    double Ee = ae[ME], Oo = ao[MO];
 #pragma unroll
-                    for (int k = 0; k < ME; ++k) Ee = fma(re[k], t.fineE[i + q][k], Ee);
+                    for (int j = ME - 1; j >= 0; --j) Ee = fma(Ee, z, ae[j]);
 #pragma unroll
-                    for (int k = 0; k < MO; ++k) Oo = fma(ro[k], t.fineO[i + q][1 + k], Oo);
+                    for (int j = MO - 1; j >= 0; --j) Oo = fma(Oo, z, ao[j]);
+                    Oo *= x;
                     up[q] = Ee + Oo;
                     um[q] = Ee - Oo;
                     if (ERR) {
                         // errors at +-xi are dE +- dO (dE, dO = even / odd part of u - exact), so
                         // err+^2 + err-^2 = 2 (dE^2 + dO^2) and max(|err+|, |err-|) = |dE| + |dO|
-                        const double dE = fma(-S, cf, Ee), dO = fma(-C, sf, Oo);
-                        const double wgt2 = (i + q == FH - 1) ? 1.0 : 2.0;
-                        sq = fma(wgt2, fma(dE, dE, dO * dO), sq);
+                        const double dE = Ee - fma(fma(ce2, z, ce1), z, S), dO = fma(-x, fma(co1, z, co0), Oo);
+                        const double q2 = fma(dE, dE, dO * dO);
+                        if (i + q == FH - 1) sq_last = q2;     // the two end points carry half the trapezoid weight
+                        sq += q2;
                         acc_mx = fmax(acc_mx, fabs(dE) + fabs(dO));
-                        rotate(sf, cf, s2f, c2f);
                     }
                 }
                 if (st) {
@@ -501,14 +566,35 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ap), "d"(up[0]), "d"(up[1]) : "memory");
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(am), "d"(um[1]), "d"(um[0]) : "memory");
                     } else {
-                        const uint32_t ap = row_tma + (pp >> 3) * (kThreads * 128) + ((((uint32_t)pp & 7) << 4) ^ sw);
-                        const uint32_t am = row_tma + (pm >> 3) * (kThreads * 128) + ((((uint32_t)pm & 7) << 4) ^ sw);
+                        const uint32_t ap = row_tma + (pp >> 3) * kBoxBytes + ((((uint32_t)pp & 7) << 4) ^ sw);
+                        const uint32_t am = row_tma + (pm >> 3) * kBoxBytes + ((((uint32_t)pm & 7) << 4) ^ sw);
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ap), "d"(up[0]), "d"(up[1]) : "memory");
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(am), "d"(um[1]), "d"(um[0]) : "memory");
                     }
                 }
             }
-            if (ERR && valid) acc_sq = fma(sq, h * (2.0 * a.cF), acc_sq);
+            if (ERR && !taylor) {      // coarse element: exact values by sincospi, one point pair at a time
+                sq = 0.0;
+                acc_mx = acc_mx0;
+#pragma unroll 1
+                for (int i = 0; i < FH; ++i) {
+                    const double z = t.z[i], x = t.xi[i];
+                    double Ee = ae[ME], Oo = ao[MO];
+#pragma unroll
+                    for (int j = ME - 1; j >= 0; --j) Ee = fma(Ee, z, ae[j]);
+#pragma unroll
+                    for (int j = MO - 1; j >= 0; --j) Oo = fma(Oo, z, ao[j]);
+                    Oo *= x;
+                    double sp, cp;
+                    sincospi((0.5 * a.k_freq) * h * x, &sp, &cp);
+                    const double dE = fma(-S, cp, Ee), dO = fma(-C, sp, Oo);
+                    const double q2 = fma(dE, dE, dO * dO);
+                    if (i == FH - 1) sq_last = q2;
+                    sq += q2;
+                    acc_mx = fmax(acc_mx, fabs(dE) + fabs(dO));
+                }
+            }
+            if (ERR && valid) acc_sq = fma(fma(2.0, sq, -sq_last), h * (2.0 * a.cF), acc_sq);
             if (st && STORE == STORE_SMEM) {
                 __syncwarp();
                 double2* g = reinterpret_cast<double2*>(a.fine + wtile_e0 * F);
@@ -537,7 +623,28 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
                 }
                 store_pending = true;
             }
-            if (st && STORE == STORE_TMA) {
+            if (st && STORE == STORE_TMA && kTmaPerWarp) {
+                // one bulk tensor store per 32-row box, issued by lane 0 of the warp that filled it: no CTA barrier, the
+                // warps of a CTA drift apart freely.  warp_u is the warp index as a warp-uniform value (shuffle from lane
+                // 0), which keeps the operands of the bulk store in uniform registers.
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && a.debug != 1) {
+                    const int row0 = (int)(ct * kThreads) + warp_u * 32;
+                    const uint32_t buf = smem_u32(smem_raw) + (uint32_t)warp_u * TILE;
+#pragma unroll
+                    for (int b = 0; b < F / 16; ++b) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                reinterpret_cast<uint64_t>(&tmap)),
+                            "r"(b * 16), "r"(row0), "r"(buf + b * (32 * 128))
+                            : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                store_pending = true;
+            }
+            if (st && STORE == STORE_TMA && !kTmaPerWarp) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();
                 if (threadIdx.x == 0 && a.debug != 1) {   // one bulk tensor store per box for the whole CTA tile; operands are CTA-uniform
@@ -558,8 +665,13 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
         }
     }
     if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && store_pending) {
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncthreads();
+        if (kTmaPerWarp && STORE == STORE_TMA) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+        } else {
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
     }
     if (a.err3 != nullptr) {
         const double wsq = warp_sum(acc_sq), wmx = warp_max(acc_mx);
@@ -593,12 +705,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [E][F] doubles, box = kThreads rows x 16 doubles (128 B inner extent, 128-byte swizzle)
-static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int F, bool rows_view = false) {
+static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int F, bool rows_view = false, int box_rows = kThreads) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return HFL_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)E};
     cuuint64_t strides[1] = {(cuuint64_t)F * sizeof(double)};
-    cuuint32_t box[2] = {16, (cuuint32_t)kThreads};
+    cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
     if (rows_view) {   // [E * F/16][16]: every row is one 128-byte line, the box is a contiguous block
         dims[0] = 16; dims[1] = (cuuint64_t)E * (F / 16);
         strides[0] = 128;
@@ -624,10 +736,57 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
         for (int k = 0; k < ME; ++k) t.fineE[i][k] = plan->fineE[(size_t)i * ME + k];
         for (int k = 0; k < MO + 1; ++k) t.fineO[i][k] = plan->fineO[(size_t)i * (MO + 1) + k];
     }
+    {
+        // Taylor moments of the collocation tables (see PrimalTables::FE): xi_j = the non-negative half of the N points
+        const int N = plan->N, NH = plan->NH;
+        for (int m = 0; m < 3; ++m) {
+            long double fe = 1.0L, fo = 1.0L;
+            for (int q = 1; q <= 2 * m; ++q) fe *= q;
+            for (int q = 1; q <= 2 * m + 1; ++q) fo *= q;
+            const long double sgn = (m & 1) ? -1.0L : 1.0L;
+            for (int i = 0; i < ME; ++i) {
+                long double acc = 0.0L;
+                for (int j = 0; j < NH; ++j) {
+                    const long double x = (long double)((N & 1) ? 2 * j : 2 * j + 1) / (long double)(N - 1);
+                    acc += (long double)plan->De[(size_t)j * ME + i] * powl(x, 2 * m);
+                }
+                t.FE[m][i] = (double)(sgn * acc / fe);
+            }
+            for (int i = 0; i < MO; ++i) {
+                long double acc = 0.0L;
+                for (int j = 0; j < NH; ++j) {
+                    const long double x = (long double)((N & 1) ? 2 * j : 2 * j + 1) / (long double)(N - 1);
+                    acc += (long double)plan->Do[(size_t)j * MO + i] * powl(x, 2 * m + 1);
+                }
+                t.FO[m][i] = (double)(sgn * acc / fo);
+            }
+        }
+    }
+    if (FH > 0) {
+        // monomial coefficients of P_n (long double recurrence, the entries are dyadic rationals: exact)
+        long double mono[HFL_MAX_M + 2][HFL_MAX_M + 2];
+        for (int n = 0; n < M; ++n)
+            for (int d = 0; d <= M; ++d) mono[n][d] = 0.0L;
+        mono[0][0] = 1.0L;
+        if (M > 1) mono[1][1] = 1.0L;
+        for (int n = 1; n + 1 < M; ++n)
+            for (int d = 0; d <= n + 1; ++d)
+                mono[n + 1][d] = ((2 * n + 1) * (d > 0 ? mono[n][d - 1] : 0.0L) - n * mono[n - 1][d]) / (long double)(n + 1);
+        for (int k = 0; k < ME; ++k)
+            for (int j = 0; j <= k + 1; ++j) t.TE[j][k] = (double)mono[2 + 2 * k][2 * j];
+        for (int k = 0; k < MO; ++k)
+            for (int j = 0; j <= k + 1; ++j) t.TO[j][k] = (double)mono[3 + 2 * k][2 * j + 1];
+        for (int i = 0; i < FH; ++i) {
+            const long double x = (long double)(2 * i + 1) / (long double)(2 * FH - 1);      // F = 2 FH points, xi+ ascending
+            t.xi[i] = (double)x;
+            t.z[i] = (double)(x * x);
+        }
+    }
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && a.fine != nullptr) {
-        int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F, STORE == STORE_TMA_ROWS);
+        int rc = make_fine_tensor_map(&tmap, a.fine, a.E, F, STORE == STORE_TMA_ROWS,
+                                      (kTmaPerWarp && STORE == STORE_TMA) ? 32 : kThreads);
         if (rc != HFL_OK) return rc;
     }
     auto kern = lssvr_element_kernel<M, FH, ERR, STORE, NHD, COEF>;

@@ -199,7 +199,7 @@ extern "C" int hfl_lssvr_primal_batch(const hfl_plan_t* plan, int64_t E, const d
     a.coef = d_coef; a.fine = d_fine; a.status = d_status; a.err3 = d_err3;
     a.De = plan->d_tables + plan->off_De; a.Do = plan->d_tables + plan->off_Do;
     a.N = plan->N; a.NH = plan->NH; a.F = plan->F; a.forcing = forcing_kind; a.debug = get_option_debug();
-    a.k_freq = k_freq; a.kk = (k_freq * pi) * (k_freq * pi);
+    a.k_freq = k_freq; a.kk = (k_freq * pi) * (k_freq * pi); a.hpk = 0.5 * pi * k_freq;
     a.c_tau = 1.0 / (16.0 * plan->gamma);
     a.cN = 0.5 / (double)(plan->N - 1);
     a.cF = plan->F >= 2 ? 0.5 / (double)(plan->F - 1) : 0.0;

@@ -77,6 +77,55 @@ int oracle_fem_p1(long n, const double* nodes, double kf, double* u) {
     return 0;
 }
 
+/* The same coarse system as oracle/fem_p1.py assembles - every matrix entry rounded to double exactly as the scikit-fem
+ * restatement rounds it (k_e = fl(fl(1/h)^2 * (h/2)) twice, d_i = fl(k_{i-1} + k_i), no fused contraction) - solved by
+ * the Thomas algorithm in IEEE binary128.  cond(K) ~ n^2 <= 1e15 leaves ~1e-19 of error: this is the exact solution of
+ * the reference's rounded system to double precision, the yardstick for the GPU coarse solve at sizes where double
+ * precision direct solvers (SuperLU, LAPACK) are themselves 1e-8 apart.  exact_rowsum != 0: unrounded diagonal
+ * k_{i-1} + k_i (HFL_COARSE_ASSEMBLED_EXACT). */
+__attribute__((optimize("fp-contract=off")))
+int oracle_fem_p1_quad(long n, const double* nodes, double kf, int exact_rowsum, double u_left, double u_right, double* u) {
+    const double pi = 3.14159265358979323846, kpi = kf * pi, kp2 = kpi * kpi;
+    const double gx0 = 0.5 * (-0.5773502691896257) + 0.5, gx1 = 0.5 * (0.5773502691896257) + 0.5;
+    if (n < 2) return 2;
+    double* kk = (double*)malloc(sizeof(double) * (size_t)n);
+    double* b = (double*)calloc((size_t)n, sizeof(double));
+    __float128* cp = (__float128*)malloc(sizeof(__float128) * (size_t)n);
+    __float128* g = (__float128*)malloc(sizeof(__float128) * (size_t)n);
+    if (!kk || !b || !cp || !g) return 1;
+    for (long e = 0; e + 1 < n; ++e) {
+        const double h = nodes[e + 1] - nodes[e], invh = 1.0 / h, gg = invh * invh, hw = h * 0.5;
+        const double kq = gg * hw;
+        kk[e] = kq + kq;
+        const double x0 = h * gx0 + nodes[e], x1 = h * gx1 + nodes[e];
+        const double f0 = kp2 * sin(kpi * x0), f1 = kp2 * sin(kpi * x1);
+        b[e] += (f0 * (1.0 - gx0)) * hw;
+        b[e + 1] += (f0 * gx0) * hw;
+        b[e] += (f1 * (1.0 - gx1)) * hw;
+        b[e + 1] += (f1 * gx1) * hw;
+    }
+    u[0] = u_left; u[n - 1] = u_right;
+    if (n > 2) {
+        __float128 prev_c = 0, prev_g = u_left;      /* row 0 is the identity row u_0 = u_left */
+        cp[0] = 0; g[0] = u_left;
+        for (long i = 1; i + 1 < n; ++i) {
+            const __float128 l = -(__float128)kk[i - 1], r = -(__float128)kk[i];
+            const __float128 dd = exact_rowsum ? (__float128)kk[i - 1] + (__float128)kk[i] : (__float128)(kk[i - 1] + kk[i]);
+            const __float128 den = dd - l * prev_c;
+            prev_c = r / den;
+            prev_g = ((__float128)b[i] - l * prev_g) / den;
+            cp[i] = prev_c; g[i] = prev_g;
+        }
+        __float128 x = u_right;
+        for (long i = n - 2; i >= 1; --i) {
+            x = g[i] - cp[i] * x;
+            u[i] = (double)x;
+        }
+    }
+    free(kk); free(b); free(cp); free(g);
+    return 0;
+}
+
 /* All element solves: coef[E][M] and (optionally) fine[E][F]; returns max |u - sin(k pi x)| over the fine grid. */
 double oracle_primal_batch(long E, const double* nodes, const double* u, int M, double gamma, int N, double kf, int F,
                            double* coef, double* fine) {

@@ -22,6 +22,8 @@ def load(build=True):
     lib.oracle_set_threads.argtypes = [C.c_int]
     lib.oracle_fem_p1.restype = C.c_int
     lib.oracle_fem_p1.argtypes = [C.c_long, dp, C.c_double, dp]
+    lib.oracle_fem_p1_quad.restype = C.c_int
+    lib.oracle_fem_p1_quad.argtypes = [C.c_long, dp, C.c_double, C.c_int, C.c_double, C.c_double, dp]
     lib.oracle_primal_batch.restype = C.c_double
     lib.oracle_primal_batch.argtypes = [C.c_long, dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                         C.c_void_p, C.c_void_p]
@@ -41,6 +43,16 @@ def fem_p1(nodes, k_freq=1.0):
     nodes = np.ascontiguousarray(nodes, dtype=np.float64)
     u = np.empty_like(nodes)
     assert load().oracle_fem_p1(nodes.size, nodes, float(k_freq), u) == 0
+    return u
+
+
+def fem_p1_quad(nodes, k_freq=1.0, exact_rowsum=False, u_left=0.0, u_right=0.0):
+    """Nodal values of the reference's rounded coarse system (oracle/fem_p1.assemble_p1's entries, Dirichlet rows as
+    identity rows) solved in IEEE binary128: its exact solution to double precision (P:117-145)."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    u = np.empty_like(nodes)
+    rc = load().oracle_fem_p1_quad(nodes.size, nodes, float(k_freq), int(bool(exact_rowsum)), float(u_left), float(u_right), u)
+    assert rc == 0, rc
     return u
 
 
