@@ -57,7 +57,13 @@ def _collocation_points(nodes, N):
 def lssvr_primal(rhs_func, domain_range, u_xmin, u_xmax, M, gamma,
                  is_left_boundary=False, is_right_boundary=False,
                  global_domain_range=(-1, 1), *, n_colloc=N_COLLOCATION):
-    """LSSVR primal solve of one element; returns ``numpy.polynomial.Legendre`` (P:20-105)."""
+    """LSSVR primal solve of one element; returns ``numpy.polynomial.Legendre`` (P:20-105).
+
+    M >= 3 (at least one coefficient beyond the two that the boundary conditions fix; the reference accepts M = 2, where
+    the QP has the linear interpolant as its only feasible point)."""
+    if M < 3:
+        raise ValueError('lssvr_primal: M = %d; this implementation needs M >= 3 (M = 2 leaves only the linear '
+                         'interpolant of the two boundary values)' % M)
     xmin, xmax = domain_range
     global_xmin, global_xmax = global_domain_range
     # boundary-flag branches P:68-69 / P:75-76
@@ -114,8 +120,9 @@ class FEMLSSVRPrimalSolver:
     """Reference class P:107-211 with the arithmetic on the GPU.
 
     Keyword-only additions (defaults reproduce the reference): ``rhs_func`` (default: the shipped
-    ``poisson_rhs``, evaluated on the device), ``k_freq`` (forcing (k pi)^2 sin(k pi x) when rhs_func is
-    None), ``n_colloc`` (P:40 hard-codes 12), ``coarse_solver`` ('assembled': the reference's rounded
+    ``poisson_rhs``, evaluated on the device; any other callable is sampled on the host - at the two Gauss points of
+    every element for the coarse solve and at the collocation points for the element solves - so that BOTH stages solve
+    -u'' = rhs_func), ``k_freq`` (forcing (k pi)^2 sin(k pi x) when rhs_func is None), ``n_colloc`` (P:40 hard-codes 12), ``coarse_solver`` ('assembled': the reference's rounded
     tridiagonal system, faithful at any size | 'assembled_exact' | 'flux': the same equations without the rounded
     diagonal, which is what to use beyond ~1e5 nodes - see include/hfl.h), ``form``
     ('primal' | 'dual').
@@ -142,13 +149,28 @@ class FEMLSSVRPrimalSolver:
         """Coarse P1 solve (P:117-145).  Returns (u_fem, basis) like the reference."""
         a, b = self.global_domain
         self._d_nodes = batch.mesh_linspace(a, b, self.num_fem_nodes)   # P:120
-        self._d_u = batch.fem_p1_solve(self._d_nodes, k_freq=self.k_freq,
-                                       u_left=main_boundary_condition_left(a),
-                                       u_right=main_boundary_condition_right(b),
-                                       coarse_solver=self.coarse_solver)
         self.fem_nodes = self._d_nodes.cpu().numpy()
+        ul, ur = main_boundary_condition_left(a), main_boundary_condition_right(b)
+        if self._sine_frequency() is not None:
+            self._d_u = batch.fem_p1_solve(self._d_nodes, k_freq=self._sine_frequency(), u_left=ul, u_right=ur,
+                                           coarse_solver=self.coarse_solver)
+        else:
+            # arbitrary rhs_func: the same P1 assembly (2-point Gauss load, P:129-136) from host samples of the callable
+            x0, h = self.fem_nodes[:-1], np.diff(self.fem_nodes)
+            pts = np.stack([x0 + h * batch.GAUSS_X[0], x0 + h * batch.GAUSS_X[1]])
+            dev = self._d_nodes.device
+            fq = torch.from_numpy(np.ascontiguousarray(_sample_rhs(self.rhs_func, pts))).to(dev)
+            self._d_u = batch.fem_p1_solve_general(self._d_nodes, torch.ones_like(fq), fq, u_left=ul, u_right=ur)
         self.fem_values = self._d_u.cpu().numpy()
         return self.fem_values.copy(), P1Basis(self.fem_nodes)
+
+    def _sine_frequency(self):
+        """k when the forcing is the device family (k pi)^2 sin(k pi x) (rhs_func None or the shipped poisson_rhs), else None."""
+        if self.rhs_func is None:
+            return self.k_freq
+        if self.rhs_func is poisson_rhs:
+            return 1.0
+        return None
 
     def solve_lssvr_subproblems(self):
         """All element solves in one launch (P:147-176)."""
@@ -158,9 +180,9 @@ class FEMLSSVRPrimalSolver:
         u = self._d_u.clone()
         u[0] = main_boundary_condition_left(self.global_domain[0])
         u[-1] = main_boundary_condition_right(self.global_domain[1])
-        if self.rhs_func is None or self.rhs_func is poisson_rhs:
+        if self._sine_frequency() is not None:
             forcing = 'sine'
-            k = 1.0 if self.rhs_func is poisson_rhs else self.k_freq
+            k = self._sine_frequency()
         else:
             pts = _collocation_points(self.fem_nodes, self.n_colloc)
             forcing = torch.from_numpy(np.ascontiguousarray(_sample_rhs(self.rhs_func, pts))).to(self._d_nodes.device)
@@ -184,6 +206,4 @@ class FEMLSSVRPrimalSolver:
         x_points = np.asarray(x_points)
         xs = torch.from_numpy(np.ascontiguousarray(x_points, dtype=np.float64).reshape(-1)).to(self._d_nodes.device)
         vals = batch.evaluate_points(self._d_nodes, self._d_coef, xs).cpu().numpy()
-        solution = np.zeros_like(x_points, dtype=np.float64)
-        solution.reshape(-1)[:] = vals
-        return solution
+        return vals.reshape(x_points.shape)      # vals is in C order of x_points, whatever its memory layout

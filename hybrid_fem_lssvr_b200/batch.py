@@ -32,16 +32,41 @@ class Plan:
             pass
 
 
-def get_plan(M, N, F, gamma):
-    key = (int(M), int(N), int(F), float(gamma), torch.cuda.current_device())
+def get_plan(M, N, F, gamma, device=None):
+    """Plan for (M, N, F, gamma) on `device` (default: the current device); its tables live on that device."""
+    index = torch.cuda.current_device() if device is None else _index(device)
+    key = (int(M), int(N), int(F), float(gamma), index)
     p = _PLANS.get(key)
     if p is None:
-        p = _PLANS[key] = Plan(M, N, F, gamma)
+        with torch.cuda.device(index):
+            p = _PLANS[key] = Plan(M, N, F, gamma)
     return p
+
+
+def _index(device):
+    device = torch.device(device)
+    return torch.cuda.current_device() if device.index is None else device.index
 
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device_of(arg=0):
+    """Run the wrapped entry point with the device of its tensor argument current: plan tables, scratch space and the
+    stream then belong to the device the data live on, whatever device the caller has selected."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            t = args[arg]
+            if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kwargs)
+            return fn(*args, **kwargs)
+        return wrapper
+    return deco
 
 
 def _ptr(t):
@@ -58,9 +83,10 @@ def _require_cuda_f64(t, name, numel=None):
 def mesh_linspace(a, b, n_global, i0=0, n_local=None, device='cuda'):
     """numpy.linspace(a, b, n_global)[i0:i0+n_local] generated on the device, bit for bit (P:120)."""
     n_local = n_global - i0 if n_local is None else n_local
-    out = torch.empty(n_local, dtype=torch.float64, device=device)
-    _lib.check(_lib.load().hfl_mesh_linspace(float(a), float(b), int(n_global), int(i0), int(n_local),
-                                             _ptr(out), _stream()), 'hfl_mesh_linspace')
+    with torch.cuda.device(_index(device)):
+        out = torch.empty(n_local, dtype=torch.float64, device='cuda')
+        _lib.check(_lib.load().hfl_mesh_linspace(float(a), float(b), int(n_global), int(i0), int(n_local),
+                                                 _ptr(out), _stream()), 'hfl_mesh_linspace')
     return out
 
 
@@ -84,6 +110,7 @@ COARSE_MODES = {'assembled': _lib.COARSE_ASSEMBLED_PCR, 'pcr': _lib.COARSE_ASSEM
                 'flux': _lib.COARSE_FLUX_SCAN, 'assembled_exact': _lib.COARSE_ASSEMBLED_EXACT}
 
 
+@_on_device_of(0)
 def fem_p1_solve(nodes, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='assembled', out=None,
                  want_reaction=False):
     """K1: nodal values of the coarse P1 FEM solve (P:117-145) for -u'' = (k pi)^2 sin(k pi x).
@@ -105,6 +132,7 @@ def fem_p1_solve(nodes, k_freq=1.0, u_left=0.0, u_right=0.0, coarse_solver='asse
     return (u, react) if want_reaction else u
 
 
+@_on_device_of(0)
 def fem_p1_solve_multi(nodes, k_freqs, u_left=0.0, u_right=0.0, coarse_solver='assembled', out=None):
     """K1 for R forcing frequencies on one mesh in a single launch sequence: u [R, n], row r bit-identical to
     fem_p1_solve(nodes, k_freq=k_freqs[r]).  k_freqs: float64 device tensor [R]."""
@@ -125,6 +153,7 @@ def fem_p1_solve_multi(nodes, k_freqs, u_left=0.0, u_right=0.0, coarse_solver='a
 GAUSS_X = (0.5 - 0.5 / math.sqrt(3.0), 0.5 + 0.5 / math.sqrt(3.0))   # 2-point Gauss abscissae on [0, 1]
 
 
+@_on_device_of(0)
 def fem_p1_solve_general(nodes, aq, fq, cq=None, u_left=0.0, u_right=0.0, out=None):
     """Coarse P1 solve of -(a u')' + c u = f; aq, cq, fq are [2, E] samples at the Gauss points
     x_e + h_e * GAUSS_X[q] of every element."""
@@ -141,6 +170,7 @@ def fem_p1_solve_general(nodes, aq, fq, cq=None, u_left=0.0, u_right=0.0, out=No
     return u
 
 
+@_on_device_of(0)
 def fem_apply_bc(nodes, u, bc_left, bc_right):
     _require_cuda_f64(nodes, 'nodes')
     _require_cuda_f64(u, 'u', nodes.numel())
@@ -159,6 +189,7 @@ def spike_interface_solve(gathered, u_left=0.0, u_right=0.0):
     return list(out)
 
 
+@_on_device_of(1)
 def _element_batch(fn_name, nodes, u, M, gamma, N, F, forcing, k_freq, bc2, want_coef, want_fine, want_status,
                    err3, coef_out, fine_out):
     _require_cuda_f64(nodes, 'nodes')
@@ -209,6 +240,7 @@ def lssvr_dual_batch(nodes, u, M, gamma, N=12, F=0, forcing='sine', k_freq=1.0, 
                           want_fine, want_status, err3, coef_out, fine_out)
 
 
+@_on_device_of(0)
 def lssvr_dual_multi(nodes, u, k_freqs, M, gamma, N=12, F=0, forcing='sine', bc2=None, want_coef=True,
                      want_fine=False, want_status=False, err3=None):
     """K4 with R right-hand sides per element sharing one factorisation (BASELINE configs[4]).
@@ -241,6 +273,7 @@ def lssvr_dual_multi(nodes, u, k_freqs, M, gamma, N=12, F=0, forcing='sine', bc2
     return coef, fine, status
 
 
+@_on_device_of(0)
 def lssvr_general_batch(nodes, u, a, f, M, gamma, N=12, F=0, da=None, c=None, bc2=None, want_coef=True,
                         want_fine=False, want_status=False):
     """Per-element LSSVR for -(a u')' + c u = f; a, da (= a'), c, f are [N, E] CUDA tensors of samples at the
@@ -262,6 +295,7 @@ def lssvr_general_batch(nodes, u, a, f, M, gamma, N=12, F=0, da=None, c=None, bc
     return coef, fine, status
 
 
+@_on_device_of(0)
 def evaluate_points(nodes, coef, x):
     """K3 unstructured: evaluate_solution's element search + legval on the device (P:184-211)."""
     _require_cuda_f64(nodes, 'nodes')
@@ -281,6 +315,7 @@ def new_error_accumulator(device='cuda'):
     return torch.zeros(3, dtype=torch.float64, device=device)
 
 
+@_on_device_of(0)
 def error_fine(nodes, fine, k_freq=1.0, err3=None):
     _require_cuda_f64(nodes, 'nodes')
     E = nodes.numel() - 1
@@ -292,6 +327,7 @@ def error_fine(nodes, fine, k_freq=1.0, err3=None):
     return err3
 
 
+@_on_device_of(0)
 def error_nodal(nodes, u, k_freq=1.0, err3=None):
     _require_cuda_f64(nodes, 'nodes')
     _require_cuda_f64(u, 'u', nodes.numel())

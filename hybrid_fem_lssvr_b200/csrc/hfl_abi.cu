@@ -13,6 +13,7 @@ static std::atomic<int> g_opt_store{0};
 static std::atomic<int> g_opt_debug{0};
 static std::atomic<int> g_opt_dual_team{0};
 static std::atomic<int> g_opt_top_smem_kb{227};
+static std::atomic<int> g_opt_peer_spin_log2{24};
 static std::atomic<int> g_sm_count{0};
 
 void set_error(const char* fmt, ...) {
@@ -26,6 +27,7 @@ int get_option_store() { return g_opt_store.load(); }
 int get_option_debug() { return g_opt_debug.load(); }
 int get_option_dual_team() { return g_opt_dual_team.load(); }
 int get_option_top_smem_kb() { return g_opt_top_smem_kb.load(); }
+int get_option_peer_spin_log2() { return g_opt_peer_spin_log2.load(); }
 
 int sm_count() {
     int v = g_sm_count.load();
@@ -92,6 +94,12 @@ extern "C" int hfl_set_option(const char* key, int value) {
     if (strcmp(key, "fem_top_smem_kb") == 0) {
         HFL_REQUIRE(value >= 64 && value <= 227, "fem_top_smem_kb must be 64..227");
         g_opt_top_smem_kb.store(value);
+        return HFL_OK;
+    }
+    // receive spin of the peer-memory exchange: 2^value polls before the call gives up and poisons its output with NaN
+    if (strcmp(key, "peer_spin_log2") == 0) {
+        HFL_REQUIRE(value >= 4 && value <= 40, "peer_spin_log2 must be 4..40");
+        g_opt_peer_spin_log2.store(value);
         return HFL_OK;
     }
     if (strcmp(key, "primal_debug") == 0) {
@@ -242,6 +250,7 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
     p->off_Vt = push(p->Vt);
     p->off_Cpe = push(p->Cpe); p->off_Cpo = push(p->Cpo); p->off_Kpe = push(p->Kpe); p->off_Kpo = push(p->Kpo);
     p->n_tables = blk.size();
+    (void)cudaGetDevice(&p->device);
     cudaError_t e = cudaMalloc((void**)&p->d_tables, blk.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tables, blk.data(), blk.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -254,16 +263,27 @@ extern "C" int hfl_plan_create(hfl_plan_t** out, int M, int N, int F, double gam
     return HFL_OK;
 }
 
+int hfl::plan_on_current_device(const hfl_plan* p, const char* who) {
+    int dev = -1;
+    HFL_CUDA_CHECK(cudaGetDevice(&dev));
+    HFL_REQUIRE(dev == p->device, "%s: the plan was created on device %d but the current device is %d (its tables are not "
+                "addressable from here); create one plan per device", who, p->device, dev);
+    return HFL_OK;
+}
+
 double* hfl::plan_scratch(const hfl_plan* p, cudaStream_t s, size_t bytes) {
     std::lock_guard<std::mutex> guard(p->scratch_mu);
     auto& slot = p->scratch[s];
     if (slot.second < bytes) {
-        if (slot.first) cudaFree(slot.first);      // synchronises: work queued on the old buffer finishes first
+        // stream-ordered (no device synchronisation on the launch path, legal under stream capture): the old buffer is
+        // released after the work already queued on it, the new one exists before the kernel that follows
+        if (slot.first) cudaFreeAsync(slot.first, s);
         slot = {nullptr, 0};
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, bytes);
+        cudaError_t e = cudaMallocAsync(&q, bytes, s);
         if (e != cudaSuccess) {
-            set_error("plan scratch: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            (void)cudaGetLastError();      // do not leave the failure latched for the next CUDA call
+            set_error("plan scratch: cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
             return nullptr;
         }
         slot = {q, bytes};

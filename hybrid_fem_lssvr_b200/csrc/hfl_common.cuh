@@ -18,6 +18,7 @@ int get_option_store();
 int get_option_debug();
 int get_option_dual_team();
 int get_option_top_smem_kb();
+int get_option_peer_spin_log2();
 int sm_count();
 
 #define HFL_CUDA_CHECK(expr)                                                            \
@@ -47,6 +48,7 @@ __host__ __device__ constexpr int n_odd(int M) { return (M - 2) / 2; }
 // Plan: element-independent tables (host copies + device copies).
 struct hfl_plan {
     int M, N, F;
+    int device = 0;   // the device the tables live on; launches with another current device are refused
     double gamma;
     int me, mo;   // even / odd bubble counts
     int NH, FH;   // ceil(N/2) collocation pairs, ceil(F/2) fine pairs
@@ -80,4 +82,6 @@ struct hfl_plan {
 namespace hfl {
 // At least `bytes` of device scratch tied to (plan, stream); NULL (and the error string set) when the allocation fails.
 double* plan_scratch(const hfl_plan* plan, cudaStream_t s, size_t bytes);
+// HFL_OK when the current device is the one the plan was created on, else HFL_ERR_ARG with the message set.
+int plan_on_current_device(const hfl_plan* plan, const char* who);
 }

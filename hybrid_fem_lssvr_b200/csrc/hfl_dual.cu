@@ -448,10 +448,14 @@ static int launch_dual(const hfl_plan* plan, long long E, int R, const double* d
         pa.Cp[0] = plan->d_tables + plan->off_Cpe; pa.Cp[1] = plan->d_tables + plan->off_Cpo;
         pa.MA[0] = n_even(plan->M) + 1; pa.MA[1] = n_odd(plan->M) + 1;
         pa.Vt = plan->d_tables + plan->off_Vt;
-        if (get_option_dual_team() != 3 && launch_dual_parity_left(pa, max_smem, plan, s)) {   // left-looking kernel (nh <= 96)
-            count_launch();
-            HFL_CUDA_CHECK(cudaGetLastError());
-            return HFL_OK;
+        if (get_option_dual_team() != 3) {                  // left-looking kernel (nh <= 96)
+            const int rc = launch_dual_parity_left(pa, max_smem, plan, s);
+            if (rc == HFL_OK) {
+                count_launch();
+                HFL_CUDA_CHECK(cudaGetLastError());
+                return HFL_OK;
+            }
+            if (rc != HFL_ERR_UNSUPPORTED) return rc;       // a CUDA failure is reported, not papered over by the fallback
         }
         const size_t td = (size_t)pa.nh * pa.ldh + pa.nh + 8;
         const size_t tb = ((td * 8 + (size_t)(pa.nh + 2) * 4) + 15) / 16 * 16;
@@ -496,6 +500,7 @@ using namespace hfl;
 static int dual_check(const hfl_plan_t* plan, int64_t E, int R, const double* d_nodes, const double* d_u,
                       int forcing_kind, const double* d_f, double* d_fine) {
     HFL_REQUIRE(plan != nullptr, "hfl_lssvr_dual: plan is NULL");
+    { const int drc = plan_on_current_device(plan, "hfl_lssvr_dual"); if (drc != HFL_OK) return drc; }
     HFL_REQUIRE(E >= 0 && R >= 1, "hfl_lssvr_dual: E < 0 or R < 1");
     HFL_REQUIRE(E == 0 || (d_nodes != nullptr && d_u != nullptr), "hfl_lssvr_dual: d_nodes / d_u is NULL");
     HFL_REQUIRE(forcing_kind == HFL_FORCING_SINE || forcing_kind == HFL_FORCING_SAMPLES,

@@ -41,6 +41,6 @@ struct DualParityArgs {
 
 // hfl_dual_parity.cu (left-looking parity kernel); returns false when the shape is not covered (nh > 96 or not
 // enough shared memory) and the caller falls back to the shared-memory right-looking kernel
-bool launch_dual_parity_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cudaStream_t s);
+int launch_dual_parity_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cudaStream_t s);   // HFL_OK | HFL_ERR_UNSUPPORTED (fall back) | HFL_ERR_CUDA
 
 }  // namespace hfl

@@ -271,27 +271,28 @@ size_t dual_parity_left_spill_doubles(int nh, int ldh, long long max_grid) {
     return (size_t)max_grid * 2 * (size_t)(nh - dual_parity_left_kc(nh)) * ldh;
 }
 
-bool launch_dual_parity_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cudaStream_t s) {
+// Returns HFL_OK (launched), HFL_ERR_UNSUPPORTED (shape not covered by this kernel: the caller falls back to the
+// shared-memory parity kernel) or HFL_ERR_CUDA (a CUDA call failed; the error string is set and nothing was launched).
+int launch_dual_parity_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cudaStream_t s) {
     const DualArgs& a = pa.d;
-    if (pa.nh > LT || pa.MA[0] > LMAXMA || pa.MA[1] > LMAXMA) return false;
+    if (pa.nh > LT || pa.MA[0] > LMAXMA || pa.MA[1] > LMAXMA) return HFL_ERR_UNSUPPORTED;
     pa.kc = dual_parity_left_kc(pa.nh);
     const size_t smem = 2 * lt_team_bytes(pa.nh, pa.ldh, pa.kc) + ((size_t)a.R * a.M + 2 * (size_t)a.R) * 8;
-    if (smem > (size_t)max_smem) return false;
-    if (cudaFuncSetAttribute(dual_parity_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return false;
+    if (smem > (size_t)max_smem) return HFL_ERR_UNSUPPORTED;
+    HFL_CUDA_CHECK(cudaFuncSetAttribute(dual_parity_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dual_parity_left_kernel, 2 * LT, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
+    HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dual_parity_left_kernel, 2 * LT, smem));
+    if (per_sm < 1) per_sm = 1;
     long long grid = a.E;
     const long long cap = (long long)sm_count() * per_sm;
     if (grid > cap) grid = cap;
     pa.spill = nullptr;
     if (pa.kc < pa.nh) {
         pa.spill = plan_scratch(plan, s, dual_parity_left_spill_doubles(pa.nh, pa.ldh, grid) * sizeof(double));
-        if (pa.spill == nullptr) return false;
+        if (pa.spill == nullptr) return HFL_ERR_CUDA;       // plan_scratch has set the error string
     }
     dual_parity_left_kernel<<<(unsigned)grid, 2 * LT, smem, s>>>(pa);
-    return true;
+    return HFL_OK;
 }
 
 }  // namespace hfl

@@ -159,6 +159,7 @@ extern "C" int hfl_lssvr_general_batch(const hfl_plan_t* plan, int64_t E, const 
                                        const double* d_bc2, double* d_coef, double* d_fine, int32_t* d_status,
                                        void* stream) {
     HFL_REQUIRE(plan != nullptr, "hfl_lssvr_general_batch: plan is NULL");
+    { const int drc = plan_on_current_device(plan, "hfl_lssvr_general_batch"); if (drc != HFL_OK) return drc; }
     HFL_REQUIRE(E >= 0, "hfl_lssvr_general_batch: E < 0");
     if (E == 0) return HFL_OK;
     HFL_REQUIRE(d_nodes && d_u && d_a && d_f, "hfl_lssvr_general_batch: d_nodes / d_u / d_a / d_f is NULL");

@@ -7,8 +7,10 @@
 // with one 8-byte store, so the receiver needs no fence - it spins (volatile loads, served by its own L2) until the
 // word's epoch matches, and a torn double cannot be observed.  Slots are double-buffered by epoch parity: a rank can
 // only be two epochs ahead of a peer after that peer has left the epoch in between, so a slot is never overwritten
-// before it has been read.  The spin is bounded (~2 s): on expiry the status word is set and the kernel returns
-// instead of hanging the GPU.
+// before it has been read.  The spin is bounded (2^peer_spin_log2 polls, default 2^24 ~ 8 s; hfl_set_option): on expiry
+// the status word is set, the missing doubles are delivered as NaN (and so are the interface values computed from them),
+// so a late or dead peer poisons every downstream result instead of passing off the stale payload of an older epoch,
+// and the kernel returns instead of hanging the GPU.
 //
 // Buffers are plain cudaMalloc allocations exported with cudaIpcGetMemHandle; the host side (dist.PeerExchange)
 // swaps the 64-byte handles through torch.distributed and opens them with cudaIpcOpenMemHandle.
@@ -32,8 +34,11 @@ __device__ __forceinline__ unsigned long long* peer_slot(void* buf, int channel,
 // gathered records - the exchange and the (G-1)-unknown solve of the partitioned coarse solve in one launch.
 __global__ void peer_allgather_kernel(int G, int rank, int W, const double* __restrict__ src, void* const* __restrict__ bufs,
                                       unsigned int epoch, int channel, double* __restrict__ out, int* __restrict__ status,
-                                      double uL, double uR, double* __restrict__ bc2) {
+                                      double uL, double uR, double* __restrict__ bc2, long long max_spin) {
     __shared__ unsigned int halves[PEER_MAX_RANKS * PEER_MAX_DOUBLES * 2];
+    __shared__ int s_expired;
+    if (threadIdx.x == 0) s_expired = 0;
+    __syncthreads();
     const int nw = 2 * W;
     for (int t = threadIdx.x; t < G * nw; t += blockDim.x) {
         const int p = t / nw, j = t - p * nw;
@@ -48,12 +53,16 @@ __global__ void peer_allgather_kernel(int G, int rank, int W, const double* __re
         const unsigned long long* slot = peer_slot(bufs[rank], channel, epoch, p) + j;
         unsigned long long word = 0ull;
         bool got = false;
-        for (long long spin = 0; spin < (1ll << 22); ++spin) {
+        for (long long spin = 0; spin < max_spin; ++spin) {
             asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(word) : "l"(slot) : "memory");
             if ((unsigned int)(word >> 32) == epoch) { got = true; break; }
             if (spin > 1024) __nanosleep(256);
         }
-        if (!got && status != nullptr) atomicExch(status, 1);
+        if (!got) {
+            s_expired = 1;
+            if (status != nullptr) atomicExch(status, 1);
+            word = (j & 1) ? 0x7ff80000ull : 0ull;        // the two halves of a quiet NaN
+        }
         halves[t] = (unsigned int)word;
     }
     __syncthreads();
@@ -63,7 +72,10 @@ __global__ void peer_allgather_kernel(int G, int rank, int W, const double* __re
     }
     if (bc2 != nullptr) {
         __syncthreads();           // out[] is complete (global writes of this CTA are visible to it after the barrier)
-        if (threadIdx.x == 0) spike_iface_solve(G, out, uL, uR, rank, bc2);
+        if (threadIdx.x == 0) {
+            spike_iface_solve(G, out, uL, uR, rank, bc2);
+            if (s_expired) { bc2[0] = __longlong_as_double(0x7ff8000000000000ll); bc2[1] = bc2[0]; }
+        }
     }
 }
 
@@ -121,7 +133,7 @@ extern "C" int hfl_peer_allgather(int G, int rank, int W, const double* d_src, v
     HFL_REQUIRE(epoch != 0, "hfl_peer_allgather: epoch 0 is the cleared state of the buffers");
     HFL_REQUIRE(d_src != nullptr && d_bufs != nullptr && d_out != nullptr, "hfl_peer_allgather: NULL pointer");
     peer_allgather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(G, rank, W, d_src, d_bufs, epoch, channel, d_out, d_status,
-                                                               0.0, 0.0, nullptr);
+                                                               0.0, 0.0, nullptr, 1ll << get_option_peer_spin_log2());
     count_launch();
     HFL_CUDA_CHECK(cudaGetLastError());
     return HFL_OK;
@@ -137,7 +149,7 @@ extern "C" int hfl_peer_spike_exchange(int G, int rank, const double* d_iface4, 
     HFL_REQUIRE(d_iface4 != nullptr && d_bufs != nullptr && d_gathered != nullptr && d_bc2 != nullptr,
                 "hfl_peer_spike_exchange: NULL pointer");
     peer_allgather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(G, rank, 4, d_iface4, d_bufs, epoch, channel, d_gathered,
-                                                               d_status, u_left, u_right, d_bc2);
+                                                               d_status, u_left, u_right, d_bc2, 1ll << get_option_peer_spin_log2());
     count_launch();
     HFL_CUDA_CHECK(cudaGetLastError());
     return HFL_OK;

@@ -183,6 +183,7 @@ extern "C" int hfl_lssvr_primal_batch(const hfl_plan_t* plan, int64_t E, const d
                                       const double* d_bc2, double* d_coef, double* d_fine, int32_t* d_status,
                                       double* d_err3, void* stream) {
     HFL_REQUIRE(plan != nullptr, "hfl_lssvr_primal_batch: plan is NULL");
+    { const int drc = plan_on_current_device(plan, "hfl_lssvr_primal_batch"); if (drc != HFL_OK) return drc; }
     HFL_REQUIRE(E >= 0, "hfl_lssvr_primal_batch: E < 0");
     if (E == 0) return HFL_OK;
     HFL_REQUIRE(d_nodes != nullptr && d_u != nullptr, "hfl_lssvr_primal_batch: d_nodes / d_u is NULL");

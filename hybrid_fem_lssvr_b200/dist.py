@@ -105,6 +105,13 @@ class PeerExchange:
         """True when a receive spin expired since construction (host sync)."""
         return bool(self.status.item())
 
+    def check(self):
+        """Raise when a receive spin expired since construction (host sync).  The kernels have already poisoned what they
+        delivered with NaN; this turns it into an exception at the host's next synchronisation point."""
+        if self.timed_out():
+            raise _lib.HflError('peer-memory exchange timed out on rank %d: a peer did not deliver its record within the '
+                                'receive spin (hfl_set_option peer_spin_log2); results of this step are NaN' % self.rank)
+
     def close(self):
         for peer in self._peers:
             self._lib.hfl_peer_buffer_close(peer)
@@ -187,9 +194,14 @@ def gather_error(err3, group=None, out=None, exchange=None):
     return out
 
 
-def finish_gathered_error(gathered):
-    """(L2, max, failed) from the [G, 3] accumulators: sum, max, sum."""
+def finish_gathered_error(gathered, exchange=None):
+    """(L2, max, failed) from the [G, 3] accumulators: sum, max, sum.  This is the host synchronisation point of a
+    step: with `exchange` given, a receive spin that expired anywhere in the step raises here."""
     g = gathered.cpu()
+    if exchange is not None:
+        exchange.check()
+    if bool(torch.isnan(g).any()):
+        raise _lib.HflError('error accumulators are NaN: an interface exchange delivered NaN (timeout) or the solve diverged')
     return math.sqrt(float(g[:, 0].sum())), float(g[:, 1].max()), int(g[:, 2].sum())
 
 

@@ -115,7 +115,9 @@ int hfl_spike_interface_solve_device(int G, const double* d_gathered, double u_l
  * transport), every rank opens its peers' buffers and keeps the G device pointers in a device array d_bufs[G]
  * (its own buffer at [rank]).  hfl_peer_allgather: d_out[G][W] <- every rank's d_src[W] (W <= 4), stream-ordered;
  * all ranks must call it with the same (epoch, channel, W); epoch != 0 increases by one per call on a channel
- * (channel < 4 separates call sites).  The receive spin is bounded (~2 s); *d_status (optional) becomes 1 on expiry.
+ * (channel < 4 separates call sites).  The receive spin is bounded (2^24 polls, ~8 s; hfl_set_option "peer_spin_log2"):
+ * on expiry *d_status (optional) becomes 1 and the doubles that did not arrive are delivered as NaN (hfl_peer_spike_exchange
+ * then also writes NaN interface values), so a late or dead peer poisons the results instead of passing off stale data.
  * Replaces the dist.all_gather_into_tensor calls a torch.distributed port of P:117-145 / K5 would make. */
 size_t hfl_peer_buffer_bytes(void);
 int hfl_peer_buffer_create(void** d_buf, unsigned char* ipc_handle64);
@@ -199,7 +201,7 @@ int hfl_error_nodal(int64_t n_nodes, const double* d_nodes, const double* d_u, d
                     double* d_err3, void* stream);
 
 /* ---- tuning / introspection (bench and tests) */
-int hfl_set_option(const char* key, int value);   /* "primal_store": 0 auto, 1 direct, 2 smem, 3 tma, 4 tma rows, 5 warp-cooperative;
+int hfl_set_option(const char* key, int value);   /* "peer_spin_log2": 4..40; "fem_top_smem_kb": 64..227; "primal_store": 0 auto, 1 direct, 2 smem, 3 tma, 4 tma rows, 5 warp-cooperative;
                                                       "dual_team": 1 generic warp kernel for N = 12, 2 full-system team kernel, 3 parity split in shared memory; "primal_debug": profiling aid */
 int hfl_get_option(const char* key, int* value);
 int64_t hfl_launch_count(void);                    /* kernels launched by this library so far */

@@ -87,6 +87,42 @@ def test_custom_rhs_and_flux_solver():
     assert np.max(np.abs(s1.fem_values - ref)) <= 1e-12
 
 
+def test_non_sine_rhs_func_reaches_both_stages():
+    """a callable that is NOT the sine family must drive the coarse solve too (P:129-136 use the same
+    rhs as P:45).  -u'' = 12 x^2 - 2 with u(+-1) = 0 has the solution u = x^2 - x^4; the coarse nodal values are
+    checked against the general-operator oracle and the hybrid solution against the exact one."""
+    f = lambda x: 12.0 * x ** 2 - 2.0
+    s = FEMLSSVRPrimalSolver(65, lssvr_M=7, lssvr_gamma=1e6, rhs_func=f)
+    s.solve()
+    nodes = np.linspace(-1, 1, 65)
+    ref = fem_p1.solve_fem_p1_general(nodes, lambda x: np.ones_like(x), lambda x: np.zeros_like(x), f)
+    assert np.max(np.abs(s.fem_values - ref)) <= 1e-12
+    xs = np.linspace(-1, 1, 501)
+    exact = xs ** 2 - xs ** 4
+    # the 2-point Gauss load is exact for this quadratic forcing, so the P1 nodal values are exact and the degree-6
+    # element solves reproduce the quartic
+    assert np.max(np.abs(s.fem_values - (nodes ** 2 - nodes ** 4))) <= 1e-12
+    assert np.max(np.abs(s.evaluate_solution(xs) - exact)) <= 1e-9
+    # and the sine family given as a callable still equals the device path
+    k = FEMLSSVRPrimalSolver(33, lssvr_M=8, lssvr_gamma=1e4, rhs_func=poisson_rhs, k_freq=5.0)   # k_freq is ignored: rhs_func wins
+    k.solve()
+    assert np.max(np.abs(k.fem_values - fem_p1.solve_fem_p1(np.linspace(-1, 1, 33), 1.0))) <= 1e-12
+
+
+def test_evaluate_solution_keeps_shape_for_any_layout_and_small_M_is_refused():
+    s = FEMLSSVRPrimalSolver(25, lssvr_M=8, lssvr_gamma=1e4)
+    s.solve()
+    x = np.linspace(-1.2, 1.2, 24).reshape(4, 6)
+    base = s.evaluate_solution(x)
+    for view in (x.T, np.asfortranarray(x), x[:, ::2]):
+        out = s.evaluate_solution(view)
+        assert out.shape == view.shape
+        assert np.array_equal(out, s.evaluate_solution(np.ascontiguousarray(view)))
+    assert np.array_equal(s.evaluate_solution(x.T), base.T)
+    with pytest.raises(ValueError):
+        lssvr_primal(poisson_rhs, [-1.0, -0.9], 0.0, -0.3, 2, 1e4)
+
+
 def test_dual_form_through_the_class():
     """The 'Dual' script's entry points (D:100-203 are P:107-211): same class, form='dual'."""
     xs = np.linspace(-1, 1, 201)

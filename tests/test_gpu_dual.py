@@ -12,12 +12,26 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
-def dual_tol(ref_dual_fine, ref_primal_fine):
-    """1e-10, or ten times what an FP64 LU solve of the same dual system loses against the primal
-    minimiser.  The dual formula w = A^T alpha + B^T beta cancels catastrophically when the collocation
-    residual e = alpha / gamma is large (under-resolved forcing, M = 5 at N = 128, random samples): that
-    loss belongs to the dual formulation in FP64, not to a particular solver."""
-    return max(TOL, 10.0 * rel(ref_dual_fine, ref_primal_fine))
+# Stated tolerances (relative to max |u| on the fine grid, against the primal KKT oracle, which tests/test_oracle.py pins
+# to the 80-digit mpmath solve at <= 1e-14).  The bar is 1e-10 (BASELINE.json north_star) except where the DUAL FORMULA
+# itself cannot deliver it in FP64: w = A^T alpha + B^T beta cancels when the collocation residual e = alpha / gamma is
+# large (under-resolved forcing, random samples, one element of width 2).  Those cases carry the fixed number below -
+# measured on B200, with the loss of an FP64 LU solve of the same dual system printed beside it for context - instead of a
+# tolerance derived from the oracle at run time.
+STATED = {
+    # N = 128, M = 5 (degree 4 against 128 collocation points, frequencies up to k = 64): measured 2.2e-9 at k = 64, 4.9e-10 at
+    # k = 48, <= 6.3e-11 below; an FP64 LU solve of the same 130 x 130 dual system loses 1.3e-9 / 2.2e-9 there
+    'large_system/M=5': 5e-9,
+    # N(0, 1) forcing samples at 12 points, M = 9: measured 3.0e-6; FP64 LU of the dual system: 1.6e-5
+    'samples/random': 1e-5,
+}
+
+
+def check_dual(case, achieved, lu_loss=None):
+    tol = STATED.get(case, TOL)
+    print('DUALTOL %-40s achieved %.3e  stated %.1e  fp64-LU-of-the-dual-system %s' %
+          (case, achieved, tol, 'n/a' if lu_loss is None else '%.3e' % lu_loss))
+    assert achieved <= tol, (case, achieved, tol)
 
 
 def _run_dual(nodes, u, M, gamma, N=12, F=32, k=1.0, samples=None, **kw):
@@ -53,7 +67,7 @@ def test_small_system_vs_oracles(E):
     fd, fp = kkt.evaluate_fine(ref_d, 32), kkt.evaluate_fine(ref_p, 32)
     if E >= 3:
         assert rel(fd, fp) <= 1e-12     # strong duality (oracle check); E = 1 is one element of width 2
-    assert rel(fine[sl], fp) <= dual_tol(fd, fp)
+    check_dual('small_system/E=%d' % E, rel(fine[sl], fp), rel(fd, fp))
 
 
 def test_dual_matches_primal_kernel_full_size():
@@ -95,7 +109,8 @@ def test_large_system_multi_rhs(M, team):
         fp = kkt.evaluate_fine(ref, F)
         sl = slice(0, 8)
         ref_d = dual.lssvr_dual_batch(nodes[:9], u[r][:9], sine_samples(nodes[:9], N, k).T.copy(), M, gamma)
-        assert rel(fine[r].cpu().numpy(), fp) <= dual_tol(kkt.evaluate_fine(ref_d, F), fp[sl]), (M, k)
+        check_dual('large_system/M=%d' % M if M == 5 else 'large_system/M=%d/k=%g/team=%d' % (M, k, team),
+                   rel(fine[r].cpu().numpy(), fp), rel(kkt.evaluate_fine(ref_d, F), fp[sl]))
     e = err3.cpu().numpy()
     assert np.all(e[:, 1] < 1e-6) and np.all(e[:, 2] == 0)
 
@@ -124,12 +139,12 @@ def test_parity_left_looking_sizes(N, M, scale):
         fp = kkt.evaluate_fine(ref, F)
         f_samp = sine_samples(nodes, N, 1.0).T.copy() if which == 0 else fs.T.copy()
         ref_d = dual.lssvr_dual_batch(nodes, u if which == 0 else ub, f_samp, M, gamma)
-        tol = dual_tol(kkt.evaluate_fine(ref_d, F), fp)
+        case = 'parity_left/%s/N=%d/M=%d/%s' % ('coarse' if scale == 1.0 else 'fine', N, M, 'sine' if which == 0 else 'samples')
         coef, fine, status = out[0][which]
         assert not status.any()
-        assert rel(fine, fp) <= tol, (N, M, scale, which, rel(fine, fp), tol)
+        check_dual(case, rel(fine, fp), rel(kkt.evaluate_fine(ref_d, F), fp))
         assert rel(kkt.evaluate_fine(coef, F), fine) <= 1e-13
-        assert rel(fine, out[3][which][1]) <= tol
+        check_dual(case, rel(out[3][which][1], fp))
 
 
 def test_samples_forcing_and_boundary_correction():
@@ -146,7 +161,7 @@ def test_samples_forcing_and_boundary_correction():
     ref_d = dual.lssvr_dual_batch(nodes, u, f.T.copy(), M, 1e4)
     assert not status.any()
     fp = kkt.evaluate_fine(ref, 32)
-    assert rel(fine, fp) <= dual_tol(kkt.evaluate_fine(ref_d, 32), fp)      # random samples: large residual
+    check_dual('samples/random', rel(fine, fp), rel(kkt.evaluate_fine(ref_d, 32), fp))      # random samples: large residual
     # smooth samples (a resolved forcing): the plain 1e-10 bar
     fs = np.exp(np.linspace(nodes[:-1], nodes[1:], N, axis=0))
     coef, fine, status = _run_dual(nodes, y, M, 1e4, samples=fs, bc2=bc2)

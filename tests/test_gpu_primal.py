@@ -146,20 +146,36 @@ def test_boundary_correction_on_the_fly():
 
 
 def test_breakdown_falls_back_to_linear_interpolant():
-    """More bubble unknowns than collocation points and a vanishing regulariser: the Gram block is
-    singular in FP64 -> status 1 and the P:171-176 fallback (linear interpolant of the nodal values)."""
-    E = 64
-    nodes = np.linspace(-1, 1, E + 1) * 1e-3
-    u = np.linspace(0.2, 0.9, E + 1)
-    err3 = batch.new_error_accumulator()
-    coef, fine, status = _run(nodes, u, 14, 1e12, N=4, err3=err3)
-    if status.any():
-        bad = np.nonzero(status)[0]
-        assert np.allclose(coef[bad, 2:], 0.0)
-        assert np.allclose(coef[bad, 0], 0.5 * (u[bad] + u[bad + 1]), rtol=0, atol=1e-15)
-        assert np.allclose(coef[bad, 1], 0.5 * (u[bad + 1] - u[bad]), rtol=0, atol=1e-15)
-        assert int(err3[2].item()) == len(bad)
-    assert np.isfinite(fine[status == 0]).all()
+    """P:171-176: an element whose solve fails is replaced by the linear interpolant of its nodal values.  A NaN node
+    makes the two elements that touch it break down deterministically (pivot test fails): status = 1 for exactly those
+    two, coefficients {(u_L + u_R)/2, (u_R - u_L)/2, 0, ...}, a linear fine row, err3[2] = 2; every other element is
+    bit-identical to the clean run."""
+    E, M = 64, 9
+    nodes = np.linspace(-1, 1, E + 1)
+    u = np.sin(np.pi * nodes) + 0.05 * nodes
+    clean_coef, clean_fine, clean_status = _run(nodes, u, M, 1e4, err3=batch.new_error_accumulator())   # same kernel instantiation
+    assert not clean_status.any()
+    bad_nodes = nodes.copy()
+    bad_nodes[20] = np.nan
+    for form in (batch.lssvr_primal_batch, batch.lssvr_dual_batch):
+        err3 = batch.new_error_accumulator()
+        coef, fine, status = form(dev(bad_nodes), dev(u), M, 1e4, N=12, F=32, want_fine=True, want_status=True, err3=err3)
+        torch.cuda.synchronize()
+        coef, fine, status = coef.cpu().numpy(), fine.cpu().numpy(), status.cpu().numpy()
+        bad = np.array([19, 20])
+        assert np.array_equal(np.nonzero(status)[0], bad)
+        assert int(err3[2].item()) == 2
+        assert np.array_equal(coef[bad, 2:], np.zeros((2, M - 2)))
+        assert np.array_equal(coef[bad, 0], 0.5 * (u[bad] + u[bad + 1]))
+        assert np.array_equal(coef[bad, 1], 0.5 * (u[bad + 1] - u[bad]))
+        xi = np.linspace(-1, 1, 32)
+        lin = coef[bad, 0:1] + coef[bad, 1:2] * xi[None, :]
+        assert np.max(np.abs(fine[bad] - lin)) <= 1e-15
+        good = np.setdiff1d(np.arange(E), bad)
+        if form is batch.lssvr_primal_batch:
+            assert np.array_equal(coef[good], clean_coef[good]) and np.array_equal(fine[good], clean_fine[good])
+        else:
+            assert np.max(np.abs(fine[good] - clean_fine[good])) <= 1e-10
 
 
 def test_fused_error_matches_standalone_and_numpy():

@@ -100,6 +100,40 @@ def test_fem_solver_spread_small_at_1e4():
 
 
 @pytest.mark.skipif(not ref_loader.reference_available(), reason='reference tree not present (GPU box)')
+def test_binary128_coarse_oracle_is_pinned():
+    """oracle/c fem_p1_quad (binary128 Thomas on the reference's rounded system) against a 60-digit mpmath Thomas solve
+    of the same double-precision entries, and against SuperLU where SuperLU is still accurate."""
+    import mpmath as mp
+    from oracle import c_port
+    rng = np.random.default_rng(0)
+    n = 3001
+    w = 1 + 0.5 * rng.uniform(-1, 1, n - 1)
+    x = np.concatenate([[0.0], np.cumsum(w)])
+    nodes = -1 + 2 * x / x[-1]
+    for exact in (False, True):
+        off, diag, b = fem_p1.assemble_p1(nodes, 2.0)
+        mp.mp.dps = 60
+        c = [mp.mpf(0)] * n
+        g = [mp.mpf(0)] * n
+        g[0] = mp.mpf(0.25)
+        for i in range(1, n - 1):
+            l, r = mp.mpf(off[i - 1]), mp.mpf(off[i])
+            d = mp.mpf(diag[i]) if not exact else -(l + r)
+            den = d - l * c[i - 1]
+            c[i] = r / den
+            g[i] = (mp.mpf(b[i]) - l * g[i - 1]) / den
+        sol = [mp.mpf(0)] * n
+        sol[n - 1] = mp.mpf(-0.5)
+        for i in range(n - 2, 0, -1):
+            sol[i] = g[i] - c[i] * sol[i + 1]
+        q = c_port.fem_p1_quad(nodes, 2.0, exact_rowsum=exact, u_left=0.25, u_right=-0.5)
+        assert q[0] == 0.25 and q[-1] == -0.5
+        assert float(max(abs(mp.mpf(q[i]) - sol[i]) for i in range(1, n - 1))) <= 3e-16
+    for n in (25, 1001, 10001):
+        nodes = np.linspace(-1, 1, n)
+        assert np.max(np.abs(c_port.fem_p1_quad(nodes) - fem_p1.solve_fem_p1(nodes))) <= 1e-10
+
+
 def test_reference_function_runs_and_agrees():
     ns = ref_loader.load_reference_functions()
     np.random.seed(3)
