@@ -27,6 +27,17 @@ METRIC = 'element_lssvr_solves_per_s'
 UNIT = 'element solves/s'
 M, NCOL, F, GAMMA, KFREQ = 9, 12, 32, 1e4, 1.0
 BYTES_PER_ELEMENT = 8 + 8 + 8 * F          # node + nodal value + fine row: 272 B
+BYTES_PER_NODE_K1 = 27                     # K1: node read twice + u written + 3 B of head rows
+
+
+def workload_config(elements, world, coarse, error, exchange=None, store=0):
+    """The `config` object, identical for the GPU arm and the reference arm (the driver compares them)."""
+    return {'workload': 'BASELINE configs[2]: primal LSSVR, %d elements/GPU, M=9 (degree 8), N=12, F=32, uniform mesh on '
+                        '[-1,1], forcing pi^2 sin(pi x); step = K1 coarse P1 solve + K2/K3 element solves with fine grid + '
+                        'K5 error norms' % elements,
+            'elements_per_gpu': elements, 'elements_total': elements * world, 'M': M, 'N_colloc': NCOL, 'F': F, 'gamma': GAMMA,
+            'parallelism': 'contiguous element ranges x%d' % world,
+            'l2_policy': 'inputs (160 MB) + outputs (2.56 GB) per step exceed the 126 MB L2; no explicit flush'}
 
 
 def parse_args():
@@ -190,7 +201,135 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+def time_kernel(fn, reps):
+    """Average CUDA-event duration of `reps` back-to-back launches on torch's current stream (after one warm-up)."""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def time_kernel_each(fn, reps):
+    """Per-launch CUDA-event durations (best, median), launches back to back on the current stream."""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[0], ts[len(ts) // 2]
+
+
+def dual_config4_record(dev, fp64_tflops, reps):
+    """BASELINE configs[4]: dual form, N = 128 collocation points, R = 64 forcing frequencies sin(k pi x), k = 1..64, sharing
+    one factorisation per element, Legendre degree 4 / 12 / 24 (M = 5 / 13 / 25).  Per (E, M): kernel time, RHS solves/s,
+    the flops the rank-revealing left-looking kernel executes (formula below) as a fraction of the measured FP64 FMA rate,
+    the achieved error against the primal KKT oracle on a sample (stated, not asserted: SURVEY.md fact 8), and the CPU
+    port (oracle/dual.py, one LU solve per right-hand side) on a sample."""
+    import numpy as np
+    import torch
+    from hybrid_fem_lssvr_b200 import batch
+    from oracle import dual as odual, kkt
+    N, R, Fd = 128, 64, 32
+    ks_h = np.arange(1, R + 1, dtype=np.float64)
+    ks = torch.from_numpy(ks_h).to(dev)
+    rows = []
+    for Ed in (10 ** 4, 10 ** 5):
+        # elements of width 2e-6 around x = 0.3: k h <= 1.3e-4, every frequency resolved (the regime of the fine meshes)
+        nodes_h = 0.3 + np.linspace(-1.0, 1.0, Ed + 1) * (1e-6 * Ed)
+        nodes = torch.from_numpy(nodes_h).to(dev)
+        u = batch.fem_p1_solve_multi(batch.mesh_linspace(-1.0, 1.0, Ed + 1, device=dev), ks, coarse_solver='flux')   # timing of the 64 coarse solves
+        k1_ms = time_kernel(lambda: batch.fem_p1_solve_multi(batch.mesh_linspace(-1.0, 1.0, Ed + 1, device=dev), ks, coarse_solver='flux', out=u), 3)
+        un = torch.sin(math.pi * ks[:, None] * nodes[None, :]).contiguous()
+        for Md in (5, 13, 25):
+            run = lambda: batch.lssvr_dual_multi(nodes, un, ks, Md, GAMMA, N=N, F=Fd, want_coef=False, want_fine=True)   # noqa: E731
+            ms = time_kernel(run, max(3, reps // 4))
+            _, fine, _ = run()
+            # executed flops per element: two parity blocks of nh = 65 rows, numerical rank r_p = number of basis functions
+            # of that parity (tau is below eps |K| on this mesh): left-looking factorisation r_p^2 nh each; per right-hand
+            # side two triangular solves (2 r_p^2), w = C^T z (2 r_p^2) and the fine grid (2 M F)
+            r_e, r_o = (Md - 1) // 2 + 1, (Md - 2) // 2 + 1
+            fl_fact = (r_e ** 2 + r_o ** 2) * (N // 2 + 1)
+            fl_rhs = 4 * (r_e ** 2 + r_o ** 2) + 2 * Md * Fd
+            flops = (fl_fact + R * fl_rhs) * Ed
+            # achieved error on a sample: first 3 elements, 4 frequencies, against the primal KKT oracle
+            sl, rs = slice(0, 3), (0, 7, 31, 63)
+            worst = 0.0
+            for r in rs:
+                f = fem_forcing(np.linspace(nodes_h[:-1][sl], nodes_h[1:][sl], N, axis=0), ks_h[r]).T.copy()
+                ref = kkt.lssvr_primal_kkt_batch(nodes_h[:4], un[r, :4].cpu().numpy(), f, Md, GAMMA)
+                fp = kkt.evaluate_fine(ref, Fd)
+                worst = max(worst, float(np.max(np.abs(fine[r, sl].cpu().numpy() - fp)) / np.max(np.abs(fp))))
+            rows.append({'E': Ed, 'M': Md, 'kernel_ms': ms, 'rhs_solves_per_s': Ed * R / (ms * 1e-3),
+                         'executed_flops_per_element': fl_fact + R * fl_rhs,
+                         'roofline_frac_fp64_executed_flops': flops / (ms * 1e-3) / 1e12 / fp64_tflops,
+                         'achieved_rel_error_vs_primal_oracle_sample': worst, 'coarse_solves_64_rhs_ms': k1_ms})
+    # CPU port on a sample: 4 elements x 8 frequencies per M, one core
+    cpu = {}
+    nodes_h = 0.3 + np.linspace(-1.0, 1.0, 5) * 4e-6
+    for Md in (5, 13, 25):
+        t0 = time.perf_counter()
+        cnt = 0
+        for r in range(0, R, 8):
+            uu = np.sin(math.pi * ks_h[r] * nodes_h)
+            f = fem_forcing(np.linspace(nodes_h[:-1], nodes_h[1:], N, axis=0), ks_h[r]).T.copy()
+            odual.lssvr_dual_batch(nodes_h, uu, f, Md, GAMMA)
+            cnt += 4
+        cpu['M=%d' % Md] = cnt / (time.perf_counter() - t0)
+    return {'workload': 'BASELINE configs[4]: dual LSSVR, N=128, R=64 frequencies k=1..64, F=32, gamma=1e4, left-looking '
+                        'rank-revealing parity kernel (two 65 x 65 blocks per element)', 'rows': rows,
+            'cpu_port_rhs_solves_per_s_per_core': cpu,
+            'cpu_port_sample': '4 elements x 8 frequencies per M, oracle/dual.py (numpy LU of the 130 x 130 system per right-hand side), 1 core',
+            'fp64_fma_probe_tflops': fp64_tflops}
+
+
+def fem_forcing(x, k):
+    import numpy as np
+    return (k * np.pi) ** 2 * np.sin(k * np.pi * x)
+
+
+def raw_copy_probe(dev, world, nbytes=1 << 30):
+    """Concurrent cudaMemcpyAsync of `nbytes` per rank, pinned host <-> device, all ranks at once (barrier first):
+    the box's ceiling for the end-to-end pipeline.  Returns GB/s per GPU (D2H, H2D), max time over ranks."""
+    import torch
+    import torch.distributed as dist
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = []
+    for src, dst in ((d, h), (h, d)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([t], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = tt.item()
+            best = min(best, t)
+        out.append(nbytes / best / 1e9)
+    del h, d
+    return out[0], out[1]
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from hybrid_fem_lssvr_b200 import batch, _lib
@@ -205,6 +344,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     E = args.elements
     E_global = E * world
+    warmup = max(args.warmup, 3)
     batch.set_option('primal_store', args.store)
 
     nodes = hdist.local_nodes_linspace(-1.0, 1.0, E_global, world, rank, device=dev)
@@ -212,54 +352,62 @@ def run_ours(args):
     u = torch.empty(E + 1, dtype=torch.float64, device=dev)
     err3 = batch.new_error_accumulator(dev)
     nerr = batch.new_error_accumulator(dev)
-    results = {}
     err_all = torch.empty((world, 3), dtype=torch.float64, device=dev)
 
     exchange = None
     if world > 1 and args.exchange != 'nccl':
         try:
             exchange = hdist.PeerExchange(device=dev)
-        except Exception as exc:                      # no peer memory here: NCCL carries the two all-gathers
+        except Exception as exc:                      # no peer memory here: NCCL carries the interface all-gather
             if args.exchange == 'peer':
                 raise
             sys.stderr.write('bench: peer-memory exchange unavailable (%s); using NCCL\n' % exc)
-    # partitioned solve: same partition + PCR kernels on the unrounded diagonal (include/hfl.h, HFL_COARSE_ASSEMBLED_EXACT)
+    # partitioned solve: same kernels on the unrounded diagonal (include/hfl.h, HFL_COARSE_ASSEMBLED_EXACT): the interface
+    # system needs discrete harmonic functions to be linear, which the reference's rounded diagonal breaks at this size
     coarse_dist = 'assembled_exact' if args.coarse == 'assembled' else args.coarse
 
-    def step():
-        err3.zero_()
-        if world > 1:
-            _, bc2 = hdist.fem_p1_solve_distributed(nodes, k_freq=KFREQ, coarse_solver=coarse_dist, out=u, exchange=exchange)
-        else:
-            batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u)
-            bc2 = None
-        batch.lssvr_primal_batch(nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, bc2=bc2,
-                                 want_coef=False, want_fine=True, fine_out=fine,
-                                 err3=err3 if args.error == 'fused' else None)
-        if args.error == 'separate':
-            batch.error_fine(nodes, fine, KFREQ, err3)
-        if world > 1 and args.error != 'none':
-            results['err_gathered'] = hdist.gather_error(err3, out=err_all, exchange=exchange)     # stream-ordered, no host sync
+    def make_step(nodes_, u_, fine_, ex):
+        def step():
+            err3.zero_()
+            if world > 1:
+                _, bc2 = hdist.fem_p1_solve_distributed(nodes_, k_freq=KFREQ, coarse_solver=coarse_dist, out=u_, exchange=ex)
+            else:
+                batch.fem_p1_solve(nodes_, k_freq=KFREQ, coarse_solver=args.coarse, out=u_)
+                bc2 = None
+            batch.lssvr_primal_batch(nodes_, u_, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, bc2=bc2,
+                                     want_coef=False, want_fine=True, fine_out=fine_,
+                                     err3=err3 if args.error == 'fused' else None)
+            if args.error == 'separate':
+                batch.error_fine(nodes_, fine_, KFREQ, err3)
+            return bc2
+        return step
+
+    step = make_step(nodes, u, fine, exchange)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    if exchange is not None:       # a receive spin that expired on any rank: fall back to NCCL on all of them
+    def exchange_expired():
+        if exchange is None:
+            return False
         bad = exchange.status.to(torch.float64)
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if bad.item() > 0:
-            if args.exchange == 'peer':
-                raise RuntimeError('peer-memory exchange timed out')
-            sys.stderr.write('bench: peer-memory exchange timed out during warm-up; using NCCL\n')
-            exchange = None
-            for _ in range(max(args.warmup, 3)):
-                step()
-            barrier()
+        return bad.item() > 0
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    if exchange_expired():       # a receive spin that expired on any rank: fall back to NCCL on all of them
+        if args.exchange == 'peer':
+            raise RuntimeError('peer-memory exchange timed out')
+        sys.stderr.write('bench: peer-memory exchange timed out during warm-up; using NCCL\n')
+        exchange = None
+        step = make_step(nodes, u, fine, None)
+        for _ in range(warmup):
+            step()
+        barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -270,7 +418,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        step()
+        bc2_last = step()
     ev1.record()
     barrier()
     t1 = time.perf_counter()
@@ -280,47 +428,32 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
+    if exchange_expired():       # a late peer during the timed steps poisons bc2 / the norms with NaN: refuse the record
+        raise RuntimeError('peer-memory exchange timed out during the timed steps; rerun with --exchange nccl')
     ms_per_step = ms / args.steps
     value = E_global * args.steps / (ms * 1e-3)
+    # the error norms of the last step: one gather after the loop (stream-ordered), not one per step
+    if world > 1 and args.error != 'none':
+        gathered = hdist.gather_error(err3, out=err_all, exchange=exchange)
+    else:
+        gathered = None
 
-    # ---- per-kernel timing of the dominant kernel (K2+K3, same launch as in the step), CUDA events
-    def time_kernel(fn, reps):
-        fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
-
-    def time_kernel_each(fn, reps):
-        """Per-launch CUDA-event durations (best, median), launches back to back on the current stream."""
-        fn()
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in evs:
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b) for a, b in evs)
-        return ts[0], ts[len(ts) // 2]
-
+    # ---- per-kernel timing (same launches as in the step), CUDA events on the launching stream
     reps = max(5, min(args.steps, 20))
-    k2_ms = time_kernel(lambda: batch.lssvr_primal_batch(
-        nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False, want_fine=True, fine_out=fine,
-        err3=err3 if args.error == 'fused' else None), reps)
-    k2_best, k2_median = time_kernel_each(lambda: batch.lssvr_primal_batch(
-        nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False, want_fine=True, fine_out=fine,
-        err3=err3 if args.error == 'fused' else None), max(10, reps))
-    k1_ms = time_kernel(lambda: batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u), reps)
-    k1_other = 'flux' if args.coarse == 'assembled' else 'assembled'
+
+    def k2(with_err):
+        return lambda: batch.lssvr_primal_batch(nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False,
+                                                want_fine=True, fine_out=fine, err3=err3 if with_err else None)
+    fused = args.error == 'fused'
+    k2_ms = time_kernel(k2(fused), reps)
+    k2_best, k2_median = time_kernel_each(k2(fused), max(10, reps))
+    k1_mode = args.coarse if world == 1 else coarse_dist
+    k1_ms = time_kernel(lambda: batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=k1_mode, out=u), reps)
+    k1_best, k1_median = time_kernel_each(lambda: batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=k1_mode, out=u), max(10, reps))
+    k1_other = 'flux' if k1_mode != 'flux' else 'assembled'
     k1_other_ms = time_kernel(lambda: batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=k1_other, out=u), reps)
-    batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=args.coarse, out=u)
-    k2_plain_ms = time_kernel(lambda: batch.lssvr_primal_batch(
-        nodes, u, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False, want_fine=True, fine_out=fine), reps)
+    batch.fem_p1_solve(nodes, k_freq=KFREQ, coarse_solver=k1_mode, out=u)
+    k2_plain_ms = time_kernel(k2(False), reps)
     k5_ms = time_kernel(lambda: batch.error_fine(nodes, fine, KFREQ, nerr), max(3, reps // 2))
     # clocks / throttle reasons sampled from just before the timed steps to the end of the per-kernel timing loops
     clocks = sampler.stop(t0, time.perf_counter()) if rank == 0 else None
@@ -331,39 +464,75 @@ def run_ours(args):
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             tj = json.load(fh)
         if E == tj.get('elements'):
-            traffic = tj['lssvr_element_kernel_fused_err' if args.error == 'fused' else 'lssvr_element_kernel']
+            traffic = tj['lssvr_element_kernel_fused_err' if fused else 'lssvr_element_kernel']
     except Exception:
         pass
 
     # ---- error norms of the last step (reported, not timed)
+    step()                                  # per-kernel timing loops overwrote u; restore the step's state
+    torch.cuda.synchronize()
     if world == 1:
         l2, mx = batch.finish_error(err3) if args.error != 'none' else (None, None)
     else:
-        l2, mx = hdist.finish_gathered_error(results['err_gathered'])[:2] if 'err_gathered' in results else (None, None)
+        gathered = hdist.gather_error(err3, out=err_all, exchange=exchange) if args.error != 'none' else None
+        l2, mx = hdist.finish_gathered_error(gathered, exchange=exchange)[:2] if gathered is not None else (None, None)
     nerr.zero_()
     if world == 1:
         nl2, nmx = batch.finish_error(batch.error_nodal(nodes, u, KFREQ, nerr))
     else:
         nl2 = nmx = None
 
-    # ---- BASELINE configs[1]: dual LSSVR, 1e6 elements, degree 8 (reported beside the headline, not part of the step)
-    dual = None
-    if rank == 0:
-        Ed = 10 ** 6
-        nd = batch.mesh_linspace(-1.0, 1.0, Ed + 1, device=dev)
-        ud = batch.fem_p1_solve(nd, k_freq=KFREQ, coarse_solver='flux')
-        fd = fine[:Ed]
-        derr = batch.new_error_accumulator(dev)
-        dms = time_kernel(lambda: batch.lssvr_dual_batch(nd, ud, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ,
-                                                         want_coef=False, want_fine=True, fine_out=fd), reps)
-        derr.zero_()
-        batch.lssvr_dual_batch(nd, ud, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False,
-                               want_fine=True, fine_out=fd, err3=derr)
-        dl2, dmx = batch.finish_error(derr)
-        dual = {'workload': 'BASELINE configs[1]: dual LSSVR (parity-split 7x7 blocks, pivot-skipping LDL^T), 1e6 elements, '
-                            'M=9, N=12, F=32, flux coarse solve', 'kernel_ms': dms,
-                'element_solves_per_s': Ed / (dms * 1e-3), 'roofline_frac_hbm': BYTES_PER_ELEMENT * Ed / (dms * 1e-3) / 1e9 / measured_peaks()[0],
-                'fine_l2_vs_sin': dl2, 'fine_max_vs_sin': dmx}
+    # ---- N > 1: parity of the partitioned path with the single-GPU path (every rank solves the whole coarse problem by
+    # itself with the single-GPU kernels and compares its own slice; a sample of its elements goes through the
+    # single-GPU element launch with those nodal values)
+    parity = None
+    strong = None
+    if world > 1:
+        e0, _ = hdist.partition(E_global, world, rank)
+        ng = batch.mesh_linspace(-1.0, 1.0, E_global + 1, device=dev)
+        ug = batch.fem_p1_solve(ng, k_freq=KFREQ, coarse_solver=coarse_dist)
+        bc2 = bc2_last
+        ul = batch.fem_apply_bc(nodes, u.clone(), float(bc2[0].item()), float(bc2[1].item()))
+        d_nodal = (ul - ug[e0:e0 + E + 1]).abs().max()
+        Es = min(E, 1 << 16)
+        _, fs, _ = batch.lssvr_primal_batch(ng[e0:e0 + Es + 1].contiguous(), ug[e0:e0 + Es + 1].contiguous(), M, GAMMA, N=NCOL, F=F,
+                                            forcing='sine', k_freq=KFREQ, want_coef=False, want_fine=True)
+        d_fine = (fs - fine[:Es]).abs().max()
+        dd = torch.stack([d_nodal, d_fine])
+        dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+        parity = {'what': 'partitioned path (local solves + interface exchange + on-the-fly linear correction) against the '
+                          'single-GPU kernels on the whole %d-element mesh, every rank checking its own slice' % E_global,
+                  'nodal_max_abs_diff': dd[0].item(), 'fine_max_abs_diff_sample': dd[1].item(), 'fine_sample_elements_per_rank': Es}
+        del ng, ug, ul, fs
+        torch.cuda.empty_cache()
+
+        # ---- BASELINE configs[3]: 1e8 elements in total, split over the ranks (strong scaling)
+        E3 = 10 ** 8
+        e30, e31 = hdist.partition(E3, world, rank)
+        El = e31 - e30
+        n3 = hdist.local_nodes_linspace(-1.0, 1.0, E3, world, rank, device=dev)
+        f3 = torch.empty((El, F), dtype=torch.float64, device=dev)
+        u3 = torch.empty(El + 1, dtype=torch.float64, device=dev)
+        step3 = make_step(n3, u3, f3, exchange)
+        for _ in range(3):
+            step3()
+        barrier()
+        a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a3.record()
+        for _ in range(5):
+            step3()
+        b3.record()
+        barrier()
+        t3 = torch.tensor([a3.elapsed_time(b3) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        g3 = hdist.gather_error(err3, out=err_all, exchange=exchange)
+        l23, mx3 = hdist.finish_gathered_error(g3, exchange=exchange)[:2]
+        strong = {'workload': 'BASELINE configs[3]: 1e8 elements in total, contiguous ranges over %d GPUs, partitioned coarse '
+                              'solve + interface exchange + NVLink/NCCL error reduction' % world,
+                  'elements_per_gpu': El, 'ms_per_step': t3.item(), 'element_solves_per_s': E3 / (t3.item() * 1e-3),
+                  'fine_l2_vs_sin': l23, 'fine_max_vs_sin': mx3, 'steps': 5, 'warmup': 3}
+        del n3, f3, u3
+        torch.cuda.empty_cache()
 
     # ---- FP64 FMA probe (no FP64 figure in MEASURED_PEAKS.json)
     fp64_tflops = None
@@ -377,12 +546,37 @@ def run_ours(args):
             _lib.check(lib.hfl_fp64_probe(148 * 8, 4096, batch._ptr(probe_out), C.byref(flops), batch._stream()), 'probe')
         pm = time_kernel(probe, 5)
         fp64_tflops = flops.value / (pm * 1e-3) / 1e12
-        if dual is not None:
-            # SURVEY.md section 8d puts the dual row on the FP64 roofline.  Flops per element: 2.3e3 for the full 14 x 14
-            # system it counts; the parity-split kernel executes ~1.3e3 (two 7 x 7 blocks): both fractions are given,
-            # against the FP64 FMA rate measured by the probe above.
-            for key, fl in (('roofline_frac_fp64_survey_flops', 2.3e3), ('roofline_frac_fp64_executed_flops', 1.3e3)):
-                dual[key] = fl * 1e6 / (dual['kernel_ms'] * 1e-3) / 1e12 / fp64_tflops
+
+    # ---- BASELINE configs[1]: dual LSSVR, 1e6 elements, degree 8 (reported beside the headline, not part of the step)
+    dual = None
+    dual4 = None
+    if rank == 0 and world == 1:
+        Ed = 10 ** 6
+        nd = batch.mesh_linspace(-1.0, 1.0, Ed + 1, device=dev)
+        ud = batch.fem_p1_solve(nd, k_freq=KFREQ, coarse_solver='flux')
+        fd = fine[:Ed]
+        derr = batch.new_error_accumulator(dev)
+        dms = time_kernel(lambda: batch.lssvr_dual_batch(nd, ud, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ,
+                                                         want_coef=False, want_fine=True, fine_out=fd), reps)
+        derr.zero_()
+        batch.lssvr_dual_batch(nd, ud, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False,
+                               want_fine=True, fine_out=fd, err3=derr)
+        dl2, dmx = batch.finish_error(derr)
+        _, fpr, _ = batch.lssvr_primal_batch(nd, ud, M, GAMMA, N=NCOL, F=F, forcing='sine', k_freq=KFREQ, want_coef=False, want_fine=True)
+        dual = {'workload': 'BASELINE configs[1]: dual LSSVR (parity-split 7x7 blocks, pivot-skipping LDL^T), 1e6 elements, '
+                            'M=9, N=12, F=32, flux coarse solve', 'kernel_ms': dms,
+                'element_solves_per_s': Ed / (dms * 1e-3),
+                'roofline': {'bound': 'hbm', 'achieved': BYTES_PER_ELEMENT * Ed / (dms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                             'frac': BYTES_PER_ELEMENT * Ed / (dms * 1e-3) / 1e9 / peak,
+                             'note': 'executed intensity ~4.8 flop/B is below the machine balance (5.6): the bound is HBM'},
+                'fp64_frac_executed_flops': 1.3e3 * Ed / (dms * 1e-3) / 1e12 / fp64_tflops,
+                'dual_vs_primal_kernel_max_abs': (fpr - fd).abs().max().item(),
+                'fine_l2_vs_sin': dl2, 'fine_max_vs_sin': dmx}
+        del fpr
+        try:
+            dual4 = dual_config4_record(dev, fp64_tflops, reps)
+        except Exception as exc:     # the sub-record must not cost the headline line
+            dual4 = {'error': '%s: %s' % (type(exc).__name__, exc)}
 
     # ---- end to end through the host-buffer API (pinned host mesh in, fine grid + norms out)
     e2e = None
@@ -404,58 +598,83 @@ def run_ours(args):
             t = torch.tensor([te], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             te = t.item()
+        d2h = runner.d2h_bytes
         e2e = {'value': E_global / te, 'unit': UNIT, 'h2d_bytes_per_step': runner.h2d_bytes,
-               'd2h_bytes_per_step': runner.d2h_bytes, 'ms_per_step': te * 1e3,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': te * 1e3, 'd2h_gbs_per_gpu': d2h / te / 1e9,
                'note': 'pinned host nodes -> H2D -> K1 -> K2/K3/K5 in element chunks -> D2H of the whole fine grid '
                        '+ error norms, copies overlapped with compute on two streams; wall clock with device sync'}
         del runner
+        torch.cuda.empty_cache()
+        # what the box itself allows: the same bytes through bare cudaMemcpyAsync, all ranks at once
+        raw_d2h, raw_h2d = raw_copy_probe(dev, world)
+        e2e['raw_d2h_gbs_per_gpu'] = raw_d2h
+        e2e['raw_h2d_gbs_per_gpu'] = raw_h2d
+        e2e['pipeline_fraction_of_raw_d2h'] = e2e['d2h_gbs_per_gpu'] / raw_d2h
+        e2e['raw_probe'] = ('1 GiB per rank, pinned host <-> device, cudaMemcpyAsync on every rank at once after a barrier, '
+                            'best of 3, max over ranks')
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:     # timed on rank 0 at N = 1 only
-        cpu = cpu_baseline_record(args.cpu_sample, steps=6)
+        cpu = cpu_baseline_record(args.cpu_sample, steps=6, warmup=1)
 
     if rank == 0:
+        cfg = workload_config(E, world, args.coarse, args.error)       # identical in the reference arm
+        run_info = {'coarse_solver': (args.coarse if world == 1 else coarse_dist + ' + SPIKE interface exchange'),
+                    'error_norms': args.error, 'store_path': args.store,
+                    'exchange': ('none (single GPU)' if world == 1 else
+                                 'NVLink peer-memory exchange fused with the interface solve (hfl_peer_spike_exchange)'
+                                 if exchange is not None else 'NCCL all-gather')}
+        step_bytes = (BYTES_PER_ELEMENT + 16) * E       # + K1: node read once more and u written
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE configs[2]: primal LSSVR, %d elements/GPU, M=9 (degree 8), N=12, F=32, '
-                                   'uniform mesh on [-1,1], forcing pi^2 sin(pi x) on device; step = K1 coarse solve '
-                                   '(%s) + K2/K3 element solves with fine grid + K5 error norms (%s)'
-                                   % (E, args.coarse if world == 1 else coarse_dist + ' + SPIKE interface exchange', args.error),
-                       'elements_per_gpu': E, 'elements_total': E_global, 'M': M, 'N_colloc': NCOL, 'F': F, 'gamma': GAMMA,
-                       'parallelism': 'contiguous element ranges x%d' % world,
-                       'exchange': ('none (single GPU)' if world == 1 else
-                                    'NVLink peer-memory all-gather (hfl_peer_allgather)' if exchange is not None else 'NCCL all-gather'),
-                       'l2_policy': 'inputs (160 MB) + outputs (2.56 GB) per step exceed the 126 MB L2; no explicit flush',
-                       'store_path': args.store},
+            'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': cfg,
+            'run': run_info,
             'fine_points_per_s': value * F,
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'kernel': 'lssvr_element_kernel<M=9,FH=16,ERR=%s> (K2+K3%s)'
-                         % ('true' if args.error == 'fused' else 'false', '+K5' if args.error == 'fused' else ''),
+                         % ('true' if fused else 'false', '+K5' if fused else ''),
                          'algorithmic_bytes_per_element': BYTES_PER_ELEMENT, 'kernel_ms': k2_ms,
                          'kernel_ms_best': k2_best, 'kernel_ms_median': k2_median, 'peak_source': peak_src},
-            'kernels_ms': {'K1_coarse_solve_' + args.coarse: k1_ms, 'K1_coarse_solve_' + k1_other: k1_other_ms, 'K2K3_primal_fine' + ('_K5' if args.error == 'fused' else ''): k2_ms,
+            'roofline_k1': {'bound': 'hbm (FP64-pipe co-limited, see profiles/)', 'kernels': 'fem_chunk_reduce + fem_heads_reduce + fem_top + fem_heads_backsub + fem_chunk_backsub',
+                            'mode': k1_mode, 'algorithmic_bytes_per_node': BYTES_PER_NODE_K1, 'kernel_ms': k1_ms, 'kernel_ms_best': k1_best,
+                            'kernel_ms_median': k1_median, 'achieved': BYTES_PER_NODE_K1 * (E + 1) / (k1_ms * 1e-3) / 1e9,
+                            'peak': peak, 'unit': 'GB/s', 'frac': BYTES_PER_NODE_K1 * (E + 1) / (k1_ms * 1e-3) / 1e9 / peak},
+            'roofline_step': {'bound': 'hbm', 'algorithmic_bytes_per_element': BYTES_PER_ELEMENT + 16,
+                              'achieved': step_bytes / (ms_per_step * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                              'frac': step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+            'kernels_ms': {'K1_coarse_solve_' + k1_mode: k1_ms, 'K1_coarse_solve_' + k1_other: k1_other_ms,
+                           'K2K3_primal_fine' + ('_K5' if fused else ''): k2_ms,
                            'K2K3_primal_fine_no_error': k2_plain_ms, 'K5_error_fine_standalone': k5_ms},
             'fp64_fma_probe_tflops': fp64_tflops,
             'errors_vs_sin': {'fine_l2': l2, 'fine_max': mx, 'nodal_l2': nl2, 'nodal_max': nmx},
             'dual_config1': dual,
+            'dual_config4': dual4,
             'e2e': e2e,
             'cpu_baseline': cpu,
         }
+        if world > 1:
+            line['scaling_note'] = ('N = 1 solves the reference\'s rounded coarse system (assembled); N > 1 solves it with the '
+                                    'unrounded diagonal (assembled_exact, same kernels and cost) because the interface system '
+                                    'needs zero row sums; weak scaling, %d elements per GPU' % E)
+            line['parity_vs_single_gpu'] = parity
+            line['config3_strong'] = strong
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline_record(sample_arg, steps):
+def cpu_baseline_record(sample_arg, steps, warmup=1):
     """cpu_baseline object: the C / OpenMP port when it builds, else the numpy port; both are restatements
     (kind "port").  Also times the numpy port and the reference's own SLSQP formulation on small samples."""
     rec = None
     try:
         sample = sample_arg or 10_000_000      # the whole headline workload; ~1-3 s per pass on a 16+ thread host
+        for _ in range(max(0, warmup - 1)):    # run_cpu_baseline_c does one small warm-up pass itself
+            run_cpu_baseline_c(sample, steps=1)
         v, cores, cmx, times = run_cpu_baseline_c(sample, steps=steps)
         rec = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                'sample': '%d elements of the same uniform mesh family (M=9, N=12, F=32) per pass, %d passes: C/OpenMP '
@@ -477,6 +696,11 @@ def cpu_baseline_record(sample_arg, steps):
     s = cpu_slsqp_sample()
     if s is not None:
         rec['reference_formulation_slsqp_solves_per_s_per_core'] = s
+    try:     # the reference's own function, timed in the build container (tests/golden/make_golden.py --time)
+        with open(os.path.join(ROOT, 'profiles', 'r02_reference_as_is.json')) as fh:
+            rec['reference_as_is_build_container'] = json.load(fh)
+    except Exception:
+        pass
     return rec
 
 
@@ -486,18 +710,20 @@ def run_reference(args):
         return
     t0 = time.perf_counter()
     steps = max(1, args.steps)
-    rec = cpu_baseline_record(args.cpu_sample, steps=steps)
+    warmup = max(args.warmup, 3)
+    rec = cpu_baseline_record(args.cpu_sample, steps=steps, warmup=warmup)
     v = rec['value']
     sample = int(rec['sample'].split()[0])
     ms = 1e3 * sample / v
     rec['note'] = ('oracle port: restatement of P:20-105 (closed-form KKT) and P:117-145; the reference scripts themselves '
                    'cannot travel to the GPU box (no scikit-fem) and their SLSQP element solve runs at ~3-15 solves/s/core '
-                   '(BASELINE.md)')
+                   '(BASELINE.md).  Every step is a bounded sample of the workload: %d elements on the host cores whatever '
+                   '--gpus is' % sample)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
-        'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[2] on the host CPU, bounded sample: ' + rec['sample']},
+        'config': workload_config(args.elements, args.gpus, args.coarse, args.error),
         'cpu_baseline': rec,
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': time.perf_counter() - t0,
