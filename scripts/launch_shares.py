@@ -13,7 +13,7 @@ print('# per-kernel device time from %s (ncu, cold-cache, serialised: compare SH
 print('# kernel, launches, mean us, share of all captured launches')
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     print('%-75s %4d %10.1f %6.1f%%' % (k[:75], len(v), sum(v) / len(v), 100.0 * sum(v) / tot))
-step = [(k, sum(v) / len(v)) for k, v in agg.items() if re.search(r'fem_reduce|fem_top|fem_backsub', k)]
+step = [(k, sum(v) / len(v)) for k, v in agg.items() if re.search(r'fem_reduce|fem_top|fem_backsub|fem_chunk_|fem_heads_', k)]
 k2 = [(k, sum(v) / len(v), len(v)) for k, v in agg.items() if 'lssvr_element_kernel' in k]
 if step and k2:
     main = max(k2, key=lambda x: x[2])
