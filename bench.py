@@ -578,6 +578,33 @@ def run_ours(args):
         except Exception as exc:     # the sub-record must not cost the headline line
             dual4 = {'error': '%s: %s' % (type(exc).__name__, exc)}
 
+    # ---- general operator -(a u')' + c u = f, manufactured solution u = sin(pi x), a = 1 + x/2,
+    # c = 2 + cos x, coefficient / forcing samples streamed from HBM (656 B per element)
+    general = None
+    if rank == 0 and world == 1:
+        try:
+            xg = nodes[:-1].unsqueeze(0) + (nodes[1:] - nodes[:-1]).unsqueeze(0) * torch.linspace(0, 1, NCOL, dtype=torch.float64, device=dev).unsqueeze(1)
+            ag = (1.0 + 0.5 * xg).contiguous(); dag = torch.full_like(xg, 0.5); cg = (2.0 + torch.cos(xg)).contiguous()
+            fg = (-(dag * (math.pi * torch.cos(math.pi * xg)) - ag * (math.pi ** 2) * torch.sin(math.pi * xg)) + cg * torch.sin(math.pi * xg)).contiguous()
+            del xg
+            ug = torch.sin(math.pi * nodes)
+            run_g = lambda: batch.lssvr_general_batch(nodes, ug, ag, fg, M, GAMMA, N=NCOL, F=F, da=dag, c=cg, want_coef=False, want_fine=True)   # noqa: E731
+            gms = time_kernel(run_g, max(3, reps // 4))
+            _, fgo, _ = run_g()
+            xs = nodes[:-1].unsqueeze(1) + (nodes[1:] - nodes[:-1]).unsqueeze(1) * torch.linspace(0, 1, F, dtype=torch.float64, device=dev)
+            gerr = (fgo - torch.sin(math.pi * xs)).abs().max().item()
+            gbytes = 8 + 8 + 8 * F + 4 * 8 * NCOL
+            general = {'workload': 'general operator -(a u\')\' + c u = f (SURVEY.md 8f-2), %d elements, M=9, N=12, F=32, exact nodal '
+                                   'values, a / a\' / c / f samples [N][E] read from HBM' % E,
+                       'kernel_ms': gms, 'element_solves_per_s': E / (gms * 1e-3), 'algorithmic_bytes_per_element': gbytes,
+                       'roofline': {'bound': 'hbm', 'achieved': gbytes * E / (gms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                    'frac': gbytes * E / (gms * 1e-3) / 1e9 / peak},
+                       'fine_max_vs_manufactured_solution': gerr}
+            del ag, dag, cg, fg, ug, fgo, xs
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            general = {'error': '%s: %s' % (type(exc).__name__, exc)}
+
     # ---- end to end through the host-buffer API (pinned host mesh in, fine grid + norms out)
     e2e = None
     if not args.no_e2e:
@@ -653,6 +680,7 @@ def run_ours(args):
             'errors_vs_sin': {'fine_l2': l2, 'fine_max': mx, 'nodal_l2': nl2, 'nodal_max': nmx},
             'dual_config1': dual,
             'dual_config4': dual4,
+            'general_operator': general,
             'e2e': e2e,
             'cpu_baseline': cpu,
         }

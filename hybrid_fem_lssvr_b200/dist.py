@@ -216,3 +216,90 @@ def reduce_error(err3, group=None):
     else:
         vals = err3.tolist()
     return math.sqrt(vals[0]), vals[1], int(vals[2])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# General operator -(a u')' + c u = f on a mesh split into contiguous ranges.  Discrete
+# homogeneous solutions are no longer linear, so every rank solves its range three times with the same matrix: y (the
+# load, zero Dirichlet data), v (no load, u = 1 at its left end), w (no load, u = 1 at its right end); u = y + U_r v +
+# U_{r+1} w for the interface values U.  At every interface the residuals of the two neighbouring end nodes must cancel:
+# a tridiagonal system in U_1 .. U_{G-1} built from six end-node residuals per rank (one all-gather of 6 doubles).
+
+def _general_end_residuals(nodes, z, aq, cq, fq, with_load):
+    """(r_left, r_right): residual of the un-enforced P1 rows of the two end nodes for the nodal vector z; host scalars."""
+    x = torch.stack([nodes[0], nodes[1], nodes[-2], nodes[-1]]).tolist()
+    zz = torch.stack([z[0], z[1], z[-2], z[-1]]).tolist()
+    E = nodes.numel() - 1
+    g0, g1 = batch.GAUSS_X
+    out = []
+    for side, e in ((0, 0), (1, E - 1)):
+        h = x[1] - x[0] if side == 0 else x[3] - x[2]
+        hw = 0.5 * h
+        a0, a1 = aq[0, e].item(), aq[1, e].item()
+        c0, c1 = (cq[0, e].item(), cq[1, e].item()) if cq is not None else (0.0, 0.0)
+        f0, f1 = (fq[0, e].item(), fq[1, e].item()) if with_load else (0.0, 0.0)
+        pl0, pl1, pr0, pr1 = 1.0 - g0, 1.0 - g1, g0, g1
+        ka = (a0 + a1) / (h * h) * hw
+        mll = (c0 * pl0 * pl0 + c1 * pl1 * pl1) * hw
+        mlr = (c0 * pl0 * pr0 + c1 * pl1 * pr1) * hw
+        mrr = (c0 * pr0 * pr0 + c1 * pr1 * pr1) * hw
+        if side == 0:
+            out.append((ka + mll) * zz[0] + (-ka + mlr) * zz[1] - (f0 * pl0 + f1 * pl1) * hw)
+        else:
+            out.append((-ka + mlr) * zz[2] + (ka + mrr) * zz[3] - (f0 * pr0 + f1 * pr1) * hw)
+    return out
+
+
+def general_interface_solve(records, u_left=0.0, u_right=0.0):
+    """Interface values U_0 .. U_G from the gathered records [G][6] = {ry_l, ry_r, rv_l, rv_r, rw_l, rw_r} per rank."""
+    import numpy as np
+    rec = np.asarray(records, dtype=np.float64).reshape(-1, 6)
+    G = rec.shape[0]
+    U = np.zeros(G + 1)
+    U[0], U[G] = u_left, u_right
+    if G > 1:
+        m = G - 1
+        A = np.zeros((m, m))
+        b = np.zeros(m)
+        for r in range(1, G):          # interface between rank r-1 (right end) and rank r (left end)
+            ryr, rvr, rwr = rec[r - 1, 1], rec[r - 1, 3], rec[r - 1, 5]
+            ryl, rvl, rwl = rec[r, 0], rec[r, 2], rec[r, 4]
+            i = r - 1
+            A[i, i] = rwr + rvl
+            b[i] = -(ryr + ryl)
+            if r - 1 >= 1:
+                A[i, i - 1] = rvr
+            else:
+                b[i] -= rvr * u_left
+            if r + 1 <= G - 1:
+                A[i, i + 1] = rwl
+            else:
+                b[i] -= rwl * u_right
+        U[1:G] = np.linalg.solve(A, b)
+    return U
+
+
+def fem_p1_solve_general_distributed(nodes_local, aq, fq, cq=None, u_left=0.0, u_right=0.0, group=None, local_solve=None):
+    """Partitioned coarse solve of -(a u')' + c u = f: returns the nodal values of this rank's range (interface values
+    included).  aq, fq, cq: [2, E_local] samples at the Gauss points (batch.fem_p1_solve_general).  One all-gather of six
+    doubles per rank; the interface system is solved on the host (this wrapper synchronises, unlike the Poisson path).
+
+    `local_solve(nodes, aq, fq, cq, u_left, u_right) -> u` defaults to the CUDA kernels (CPU tests inject a stand-in)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    solve = local_solve or (lambda n, a, f, c, ul, ur: batch.fem_p1_solve_general(n, a, f, c, u_left=ul, u_right=ur))
+    zero = torch.zeros_like(fq)
+    y = solve(nodes_local, aq, fq, cq, 0.0, 0.0)
+    v = solve(nodes_local, aq, zero, cq, 1.0, 0.0)
+    w = solve(nodes_local, aq, zero, cq, 0.0, 1.0)
+    ry = _general_end_residuals(nodes_local, y, aq, cq, fq, True)
+    rv = _general_end_residuals(nodes_local, v, aq, cq, fq, False)
+    rw = _general_end_residuals(nodes_local, w, aq, cq, fq, False)
+    mine = torch.tensor([ry[0], ry[1], rv[0], rv[1], rw[0], rw[1]], dtype=torch.float64, device=nodes_local.device)
+    if world > 1:
+        gathered = torch.empty(6 * world, dtype=torch.float64, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    else:
+        gathered = mine
+    U = general_interface_solve(gathered.cpu().numpy(), u_left, u_right)
+    return y + float(U[rank]) * v + float(U[rank + 1]) * w

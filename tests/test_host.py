@@ -115,3 +115,71 @@ def test_spike_exchange_over_gloo(tmp_path, world):
         assert np.max(np.abs(u - u_ref[e0:e1 + 1])) <= 1e-11, r
         l2, mx, failed = np.load(tmp_path / ('r%d.npy' % r))
         assert abs(l2 - np.sqrt(world * (world + 1) / 2)) <= 1e-14 and mx == world - 1 and failed == 1
+
+
+# ---- general operator -(a u')' + c u = f across ranks (dist.fem_p1_solve_general_distributed), CPU stand-in for the
+# local solves: the exchange, the interface system and the superposition are what is tested here
+_A = lambda x: 1.0 + 0.5 * np.sin(2.0 * x) ** 2      # noqa: E731
+_C = lambda x: 2.0 + x                               # noqa: E731
+_F = lambda x: 10.0 * np.cos(3.0 * x)                # noqa: E731
+
+
+def _gauss_samples(nodes, fn):
+    x0, h = nodes[:-1], np.diff(nodes)
+    return np.stack([fn(x0 + h * fem_p1._GX[0]), fn(x0 + h * fem_p1._GX[1])])
+
+
+def _oracle_general_local(nodes, aq, fq, cq, ul, ur):
+    """Local P1 solve from the SAMPLES (as the kernels do): assemble with the oracle's rule from aq / cq / fq."""
+    x = nodes.numpy()
+    n = x.size
+    h = np.diff(x)
+    gx = fem_p1._GX
+    kd = np.zeros(n); ko = np.zeros(n - 1); b = np.zeros(n)
+    a_, f_ = aq.numpy(), fq.numpy()
+    c_ = cq.numpy() if cq is not None else np.zeros_like(a_)
+    for q in range(2):
+        w = h * 0.5
+        pl, pr = 1.0 - gx[q], gx[q]
+        ka = a_[q] / h / h * w
+        kd[:-1] += ka + c_[q] * pl * pl * w
+        kd[1:] += ka + c_[q] * pr * pr * w
+        ko += -ka + c_[q] * pl * pr * w
+        b[:-1] += f_[q] * pl * w
+        b[1:] += f_[q] * pr * w
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    lo, up, dg = ko.copy(), ko.copy(), kd.copy()
+    dg[0] = dg[-1] = 1.0
+    up[0] = 0.0
+    lo[-1] = 0.0
+    b[0], b[-1] = ul, ur
+    return torch.from_numpy(spla.spsolve(sp.diags([lo, dg, up], [-1, 0, 1], format='csr'), b))
+
+
+def _general_worker(rank, world, port, E, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        nodes_g = _jittered_mesh(E)
+        e0, e1 = hdist.partition(E, world, rank)
+        x = nodes_g[e0:e1 + 1].copy()
+        aq, cq, fq = (torch.from_numpy(_gauss_samples(x, fn)) for fn in (_A, _C, _F))
+        u = hdist.fem_p1_solve_general_distributed(torch.from_numpy(x), aq, fq, cq, u_left=0.3, u_right=-0.2,
+                                                   local_solve=_oracle_general_local)
+        np.save(os.path.join(out_dir, 'g%d.npy' % rank), u.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_general_operator_interface_system_over_gloo(tmp_path, world):
+    E = 257
+    mp.spawn(_general_worker, args=(world, _free_port(), E, str(tmp_path)), nprocs=world, join=True)
+    nodes_g = _jittered_mesh(E)
+    ref = fem_p1.solve_fem_p1_general(nodes_g, _A, _C, _F, u_left=0.3, u_right=-0.2)
+    for r in range(world):
+        e0, e1 = hdist.partition(E, world, r)
+        u = np.load(tmp_path / ('g%d.npy' % r))
+        assert np.max(np.abs(u - ref[e0:e1 + 1])) <= 1e-11, r
