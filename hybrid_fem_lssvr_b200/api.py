@@ -156,10 +156,8 @@ class FEMLSSVRPrimalSolver:
                                            coarse_solver=self.coarse_solver)
         else:
             # arbitrary rhs_func: the same P1 assembly (2-point Gauss load, P:129-136) from host samples of the callable
-            x0, h = self.fem_nodes[:-1], np.diff(self.fem_nodes)
-            pts = np.stack([x0 + h * batch.GAUSS_X[0], x0 + h * batch.GAUSS_X[1]])
-            dev = self._d_nodes.device
-            fq = torch.from_numpy(np.ascontiguousarray(_sample_rhs(self.rhs_func, pts))).to(dev)
+            from .host_api import stream_samples
+            fq = stream_samples(self.rhs_func, self.fem_nodes[:-1], self.fem_nodes[1:], batch.GAUSS_X, self._d_nodes.device)
             self._d_u = batch.fem_p1_solve_general(self._d_nodes, torch.ones_like(fq), fq, u_left=ul, u_right=ur)
         self.fem_values = self._d_u.cpu().numpy()
         return self.fem_values.copy(), P1Basis(self.fem_nodes)
@@ -184,8 +182,9 @@ class FEMLSSVRPrimalSolver:
             forcing = 'sine'
             k = self._sine_frequency()
         else:
-            pts = _collocation_points(self.fem_nodes, self.n_colloc)
-            forcing = torch.from_numpy(np.ascontiguousarray(_sample_rhs(self.rhs_func, pts))).to(self._d_nodes.device)
+            from .host_api import stream_samples          # pinned staging + async copies (P:45 evaluated on the host)
+            forcing = stream_samples(self.rhs_func, self.fem_nodes[:-1], self.fem_nodes[1:],
+                                     np.linspace(0.0, 1.0, self.n_colloc), self._d_nodes.device)
             k = self.k_freq
         fn = batch.lssvr_primal_batch if self.form == 'primal' else batch.lssvr_dual_batch
         coef, _, status = fn(self._d_nodes, u, self.lssvr_M, self.lssvr_gamma, N=self.n_colloc,

@@ -4,9 +4,56 @@
 Pinned host nodes -> H2D -> K1 coarse solve -> K2/K3/K5 over element chunks -> D2H of each chunk's
 fine rows while the next chunk computes (two device staging buffers, compute + copy streams).
 """
+import numpy as np
 import torch
 
 from . import batch
+
+
+def stream_samples(func, lo, hi, rel_points, device, chunk_elements=1 << 20):
+    """Samples of a host callable on every element, streamed to the device through pinned memory.
+
+    Row j of the result holds func(lo + rel_points[j] * (hi - lo)) for every element (lo, hi: host arrays [E] of the
+    element end points): rel_points = linspace(0, 1, N) gives the collocation samples d_f[j * E + e] of
+    HFL_FORCING_SAMPLES (P:40, P:45), the two Gauss abscissae the samples of hfl_fem_p1_solve_general.  The callable is
+    evaluated chunk by chunk into one of two pinned staging buffers while the previous chunk's cudaMemcpyAsync runs on
+    a copy stream, so at 1e7 elements the 960 MB of samples never sit in pageable memory and the copy hides behind the
+    host evaluation.  Returns a [len(rel_points), E] float64 CUDA tensor, ready for the current stream."""
+    from .api import _sample_rhs          # vectorised / scalar / constant callables
+    device = torch.device(device)
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    rel = np.asarray(rel_points, dtype=np.float64).reshape(-1, 1)
+    E, N = lo.size, rel.shape[0]
+    out = torch.empty((N, E), dtype=torch.float64, device=device)
+    if E == 0:
+        return out
+    chunk = max(1, min(int(chunk_elements), E))
+    stage = [torch.empty((N, chunk), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+    done = [None, None]
+    copy_stream = torch.cuda.Stream(device=device)
+    copy_stream.wait_stream(torch.cuda.current_stream(device))      # `out` exists before the first copy lands in it
+    for c, e0 in enumerate(range(0, E, chunk)):
+        e1 = min(E, e0 + chunk)
+        buf = stage[c & 1]
+        if done[c & 1] is not None:
+            done[c & 1].synchronize()                                # the copy that last used this staging buffer
+        a, b = lo[e0:e1], hi[e0:e1]
+        if N > 1 and rel[0, 0] == 0.0 and rel[-1, 0] == 1.0 and np.allclose(rel[:, 0], np.linspace(0.0, 1.0, N), rtol=0, atol=0):
+            pts = np.linspace(a, b, N, axis=0)                       # the reference's own points (P:40), bit for bit
+        else:
+            pts = a[None, :] + rel * (b - a)[None, :]
+        buf.numpy()[:, :e1 - e0] = _sample_rhs(func, pts)
+        with torch.cuda.stream(copy_stream):
+            out[:, e0:e1].copy_(buf[:, :e1 - e0], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        done[c & 1] = ev
+    torch.cuda.current_stream(device).wait_stream(copy_stream)
+    for ev in done:                      # the staging buffers die with this frame: their copies must have been issued AND done
+        if ev is not None:
+            ev.synchronize()
+    return out
 
 
 class HostPipeline:

@@ -123,6 +123,26 @@ def test_evaluate_solution_keeps_shape_for_any_layout_and_small_M_is_refused():
         lssvr_primal(poisson_rhs, [-1.0, -0.9], 0.0, -0.3, 2, 1e4)
 
 
+def test_streamed_forcing_samples_equal_a_plain_copy():
+    """host_api.stream_samples (pinned double buffer + copy stream) delivers the same [N, E] array as evaluating the
+    callable on all collocation points at once and copying it in one piece; chunk sizes that do and do not divide E."""
+    from hybrid_fem_lssvr_b200 import host_api
+    E, N = 100003, 12
+    nodes = np.sort(np.random.default_rng(5).uniform(-1, 1, E + 1))
+    f = lambda x: np.exp(x) * np.cos(7.0 * x)
+    ref = f(np.linspace(nodes[:-1], nodes[1:], N, axis=0))
+    for chunk in (E, 4096, 33333, 1):
+        if chunk == 1:
+            got = host_api.stream_samples(f, nodes[:50], nodes[1:51], np.linspace(0, 1, N), 'cuda', chunk_elements=1)
+            assert np.array_equal(got.cpu().numpy(), ref[:, :50])
+            continue
+        got = host_api.stream_samples(f, nodes[:-1], nodes[1:], np.linspace(0, 1, N), 'cuda', chunk_elements=chunk)
+        assert np.array_equal(got.cpu().numpy(), ref)
+    gq = host_api.stream_samples(f, nodes[:-1], nodes[1:], batch.GAUSS_X, 'cuda', chunk_elements=7777)
+    h = np.diff(nodes)
+    assert np.array_equal(gq.cpu().numpy(), f(np.stack([nodes[:-1] + batch.GAUSS_X[0] * h, nodes[:-1] + batch.GAUSS_X[1] * h])))
+
+
 def test_dual_form_through_the_class():
     """The 'Dual' script's entry points (D:100-203 are P:107-211): same class, form='dual'."""
     xs = np.linspace(-1, 1, 201)
