@@ -724,6 +724,31 @@ static int make_fine_tensor_map(CUtensorMap* m, double* d_fine, long long E, int
     return HFL_OK;
 }
 
+// Horner tables of PrimalTables: monomial coefficients of P_n (long double recurrence, the entries are dyadic rationals:
+// exact) by parity, and the fine points xi+_i with their squares.
+template <int M, int FH>
+static void fill_horner_tables(PrimalTables<M, FH>& t) {
+    constexpr int ME = n_even(M), MO = n_odd(M);
+    if (FH <= 0) return;
+    long double mono[HFL_MAX_M + 2][HFL_MAX_M + 2];
+    for (int n = 0; n < M; ++n)
+        for (int d = 0; d <= M; ++d) mono[n][d] = 0.0L;
+    mono[0][0] = 1.0L;
+    if (M > 1) mono[1][1] = 1.0L;
+    for (int n = 1; n + 1 < M; ++n)
+        for (int d = 0; d <= n + 1; ++d)
+            mono[n + 1][d] = ((2 * n + 1) * (d > 0 ? mono[n][d - 1] : 0.0L) - n * mono[n - 1][d]) / (long double)(n + 1);
+    for (int k = 0; k < ME; ++k)
+        for (int j = 0; j <= k + 1; ++j) t.TE[j][k] = (double)mono[2 + 2 * k][2 * j];
+    for (int k = 0; k < MO; ++k)
+        for (int j = 0; j <= k + 1; ++j) t.TO[j][k] = (double)mono[3 + 2 * k][2 * j + 1];
+    for (int i = 0; i < FH; ++i) {
+        const long double x = (long double)(2 * i + 1) / (long double)(2 * FH - 1);      // F = 2 FH points, xi+ ascending
+        t.xi[i] = (double)x;
+        t.z[i] = (double)(x * x);
+    }
+}
+
 template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true>
 static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t stream,
                        const DualSmallTables<M, NHD>* dtp = nullptr) {
@@ -762,26 +787,7 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
             }
         }
     }
-    if (FH > 0) {
-        // monomial coefficients of P_n (long double recurrence, the entries are dyadic rationals: exact)
-        long double mono[HFL_MAX_M + 2][HFL_MAX_M + 2];
-        for (int n = 0; n < M; ++n)
-            for (int d = 0; d <= M; ++d) mono[n][d] = 0.0L;
-        mono[0][0] = 1.0L;
-        if (M > 1) mono[1][1] = 1.0L;
-        for (int n = 1; n + 1 < M; ++n)
-            for (int d = 0; d <= n + 1; ++d)
-                mono[n + 1][d] = ((2 * n + 1) * (d > 0 ? mono[n][d - 1] : 0.0L) - n * mono[n - 1][d]) / (long double)(n + 1);
-        for (int k = 0; k < ME; ++k)
-            for (int j = 0; j <= k + 1; ++j) t.TE[j][k] = (double)mono[2 + 2 * k][2 * j];
-        for (int k = 0; k < MO; ++k)
-            for (int j = 0; j <= k + 1; ++j) t.TO[j][k] = (double)mono[3 + 2 * k][2 * j + 1];
-        for (int i = 0; i < FH; ++i) {
-            const long double x = (long double)(2 * i + 1) / (long double)(2 * FH - 1);      // F = 2 FH points, xi+ ascending
-            t.xi[i] = (double)x;
-            t.z[i] = (double)(x * x);
-        }
-    }
+    fill_horner_tables<M, FH>(t);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if ((STORE == STORE_TMA || STORE == STORE_TMA_ROWS) && a.fine != nullptr) {
