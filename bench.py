@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument('--coarse', default='assembled', choices=['assembled', 'assembled_exact', 'flux'])
     ap.add_argument('--store', type=int, default=0, help='primal store path: 0 auto, 1 direct, 2 smem, 3 tma')
     ap.add_argument('--cpu-sample', type=int, default=0, help='elements in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'],
+                    help='N = 1: replay the step (5 K1 launches + the element launch) as a CUDA graph')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -399,6 +401,32 @@ def run_ours(args):
     for _ in range(warmup):
         step()
     barrier()
+    # N = 1: the step is six dependent launches of 8-480 us; replaying them as a CUDA graph removes the per-launch host
+    # work and most of the gap between dependent kernels.  N > 1 keeps stream launches (the exchange kernel takes its
+    # epoch as a launch argument).
+    graph = None
+    if world == 1 and args.graph != 'off':
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            g.replay()
+            torch.cuda.synchronize()
+            graph = g
+        except Exception as exc:
+            if args.graph == 'on':
+                raise
+            sys.stderr.write('bench: CUDA graph capture failed (%s); using stream launches\n' % exc)
+            torch.cuda.synchronize()
+    eager_step = step
+    if graph is not None:
+        lpg = _lib.launch_count()
+        eager_step()
+        lpg = _lib.launch_count() - lpg         # our launches per step, counted once outside the graph
+        step = lambda: graph.replay()           # noqa: E731
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
     if exchange_expired():       # a receive spin that expired on any rank: fall back to NCCL on all of them
         if args.exchange == 'peer':
             raise RuntimeError('peer-memory exchange timed out')
@@ -422,7 +450,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     t1 = time.perf_counter()
-    launches = _lib.launch_count() - l0
+    launches = (_lib.launch_count() - l0) if graph is None else lpg * args.steps
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -469,6 +497,7 @@ def run_ours(args):
         pass
 
     # ---- error norms of the last step (reported, not timed)
+    step = eager_step
     step()                                  # per-kernel timing loops overwrote u; restore the step's state
     torch.cuda.synchronize()
     if world == 1:
@@ -646,7 +675,8 @@ def run_ours(args):
 
     if rank == 0:
         cfg = workload_config(E, world, args.coarse, args.error)       # identical in the reference arm
-        run_info = {'coarse_solver': (args.coarse if world == 1 else coarse_dist + ' + SPIKE interface exchange'),
+        run_info = {'cuda_graph': graph is not None,
+                    'coarse_solver': (args.coarse if world == 1 else coarse_dist + ' + SPIKE interface exchange'),
                     'error_norms': args.error, 'store_path': args.store,
                     'exchange': ('none (single GPU)' if world == 1 else
                                  'NVLink peer-memory exchange fused with the interface solve (hfl_peer_spike_exchange)'

@@ -38,30 +38,6 @@ namespace hfl {
 // ---------------------------------------------------------------------------------------------------------
 // Element terms.
 
-// Taylor polynomial of the forcing about the chunk's head node: (k pi)^2 sin(k pi (x_ref + dx)) = sum_j tc[j] dx^j,
-// tc[j] = ta[j] * (sin | cos)(k pi x_ref).  TIER 1: degree 9, |k pi dx| <= 2^-4 (truncation < 3e-19 of the amplitude);
-// TIER 2: degree 4, |k pi dx| <= 2^-10 (truncation < 1e-17); TIER 3: degree 2, |k pi dx| <= 2^-17.5 (truncation < 4e-17).
-template <int TIER>
-struct ForcingPoly {
-    static constexpr int DEG = (TIER == 3) ? 2 : ((TIER == 2) ? 4 : 9);
-    double tc[DEG + 1];
-    __device__ __forceinline__ void init(const FemArgs& a, double S, double C) {
-#pragma unroll
-        for (int j = 0; j <= DEG; ++j) tc[j] = a.ta[j] * ((j & 1) ? C : S);
-    }
-    __device__ __forceinline__ double eval(double dx) const {
-        double p = tc[DEG];
-#pragma unroll
-        for (int j = DEG - 1; j >= 0; --j) p = fma(p, dx, tc[j]);
-        return p;
-    }
-};
-template <>
-struct ForcingPoly<0> {
-    __device__ __forceinline__ void init(const FemArgs&, double, double) {}
-    __device__ __forceinline__ double eval(double) const { return 0.0; }
-};
-
 // Stiffness entry and load shares of one element of the reference's Poisson problem.  k carries the reference's
 // rounding (P:125-136 through scikit-fem's quadrature loop: fl(fl(1/h)^2 * (h W_q)) twice) because the row-sum
 // residues of the assembled diagonal depend on its last bit; the load (2-point Gauss, P:129-136) is formed with
