@@ -410,14 +410,14 @@ __global__ void __launch_bounds__(FT, HFL_FEM_MINB) fem_chunk_reduce_kernel(cons
 // The 8 head rows of a level-1 chunk (heads H0 .. H0 + 7), heads past NH padded with identity rows.
 struct HeadRows {
     double l[FS], s[FS], r[FS], b[FS];
-    __device__ __forceinline__ void load(const double* __restrict__ hrow, long long NH, long long H0) {
+    __device__ __forceinline__ void load(const double* hrow, long long NH, long long H0) {
         if (H0 + FS <= NH) {
 #pragma unroll
             for (int i = 0; i < FS; i += 2) {
-                const double2 vl = *reinterpret_cast<const double2*>(hrow + H0 + i);
-                const double2 vs = *reinterpret_cast<const double2*>(hrow + NH + H0 + i);
-                const double2 vr = *reinterpret_cast<const double2*>(hrow + 2 * NH + H0 + i);
-                const double2 vb = *reinterpret_cast<const double2*>(hrow + 3 * NH + H0 + i);
+                const double2 vl = __ldcg(reinterpret_cast<const double2*>(hrow + H0 + i));
+                const double2 vs = __ldcg(reinterpret_cast<const double2*>(hrow + NH + H0 + i));
+                const double2 vr = __ldcg(reinterpret_cast<const double2*>(hrow + 2 * NH + H0 + i));
+                const double2 vb = __ldcg(reinterpret_cast<const double2*>(hrow + 3 * NH + H0 + i));
                 l[i] = vl.x; l[i + 1] = vl.y; s[i] = vs.x; s[i + 1] = vs.y;
                 r[i] = vr.x; r[i + 1] = vr.y; b[i] = vb.x; b[i + 1] = vb.y;
             }
@@ -434,26 +434,23 @@ struct HeadRows {
 // Level 1, pass 1.  Tile record (SoA, rec[f * ntile + tile]): f = 0..3 {l, sigma, r, b} of the tile head's row,
 // 4..7 {y, v, w, e} of the tile's first interior head, 8..11 of its last one (x = y - v u_P - w u_Q, e = 1 + v + w).
 // sheads[tile][3][FT]: final cyclic-reduction row {L/d, R/d, B/d} of every super head.
-__global__ void __launch_bounds__(FT, 3) fem_heads_reduce_kernel(const double* __restrict__ hrow, const double* __restrict__ edge,
-                                                              long long NH, double* __restrict__ rec,
-                                                              double* __restrict__ sheads, long long ws_stride) {
-    __shared__ double s_ex2[3 * FT], s_cr[4 * CRLEN];
-    hrow += (size_t)blockIdx.y * ws_stride; edge += (size_t)blockIdx.y * ws_stride;
-    rec += (size_t)blockIdx.y * ws_stride; sheads += (size_t)blockIdx.y * ws_stride;
+__device__ __forceinline__ void heads_reduce_tile(long long tile, long long ntile, const double* hrow, const double* edge,
+                                                  long long NH, double* __restrict__ rec, double* __restrict__ sheads,
+                                                  double* s_ex2, double* s_cr) {
     const int t = threadIdx.x;
-    const long long H0 = (long long)blockIdx.x * FTS + (long long)t * FS;
+    const long long H0 = tile * FTS + (long long)t * FS;
     HeadRows hr;
     hr.load(hrow, NH, H0);
     if ((t & (FT / FS - 1)) == 0 && H0 < NH) {            // first head of a level-0 CTA: finish its row from the edge records
         const long long cta = H0 / FT;
         const double* eo = edge + (size_t)cta * 8;
-        const double lp = eo[0], sp = eo[1];
+        const double lp = __ldcg(eo + 0), sp = __ldcg(eo + 1);
         double ysp = 0.0, vsp = 0.0, esp = 0.0;
-        if (cta > 0) { ysp = eo[5 - 8]; vsp = eo[6 - 8]; esp = eo[7 - 8]; }
+        if (cta > 0) { ysp = __ldcg(eo + 5 - 8); vsp = __ldcg(eo + 6 - 8); esp = __ldcg(eo + 7 - 8); }
         hr.l[0] = __dmul_rn(-lp, vsp);
-        hr.r[0] = eo[3];
-        hr.s[0] = __dadd_rn(sp, __dadd_rn(__dmul_rn(-lp, esp), eo[2]));          // the sum head_equation forms
-        hr.b[0] = fma(-lp, ysp, eo[4]);
+        hr.r[0] = __ldcg(eo + 3);
+        hr.s[0] = __dadd_rn(sp, __dadd_rn(__dmul_rn(-lp, esp), __ldcg(eo + 2)));          // the sum head_equation forms
+        hr.b[0] = fma(-lp, ysp, __ldcg(eo + 4));
     }
     double e8[8];
     chunk_sweeps([&](int i, double& l, double& sg, double& r, double& b) { hr.get(i, l, sg, r, b); }, e8);
@@ -475,15 +472,15 @@ __global__ void __launch_bounds__(FT, 3) fem_heads_reduce_kernel(const double* _
         const double inv = fast_rcp(diag_of(S, L, R));
         const double Ld = __dmul_rn(L, inv), Rd = __dmul_rn(R, inv), Bd = B * inv;
         sL[ii] = Ld; sR[ii] = Rd; sB[ii] = Bd; sS[ii] = __dmul_rn(S, inv);
-        double* o = sheads + (size_t)blockIdx.x * 3 * FT;
+        double* o = sheads + (size_t)tile * 3 * FT;
         o[t] = Ld; o[FT + t] = Rd; o[2 * FT + t] = Bd;
     } else {             // slot 0 is the tile head itself (solved at the top level)
-        double* o = sheads + (size_t)blockIdx.x * 3 * FT;
+        double* o = sheads + (size_t)tile * 3 * FT;
         o[0] = 0.0; o[FT] = 0.0; o[2 * FT] = 0.0;
     }
     __syncthreads();
-    const long long nt = gridDim.x;
-    double* out = rec + blockIdx.x;
+    const long long nt = ntile;
+    double* out = rec + tile;
     if (t == 0 || t == FT - 1) {
         // super head FT/2 through the two tile heads, then down the tree to super head 1 (t = 0) or FT-1 (t = FT-1):
         // u = Y - V u_P - W u_Q, E = 1 + V + W
@@ -514,6 +511,16 @@ __global__ void __launch_bounds__(FT, 3) fem_heads_reduce_kernel(const double* _
             out[11 * nt] = __fma_rn(-e8[5], E, e8[7]);
         }
     }
+}
+
+// Level 1, pass 1: one CTA per tile.
+__global__ void __launch_bounds__(FT, 3) fem_heads_reduce_kernel(const double* hrow, const double* edge, long long NH,
+                                                              double* __restrict__ rec, double* __restrict__ sheads,
+                                                              long long ws_stride) {
+    __shared__ double s_ex2[3 * FT], s_cr[4 * CRLEN];
+    hrow += (size_t)blockIdx.y * ws_stride; edge += (size_t)blockIdx.y * ws_stride;
+    rec += (size_t)blockIdx.y * ws_stride; sheads += (size_t)blockIdx.y * ws_stride;
+    heads_reduce_tile(blockIdx.x, gridDim.x, hrow, edge, NH, rec, sheads, s_ex2, s_cr);
 }
 
 // Thomas elimination of a chunk interior between two known head values, in (l, sigma, r) form: s = row sum over
