@@ -75,11 +75,29 @@ class HostPipeline:
         self.h2d_bytes = 8 * (self.E + 1)
         self.d2h_bytes = 8 * self.E * self.F + 8 * (self.E + 1) + 24
 
+    def _run_resident(self, nodes_h):
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, 'fine_d', None) is None:
+            self.fine_d = torch.empty((self.E, self.F), dtype=torch.float64, device=self.device)
+        self.nodes_d.copy_(nodes_h, non_blocking=True)
+        self.err3.zero_()
+        batch.fem_p1_solve(self.nodes_d, k_freq=self.k_freq, coarse_solver=self.coarse_solver, out=self.u_d)
+        batch.lssvr_primal_batch(self.nodes_d, self.u_d, self.M, self.gamma, N=self.N, F=self.F, forcing='sine',
+                                 k_freq=self.k_freq, want_coef=False, want_fine=True, fine_out=self.fine_d, err3=self.err3)
+        self.u_h.copy_(self.u_d, non_blocking=True)
+        self.err_h.copy_(self.err3, non_blocking=True)
+        cur.synchronize()
+        return self.fine_d, self.u_h, (float(self.err_h[0]) ** 0.5, float(self.err_h[1]))
+
     def pinned_nodes(self):
         return torch.empty(self.E + 1, dtype=torch.float64, pin_memory=True)
 
-    def run(self, nodes_h):
-        """nodes_h: pinned host tensor [E + 1].  Returns (fine_h [E, F], u_h [E + 1], (l2, max)) on the host."""
+    def run(self, nodes_h, fetch_fine=True):
+        """nodes_h: pinned host tensor [E + 1].  Returns (fine_h [E, F], u_h [E + 1], (l2, max)) on the host.
+        fetch_fine=False: the fine grid stays on the device (one launch over all elements into `self.fine_d`); only the
+        nodal values and the error norms come back."""
+        if not fetch_fine:
+            return self._run_resident(nodes_h)
         cur = torch.cuda.current_stream(self.device)
         self.nodes_d.copy_(nodes_h, non_blocking=True)
         self.err3.zero_()

@@ -39,10 +39,11 @@ extern "C" {
 #define HFL_FORCING_SAMPLES 1  /* f given as samples d_f[j * E + e] = f(x_e + j h_e / (N - 1)), j < N (any rhs_func, P:20/P:45) */
 
 /* coarse_solver */
-#define HFL_COARSE_ASSEMBLED_PCR 0  /* the reference's assembled tridiagonal system, partition + parallel cyclic reduction */
+#define HFL_COARSE_ASSEMBLED_PCR 0  /* the reference's assembled tridiagonal system: three-level partition (register-resident
+                                       chunks of 8 nodes, cyclic reduction over the chunk heads, one CTA for the tile heads) */
 #define HFL_COARSE_FLUX_SCAN 1      /* same equations in first-order (flux) form by two prefix sums; better conditioned */
 #define HFL_COARSE_ASSEMBLED_EXACT 2 /* the assembled system with the UNROUNDED diagonal k_l + k_r (zero row sums), same
-                                        partition + PCR kernels.  The reference's rounded diagonal fl(k_l + k_r) acts as a
+                                        partition kernels.  The reference's rounded diagonal fl(k_l + k_r) acts as a
                                         spurious reaction term eps k_i u_i: invisible at the reference's sizes (both
                                         modes are within 1e-10 of it up to ~1e4 nodes), 3e-6 at 1e6 nodes and 1e-3 at 1e7
                                         nodes on unlucky meshes.  Mode 0 reproduces that system faithfully; mode 2 (and
@@ -90,7 +91,7 @@ int hfl_fem_p1_solve_multi(int64_t n_nodes, const double* d_nodes, int R, const 
 
 /* Coarse P1 solve of the general operator -(a u')' + c u = f (stiffness of a, mass matrix of c, load of f, each by
  * the same 2-point Gauss rule): d_aq, d_cq, d_fq are samples [2][n-1] at the two Gauss points
- * x_e + h_e (1/2 -+ 1/(2 sqrt 3)) of every element (d_cq may be NULL = 0).  Assembled partition + PCR solver in
+ * x_e + h_e (1/2 -+ 1/(2 sqrt 3)) of every element (d_cq may be NULL = 0).  Assembled three-level partition solver in
  * row-sum form; same workspace as hfl_fem_p1_solve. */
 int hfl_fem_p1_solve_general(int64_t n_nodes, const double* d_nodes,
                              const double* d_aq, const double* d_cq, const double* d_fq,

@@ -183,3 +183,5 @@ def test_host_pipeline_matches_device_path():
     l2d, mxd = batch.finish_error(err)
     assert abs(l2 - l2d) <= 1e-9 * l2d and mx == mxd
     assert pipe.d2h_bytes == 8 * E * 32 + 8 * (E + 1) + 24 and pipe.h2d_bytes == 8 * (E + 1)
+    fine_d, u_h2, (l2r, mxr) = pipe.run(nodes_h, fetch_fine=False)          # fine grid left on the device
+    assert torch.equal(fine_d.cpu(), fine_h) and torch.equal(u_h2, u_h) and mxr == mx
