@@ -7,9 +7,11 @@ namespace hfl {
 
 template <int M, int FH, bool ERR>
 static int dispatch_store(const hfl_plan* plan, const PrimalArgs& a, int store, cudaStream_t s) {
-    // Coefficient output and the fused error norms always take the TMA-store instantiation that has the coefficient
-    // path compiled in: measured 0.54 ms against 0.60 ms for the fused-error kernel without it (register allocation),
-    // while the plain fine-grid kernel is 7 % faster without it.  The store-path option applies to the plain kernel.
+    // The store-path option applies to the plain fine-grid kernel.
+    // The fused error norms without coefficient output take the instantiation WITHOUT the coefficient path (130 registers
+    // instead of 164 at M = 9; measured 0.500 against 0.513 ms - in round 1, before the Horner / Taylor rewrite of the
+    // epilogue, it was the other way round).  Coefficient output always takes the TMA-store instantiation.
+    if (ERR && a.coef == nullptr) return launch_fast<M, FH, ERR, STORE_TMA, 0, false>(plan, a, s);
     if (a.coef != nullptr || ERR) return launch_fast<M, FH, ERR, STORE_TMA, 0, true>(plan, a, s);
     if constexpr (!ERR && FH != 16) return launch_fast<M, FH, ERR, STORE_TMA, 0, false>(plan, a, s);   // other F: TMA only
     if constexpr (!ERR && FH == 16) {
