@@ -91,8 +91,11 @@ __host__ __device__ constexpr int tile_bytes(int F) {
 #ifndef HFL_ERR_MINB
 #define HFL_ERR_MINB 3
 #endif
+#ifndef HFL_PLAIN_MINB
+#define HFL_PLAIN_MINB 4
+#endif
 __host__ __device__ constexpr int min_ctas(int M, bool err, bool coef) {
-    return (M <= 10 && !err && !coef) ? 4 : (err ? HFL_ERR_MINB : (coef ? 2 : 3));
+    return (M <= 10 && !err && !coef) ? HFL_PLAIN_MINB : (err ? HFL_ERR_MINB : (coef ? 2 : 3));
 }
 
 // LDL^T of a packed-lower PSD matrix in a FIXED (plan-supplied) pivot order with a skip rule: a pivot that

@@ -285,3 +285,21 @@ def test_large_meshes_three_solvers(n):
     assert torch.max(torch.abs(ue - torch.sin(np.pi * nodes))).item() <= 1e-12
     ua = batch.fem_p1_solve(nodes, coarse_solver='assembled')
     assert torch.max(torch.abs(ua - uf)).item() <= 1e-2 and ua[0].item() == 0.0 and ua[-1].item() == 0.0
+
+
+@pytest.mark.parametrize('n', [4 * 10 ** 6 + 1, 16384 * 1100 + 3])
+def test_top_level_with_rows_in_the_workspace(n):
+    """The top-level CTA keeps the tile-head rows in shared memory while they fit; beyond ~8.5e7 nodes they live in the
+    workspace.  fem_top_smem_kb = 64 forces that path at testable sizes: 245 tiles (one head per top-level thread) and
+    1101 tiles (chunks of two heads per thread); same answers as with the rows in shared memory, bit for bit."""
+    nodes = batch.mesh_linspace(-1.0, 1.0, n)
+    ref = batch.fem_p1_solve(nodes, coarse_solver='assembled_exact')
+    refa = batch.fem_p1_solve(nodes, coarse_solver='assembled')
+    batch.set_option('fem_top_smem_kb', 64)
+    try:
+        ue = batch.fem_p1_solve(nodes, coarse_solver='assembled_exact')
+        ua = batch.fem_p1_solve(nodes, coarse_solver='assembled')
+    finally:
+        batch.set_option('fem_top_smem_kb', 227)
+    assert torch.equal(ue, ref) and torch.equal(ua, refa)
+    assert torch.max(torch.abs(ue - torch.sin(np.pi * nodes))).item() <= 1e-12
