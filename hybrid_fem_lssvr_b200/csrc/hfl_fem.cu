@@ -76,6 +76,12 @@ struct Chunk {
 
 
 
+// Node loads of the level-0 kernels: streaming (evict-first) so that the 80 MB of nodes do not push the head rows and
+// head values (40 + 10 MB, written by one kernel and read by the next two) out of L2.
+#ifndef HFL_NODE_LOAD
+#define HFL_NODE_LOAD __ldcs
+#endif
+
 // First half: loads the chunk's nodes, forms elements j = 1 .. FS (left of nodes g0 + 1 .. g0 + FS), publishes the last
 // one for the next thread; thread 0 forms the element left of its head itself.  Call __syncthreads(), then
 // chunk_build_finish.  SPECIAL = the tile holds a Dirichlet node or padding past the mesh.
@@ -89,14 +95,14 @@ __device__ __forceinline__ void chunk_build_start(const FemArgs& a, long long g0
         if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < FS; i += 2) {
-                const double2 v = __ldg(reinterpret_cast<const double2*>(p + i));
+                const double2 v = HFL_NODE_LOAD(reinterpret_cast<const double2*>(p + i));
                 x[i] = v.x; x[i + 1] = v.y;
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < FS; ++i) x[i] = __ldg(p + i);
+            for (int i = 0; i < FS; ++i) x[i] = HFL_NODE_LOAD(p + i);
         }
-        x[FS] = __ldg(p + FS);
+        x[FS] = HFL_NODE_LOAD(p + FS);
     } else {
 #pragma unroll
         for (int i = 0; i <= FS; ++i) x[i] = __ldg(a.nodes + min(g0 + i, a.n - 1));
@@ -307,7 +313,17 @@ __device__ __forceinline__ void head_equation(double lp, double sp, double rp, d
 // Shared-memory index of chunk head i (0 .. FT; index FT = the next tile's head): one pad per 16 doubles keeps the
 // strided accesses of the cyclic reduction (stride 2, 4, ..., 128 heads) free of bank conflicts.
 __host__ __device__ constexpr int cp(int i) { return i + (i >> 4); }
-constexpr int CRLEN = cp(FT) + 1;
+
+// Level 1: FT1 threads per CTA, one chunk of FS heads each: a tile is FTS1 = FT1 * FS heads = 8192 nodes.  Smaller tiles
+// than the level-0 CTA (FT = 256): the level-1 kernels are chains of dependent steps (sweeps, reduction tree, paths), so
+// what counts is how many of them are resident at once and how deep the tree is (6 levels over 127 super heads).
+#ifndef HFL_FEM_FT1
+#define HFL_FEM_FT1 128
+#endif
+constexpr int FT1 = HFL_FEM_FT1;
+constexpr int FTS1 = FT1 * FS;
+constexpr int CRLEN1 = cp(FT1) + 1;
+static_assert(FT1 >= 32 && (FT1 & (FT1 - 1)) == 0 && FT1 % (FT / FS) == 0, "level-1 CTA size");
 
 // Forward cyclic reduction over rows 1 .. N-1 (rows as (l, sigma, r, b) at padded index cp(i); index 0 and index N are
 // unknown columns without rows of their own).  Level delta updates the rows at multiples of 2 delta from their
@@ -433,12 +449,12 @@ struct HeadRows {
 
 // Level 1, pass 1.  Tile record (SoA, rec[f * ntile + tile]): f = 0..3 {l, sigma, r, b} of the tile head's row,
 // 4..7 {y, v, w, e} of the tile's first interior head, 8..11 of its last one (x = y - v u_P - w u_Q, e = 1 + v + w).
-// sheads[tile][3][FT]: final cyclic-reduction row {L/d, R/d, B/d} of every super head.
+// sheads[tile][3][FT1]: final cyclic-reduction row {L/d, R/d, B/d} of every super head.
 __device__ __forceinline__ void heads_reduce_tile(long long tile, long long ntile, const double* hrow, const double* edge,
                                                   long long NH, double* __restrict__ rec, double* __restrict__ sheads,
                                                   double* s_ex2, double* s_cr) {
     const int t = threadIdx.x;
-    const long long H0 = tile * FTS + (long long)t * FS;
+    const long long H0 = tile * FTS1 + (long long)t * FS;
     HeadRows hr;
     hr.load(hrow, NH, H0);
     if ((t & (FT / FS - 1)) == 0 && H0 < NH) {            // first head of a level-0 CTA: finish its row from the edge records
@@ -455,40 +471,40 @@ __device__ __forceinline__ void heads_reduce_tile(long long tile, long long ntil
     double e8[8];
     chunk_sweeps([&](int i, double& l, double& sg, double& r, double& b) { hr.get(i, l, sg, r, b); }, e8);
     const double lp = hr.l[0], sp = hr.s[0], rp = hr.r[0], bp = hr.b[0];
-    s_ex2[0 * FT + t] = e8[4]; s_ex2[1 * FT + t] = e8[5]; s_ex2[2 * FT + t] = e8[7];     // ys, vs, es of this chunk
+    s_ex2[0 * FT1 + t] = e8[4]; s_ex2[1 * FT1 + t] = e8[5]; s_ex2[2 * FT1 + t] = e8[7];     // ys, vs, es of this chunk
     __syncthreads();
-    double* sL = s_cr; double* sS = s_cr + CRLEN; double* sR = s_cr + 2 * CRLEN; double* sB = s_cr + 3 * CRLEN;
+    double* sL = s_cr; double* sS = s_cr + CRLEN1; double* sR = s_cr + 2 * CRLEN1; double* sB = s_cr + 3 * CRLEN1;
     if (t >= 1) {
         double L, S, R, B;
-        head_equation(lp, sp, rp, bp, s_ex2[0 * FT + t - 1], s_ex2[1 * FT + t - 1], s_ex2[2 * FT + t - 1], e8, L, S, R, B);
+        head_equation(lp, sp, rp, bp, s_ex2[0 * FT1 + t - 1], s_ex2[1 * FT1 + t - 1], s_ex2[2 * FT1 + t - 1], e8, L, S, R, B);
         sL[cp(t)] = L; sS[cp(t)] = S; sR[cp(t)] = R; sB[cp(t)] = B;
     }
     __syncthreads();
-    // cyclic reduction over super heads 1 .. FT-1; heads 0 (this tile's) and FT (the next tile's) stay as unknown columns
-    cr_forward<FT>(sL, sS, sR, sB, t);
+    // cyclic reduction over super heads 1 .. FT1-1; heads 0 (this tile's) and FT1 (the next tile's) stay as unknown columns
+    cr_forward<FT1>(sL, sS, sR, sB, t);
     if (t >= 1) {        // every row is final: scale by its diagonal, keep it for the back-substitution pass
         const int ii = cp(t);
         const double L = sL[ii], S = sS[ii], R = sR[ii], B = sB[ii];
         const double inv = fast_rcp(diag_of(S, L, R));
         const double Ld = __dmul_rn(L, inv), Rd = __dmul_rn(R, inv), Bd = B * inv;
         sL[ii] = Ld; sR[ii] = Rd; sB[ii] = Bd; sS[ii] = __dmul_rn(S, inv);
-        double* o = sheads + (size_t)tile * 3 * FT;
-        o[t] = Ld; o[FT + t] = Rd; o[2 * FT + t] = Bd;
+        double* o = sheads + (size_t)tile * 3 * FT1;
+        o[t] = Ld; o[FT1 + t] = Rd; o[2 * FT1 + t] = Bd;
     } else {             // slot 0 is the tile head itself (solved at the top level)
-        double* o = sheads + (size_t)tile * 3 * FT;
-        o[0] = 0.0; o[FT] = 0.0; o[2 * FT] = 0.0;
+        double* o = sheads + (size_t)tile * 3 * FT1;
+        o[0] = 0.0; o[FT1] = 0.0; o[2 * FT1] = 0.0;
     }
     __syncthreads();
     const long long nt = ntile;
     double* out = rec + tile;
-    if (t == 0 || t == FT - 1) {
-        // super head FT/2 through the two tile heads, then down the tree to super head 1 (t = 0) or FT-1 (t = FT-1):
+    if (t == 0 || t == FT1 - 1) {
+        // super head FT1/2 through the two tile heads, then down the tree to super head 1 (t = 0) or FT1-1 (t = FT1-1):
         // u = Y - V u_P - W u_Q, E = 1 + V + W
-        int i = cp(FT / 2);
+        int i = cp(FT1 / 2);
         double Y = sB[i], V = sL[i], W = sR[i], E = sS[i];
         if (t == 0) {
 #pragma unroll
-            for (int delta = FT / 4; delta >= 1; delta >>= 1) {        // node delta: left neighbour 0, right neighbour 2 delta
+            for (int delta = FT1 / 4; delta >= 1; delta >>= 1) {        // node delta: left neighbour 0, right neighbour 2 delta
                 i = cp(delta);
                 const double Rd = sR[i];
                 Y = fma(-Rd, Y, sB[i]); V = __fma_rn(-Rd, V, sL[i]); W = __dmul_rn(-Rd, W); E = __fma_rn(-Rd, E, sS[i]);
@@ -500,8 +516,8 @@ __device__ __forceinline__ void heads_reduce_tile(long long tile, long long ntil
             out[7 * nt] = __fma_rn(-e8[2], E, e8[3]);
         } else {
 #pragma unroll
-            for (int delta = FT / 4; delta >= 1; delta >>= 1) {        // node FT - delta: left neighbour FT - 2 delta, right FT
-                i = cp(FT - delta);
+            for (int delta = FT1 / 4; delta >= 1; delta >>= 1) {        // node FT1 - delta: left neighbour FT1 - 2 delta, right FT1
+                i = cp(FT1 - delta);
                 const double Ld = sL[i];
                 Y = fma(-Ld, Y, sB[i]); V = __dmul_rn(-Ld, V); W = __fma_rn(-Ld, W, sR[i]); E = __fma_rn(-Ld, E, sS[i]);
             }
@@ -514,10 +530,10 @@ __device__ __forceinline__ void heads_reduce_tile(long long tile, long long ntil
 }
 
 // Level 1, pass 1: one CTA per tile.
-__global__ void __launch_bounds__(FT, 3) fem_heads_reduce_kernel(const double* hrow, const double* edge, long long NH,
+__global__ void __launch_bounds__(FT1) fem_heads_reduce_kernel(const double* hrow, const double* edge, long long NH,
                                                               double* __restrict__ rec, double* __restrict__ sheads,
                                                               long long ws_stride) {
-    __shared__ double s_ex2[3 * FT], s_cr[4 * CRLEN];
+    __shared__ double s_ex2[3 * FT1], s_cr[4 * CRLEN1];
     hrow += (size_t)blockIdx.y * ws_stride; edge += (size_t)blockIdx.y * ws_stride;
     rec += (size_t)blockIdx.y * ws_stride; sheads += (size_t)blockIdx.y * ws_stride;
     heads_reduce_tile(blockIdx.x, gridDim.x, hrow, edge, NH, rec, sheads, s_ex2, s_cr);
@@ -649,40 +665,40 @@ __global__ void __launch_bounds__(TOPT) fem_top_kernel(const double* __restrict_
 // u_i = B_i - L_i u_{i-d} - R_i u_{i+d} with d = lowbit(i): levels d >= 4 (the 63 super heads at multiples of 4) on warp
 // 0, then every thread evaluates the two rows (d = 2, d = 1) its own u_t, u_{t+1} need -> the 7 interior heads of every
 // level-1 chunk by Thomas in registers -> uh[h] for every head h.
-__global__ void __launch_bounds__(FT) fem_heads_backsub_kernel(const double* __restrict__ hrow, long long NH,
+__global__ void __launch_bounds__(FT1) fem_heads_backsub_kernel(const double* __restrict__ hrow, long long NH,
                                                                const double* __restrict__ utop, int ntile,
                                                                const double* __restrict__ sheads, double* __restrict__ uh,
                                                                long long ws_stride) {
-    __shared__ double s_u[CRLEN];
+    __shared__ double s_u[CRLEN1];
     hrow += (size_t)blockIdx.y * ws_stride; utop += (size_t)blockIdx.y * ws_stride;
     sheads += (size_t)blockIdx.y * ws_stride; uh += (size_t)blockIdx.y * ws_stride;
     const int t = threadIdx.x;
-    const long long H0 = (long long)blockIdx.x * FTS + (long long)t * FS;
-    const double* o = sheads + (size_t)blockIdx.x * 3 * FT;
+    const long long H0 = (long long)blockIdx.x * FTS1 + (long long)t * FS;
+    const double* o = sheads + (size_t)blockIdx.x * 3 * FT1;
     const int od = t | 1;                                  // the odd one of {t, t + 1}
     const int m2 = (od & 2) ? (od - 1) : (od + 1);         // its neighbour that is 2 mod 4 (the other one is 0 mod 4)
-    const double oL = o[od], oR = o[FT + od], oB = o[2 * FT + od];
-    const double mL = o[m2], mR = o[FT + m2], mB = o[2 * FT + m2];
+    const double oL = o[od], oR = o[FT1 + od], oB = o[2 * FT1 + od];
+    const double mL = o[m2], mR = o[FT1 + m2], mB = o[2 * FT1 + m2];
     HeadRows hr;
     hr.load(hrow, NH, H0);                                 // rows 1 .. 7 are never the first head of a level-0 CTA
     if (t < 32) {
-        constexpr int NLV = 6;                             // d = FT/2 .. 4
-        static_assert(FT == 256, "level count of the warp-0 tree");
+        constexpr int NLV = (FT1 == 256 ? 6 : (FT1 == 128 ? 5 : (FT1 == 64 ? 4 : 3)));   // d = FT1/2 .. 4
+        static_assert((4 << NLV) == FT1 && FT1 / 8 <= 32, "level count of the warp-0 tree");
         double rl[NLV], rr[NLV], rb[NLV];
 #pragma unroll
         for (int q = 0; q < NLV; ++q) {
-            const int delta = (FT / 2) >> q, cnt = 1 << q;
+            const int delta = (FT1 / 2) >> q, cnt = 1 << q;
             const int i = (t < cnt) ? delta * (2 * t + 1) : delta;
-            rl[q] = o[i]; rr[q] = o[FT + i]; rb[q] = o[2 * FT + i];
+            rl[q] = o[i]; rr[q] = o[FT1 + i]; rb[q] = o[2 * FT1 + i];
         }
         if (t == 0) {
             s_u[cp(0)] = utop[blockIdx.x];
-            s_u[cp(FT)] = ((int)blockIdx.x + 1 < ntile) ? utop[blockIdx.x + 1] : 0.0;
+            s_u[cp(FT1)] = ((int)blockIdx.x + 1 < ntile) ? utop[blockIdx.x + 1] : 0.0;
         }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < NLV; ++q) {
-            const int delta = (FT / 2) >> q, cnt = 1 << q;
+            const int delta = (FT1 / 2) >> q, cnt = 1 << q;
             if (t < cnt) {
                 const int i = delta * (2 * t + 1);
                 s_u[cp(i)] = fma(-rr[q], s_u[cp(i + delta)], fma(-rl[q], s_u[cp(i - delta)], rb[q]));
@@ -808,12 +824,12 @@ __global__ void spike_iface_kernel(int G, const double* __restrict__ g, double u
 using namespace hfl;
 
 static inline long long fem_nchunkcta(long long n) { return (n + FTS - 1) / FTS; }                  // level-0 CTAs (2048 nodes each)
-static inline long long fem_ntile(long long n) { return (fem_nchunkcta(n) * FT + FTS - 1) / FTS; }    // level-1 CTAs (2048 heads each)
+static inline long long fem_ntile(long long n) { return (fem_nchunkcta(n) * FT + FTS1 - 1) / FTS1; }  // level-1 CTAs (FTS1 heads each)
 // rec | utop | top rows | sheads | hrow | edge | uh (see the layout comment above fem_chunk_reduce_body); every block
 // starts on a 16-byte boundary
 static size_t fem_ws_doubles(long long n) {
     const size_t nc = (size_t)fem_nchunkcta(n), nt = (size_t)fem_ntile(n), NH = nc * FT;
-    size_t top = (REC + 1 + 6 + 3 * FT) * nt;
+    size_t top = (REC + 1 + 6 + 3 * FT1) * nt;
     top += top & 1;
     return top + 4 * NH + 8 * nc + NH + 8;
 }
@@ -848,14 +864,14 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
         const long long nc = fem_nchunkcta(n), nt = fem_ntile(n), NH = nc * FT;
         if (nt > (long long)TOPT * TOP_MAX_CHUNK) {
             set_error("hfl_fem_p1_solve: %lld nodes exceed the single-call limit of %lld; split the mesh across GPUs",
-                      (long long)n, (long long)TOPT * TOP_MAX_CHUNK * FTS * FS);
+                      (long long)n, (long long)TOPT * TOP_MAX_CHUNK * FTS1 * FS);
             return HFL_ERR_UNSUPPORTED;
         }
         double* rec = reinterpret_cast<double*>(d_ws);
         double* utop = rec + (size_t)REC * nt;
         double* wsrows = utop + nt;
         double* sheads = wsrows + 6 * (size_t)nt;
-        size_t top = (size_t)(REC + 1 + 6 + 3 * FT) * nt;
+        size_t top = (size_t)(REC + 1 + 6 + 3 * FT1) * nt;
         top += top & 1;
         double* hrow = rec + top;
         double* edge = hrow + 4 * (size_t)NH;
@@ -873,10 +889,10 @@ static int fem_solve_impl(FemArgs a, int R, int coarse_solver, double* d_u, doub
         if (a.aq != nullptr) fem_chunk_reduce_kernel<true><<<grid0, FT, 0, s>>>(a, hrow, edge);
         else if (a.exact_rowsum) fem_chunk_reduce_kernel<false, true><<<grid0, FT, 0, s>>>(a, hrow, edge);
         else fem_chunk_reduce_kernel<false><<<grid0, FT, 0, s>>>(a, hrow, edge);
-        fem_heads_reduce_kernel<<<grid1, FT, 0, s>>>(hrow, edge, NH, rec, sheads, a.ws_stride);
+        fem_heads_reduce_kernel<<<grid1, FT1, 0, s>>>(hrow, edge, NH, rec, sheads, a.ws_stride);
         if (top_in_smem) fem_top_kernel<true><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
         else fem_top_kernel<false><<<dim3(1, R), TOPT, top_smem, s>>>(rec, (int)nt, S, wsrows, utop, a.ws_stride);
-        fem_heads_backsub_kernel<<<grid1, FT, 0, s>>>(hrow, NH, utop, (int)nt, sheads, uh, a.ws_stride);
+        fem_heads_backsub_kernel<<<grid1, FT1, 0, s>>>(hrow, NH, utop, (int)nt, sheads, uh, a.ws_stride);
         if (a.aq != nullptr) fem_chunk_backsub_kernel<true><<<grid0, FT, 0, s>>>(a, uh, d_u, nullptr);
         else if (a.exact_rowsum) fem_chunk_backsub_kernel<false, true><<<grid0, FT, 0, s>>>(a, uh, d_u, d_iface4);
         else fem_chunk_backsub_kernel<false><<<grid0, FT, 0, s>>>(a, uh, d_u, d_iface4);
