@@ -156,11 +156,11 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             rank = k + 1;
             lt_sync(team);
         }
+        // No CTA barrier here: a team's solves need only its own factor (perm / invl / L were published by the team
+        // barrier that ends every pivot step), so the team that finishes its factorisation first starts solving while
+        // the other is still factorising.  The other team's rank (element status) is read after the CTA barrier that
+        // follows the solves.
         if (row == 0) *rank_s = rank;
-        __syncthreads();
-        const bool ok = rank >= 1 && *rank_other >= 1;
-        if (threadIdx.x == 0 && a.status != nullptr) a.status[e] = ok ? 0 : 1;
-        if (!ok) ++nfail;
 
         for (int r0 = 0; r0 < R; r0 += LT) {
             const int r = r0 + row;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                     if (pk < NHc) {
                         if (a.forcing == HFL_FORCING_SINE) {
                             double sj, cj;
-                            sincospi(tb * (double)(2 * pk + 1), &sj, &cj);
+                            sincospi_base(tb * (double)(2 * pk + 1), &sj, &cj);     // Taylor below 2^-7 (any fine mesh)
                             b = amp * (team == 0 ? cj : sj);
                         } else {
                             const double fp = a.f[((long long)r * N + NHc + pk) * a.E + e];
@@ -223,9 +223,26 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                 double* w = wbuf + (size_t)r * M;
 #pragma unroll
                 for (int q = 0; q < LMAXMA; ++q)
-                    if (q < MA) w[2 * q + team] = ok ? wq[q] : (q == 0 ? gpar : 0.0);   // P:171-176 fallback: linear interpolant
+                    if (q < MA) w[2 * q + team] = (rank >= 1) ? wq[q] : (q == 0 ? gpar : 0.0);
             }
             __syncthreads();
+            const bool ok = rank >= 1 && *rank_other >= 1;
+            if (!ok) {      // P:171-176 fallback: linear interpolant of the nodal values, both parities (CTA-uniform branch)
+                for (int r = r0 + row; r < min(R, r0 + LT); r += LT) {
+                    double ul = a.u[(long long)r * (a.E + 1) + e], ur = a.u[(long long)r * (a.E + 1) + e + 1];
+                    if (a.bc2 != nullptr) {
+                        ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
+                        ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;
+                    }
+                    double* w = wbuf + (size_t)r * M;
+                    for (int q = 0; q < MA; ++q) w[2 * q + team] = (q == 0) ? (team == 0 ? 0.5 * (ul + ur) : 0.5 * (ur - ul)) : 0.0;
+                }
+                __syncthreads();
+            }
+            if (r0 == 0) {
+                if (threadIdx.x == 0 && a.status != nullptr) a.status[e] = ok ? 0 : 1;
+                if (!ok) ++nfail;
+            }
             const int rb = min(LT, R - r0);
             if (a.coef != nullptr)
                 for (int idx = threadIdx.x; idx < rb * M; idx += 2 * LT)
