@@ -146,7 +146,8 @@ __device__ __forceinline__ int ldl_solve_skip(double (&A)[n * (n + 1) / 2], doub
 // keeps its register budget).
 template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true>
 #ifndef HFL_DUAL_SMALL_MINB
-#define HFL_DUAL_SMALL_MINB 2      // 254 registers, no spills: 3 CTAs per SM (168 registers) spilled the prefetched nodal data, 1.01 -> 0.77 ms at 1e7 elements
+#define HFL_DUAL_SMALL_MINB 3      // 168 registers, no spills since the Horner / Taylor epilogue (round 2): 0.645 against 0.72 ms per 1e7 elements
+                                   // at 2 CTAs (254 registers); 4 CTAs (128 registers) spill and run at 0.89 ms.  Round 1's epilogue spilled at 3.
 #endif
 __global__ void __launch_bounds__(kThreads, NHD > 0 ? HFL_DUAL_SMALL_MINB : min_ctas(M, ERR, COEF))
 lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
