@@ -149,8 +149,11 @@ __global__ void __launch_bounds__(GT, 3) general_kernel(const GeneralArgs g) {
 
 // F = 2 FH compile-time: fine rows evaluated in Horner form, staged in 128-byte-swizzled shared memory and written by one
 // TMA bulk tensor store per 16-column box and CTA (the store path of the Poisson kernel).  Gram formation as above.
+// CTAs per SM the register budget is sized for: the packed (M-2) x (M-2) Gram matrix lives in registers.  M = 9: 126
+// registers without spills at 4 CTAs (1.92 ms per 1e7 elements; 2.27 ms at 3 CTAs / 160 registers, 3.5 ms at 5 with spills).
+__host__ __device__ constexpr int general_minb(int M) { return M <= 9 ? 4 : (M <= 10 ? 3 : 2); }
 template <int M, int FH>
-__global__ void __launch_bounds__(GT, 3) general_fast_kernel(const GeneralArgs g, const __grid_constant__ GeneralFineTables<M, FH> ft,
+__global__ void __launch_bounds__(GT, general_minb(M)) general_fast_kernel(const GeneralArgs g, const __grid_constant__ GeneralFineTables<M, FH> ft,
                                                               const __grid_constant__ CUtensorMap tmap) {
     constexpr int m = M - 2, F = 2 * FH, KE = (M + 1) / 2, KO = M / 2;
     extern __shared__ __align__(1024) unsigned char gsm_raw[];
