@@ -14,6 +14,7 @@ static std::atomic<int> g_opt_debug{0};
 static std::atomic<int> g_opt_dual_team{0};
 static std::atomic<int> g_opt_top_smem_kb{227};
 static std::atomic<int> g_opt_peer_spin_log2{24};
+static std::atomic<int> g_opt_dual_reuse{1};
 static std::atomic<int> g_sm_count{0};
 
 void set_error(const char* fmt, ...) {
@@ -28,6 +29,7 @@ int get_option_debug() { return g_opt_debug.load(); }
 int get_option_dual_team() { return g_opt_dual_team.load(); }
 int get_option_top_smem_kb() { return g_opt_top_smem_kb.load(); }
 int get_option_peer_spin_log2() { return g_opt_peer_spin_log2.load(); }
+int get_option_dual_reuse() { return g_opt_dual_reuse.load(); }
 
 int sm_count() {
     int v = g_sm_count.load();
@@ -100,6 +102,13 @@ extern "C" int hfl_set_option(const char* key, int value) {
     if (strcmp(key, "peer_spin_log2") == 0) {
         HFL_REQUIRE(value >= 4 && value <= 40, "peer_spin_log2 must be 4..40");
         g_opt_peer_spin_log2.store(value);
+        return HFL_OK;
+    }
+    // left-looking dual kernel: 1 = keep the factor of the previous element while K + tau J is the same floating-point
+    // matrix (tau below half an ulp of every diagonal entry); 0 = factorise every element (same results, bit for bit)
+    if (strcmp(key, "dual_reuse_factor") == 0) {
+        HFL_REQUIRE(value == 0 || value == 1, "dual_reuse_factor must be 0 or 1");
+        g_opt_dual_reuse.store(value);
         return HFL_OK;
     }
     if (strcmp(key, "primal_debug") == 0) {

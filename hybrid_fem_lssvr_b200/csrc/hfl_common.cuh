@@ -19,6 +19,7 @@ int get_option_debug();
 int get_option_dual_team();
 int get_option_top_smem_kb();
 int get_option_peer_spin_log2();
+int get_option_dual_reuse();
 int sm_count();
 
 #define HFL_CUDA_CHECK(expr)                                                            \

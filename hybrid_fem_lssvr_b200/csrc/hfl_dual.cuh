@@ -37,6 +37,7 @@ struct DualParityArgs {
     const double* Vt;       // [M][F]
     double* spill;          // left-looking kernel: global scratch for L columns kc.. (per CTA and team)
     int kc;                 // L columns held in shared memory
+    int reuse;              // left-looking kernel: keep the factor while the element matrix is bitwise unchanged
 };
 
 // hfl_dual_parity.cu (left-looking parity kernel); returns false when the shape is not covered (nh > 96 or not

@@ -129,15 +129,33 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
     const double kdiag = live_row ? __ldg(Kp + row * nh + row) : 0.0;
     const double* vht = vh + team * MAPT * nhp;
     const double* crow = Lc + (stores ? row : 0);      // this row's entries of the columns of L
+    // this row's entry of column p of A (the table is symmetric) or, for an extra row, of C^T: abase[p * astride]
+    const double* abase = live_row ? Kp + row : (ext_live ? Cp + q_ext : Kp);
+    const int astride = live_row ? nh : (ext_live ? MA : 0);
+    const bool active = live_row || ext_live;
+    // Reuse of the factor.  tau enters A only as fl(K_ii + tau) on the collocation rows: while tau stays below half an
+    // ulp of the smallest of those K_ii, every element sees the SAME floating-point matrix, so L, the pivot order and
+    // G of the previous element are bit for bit what a new factorisation would produce.  thr_same = min K_ii 2^-54.
+    dval[row] = (live_row && row < NHc) ? kdiag : 1.7976931348623157e308;
+    lt_sync(team);
+    double kmin = 1.7976931348623157e308;
+    for (int i = 0; i < NHc; ++i) kmin = fmin(kmin, dval[i]);
+    const double thr_same = pa.reuse ? kmin * 5.551115123125783e-17 : -1.0;     // 2^-54
+    bool cached = false;
+    int rank = 0;
+    lt_sync(team);
 
     for (long long e = blockIdx.x; e < a.E; e += gridDim.x) {
         const double xl = a.nodes[e], xr = a.nodes[e + 1];
         const double h = xr - xl, h2 = h * h;
         const double isig = 0.25 * h2, th = 0.5 * (h2 * h2) * a.c_tau;
+        const bool same = th < thr_same;          // team-uniform (every thread holds the same th and threshold)
+        if (!(cached && same)) {
+        cached = same;
         double dii = live_row ? kdiag + (row < NHc ? th : 0.0) : 0.0;    // running diagonal entry of this row
         bool alive = live_row;
         double dmax0 = 0.0;
-        int rank = 0;
+        rank = 0;
         // red / dval buffer 0 are free: their last readers passed the CTA barrier that ended the previous element
         lt_publish_key(lt_key(alive, dii, row), red, row);
         dval[row] = dii;
@@ -154,9 +172,8 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             if (!(vkey > eps_tol * dmax0)) break;
             const double v = dval[buf * LT + p];       // the pivot: running diagonal of row p (>= vkey > 0)
             // this row's entry of column p of the current Schur complement (for an extra row: of C^T), two chains
-            double a0 = 0.0, a1 = 0.0;
-            if (live_row) a0 = __ldg(Kp + p * nh + row) + ((row == p && row < NHc) ? th : 0.0);   // symmetric table
-            else if (ext_live) a0 = __ldg(Cp + p * MA + q_ext);
+            // (the pivot row itself needs no entry: its Schur complement entry IS the running diagonal v)
+            double a0 = __ldg(abase + p * astride), a1 = 0.0;
             const double* cp = Lc + p;
             const int ks = min(k, kc);             // columns held in shared memory
             int j = 0;
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                 a1 = fma(-g[stores ? row : 0], g[p], a1);
             }
             const double il = rsqrt(v);
-            const double l = (alive || ext) ? (a0 + a1) * il : 0.0;
+            const double l = (row == p) ? v * il : (((alive || ext_live) && active) ? (a0 + a1) * il : 0.0);
             if (stores) {
                 if (k < kc) Lc[k * LDL + row] = l;
                 else Lg[(size_t)(k - kc) * LDL + row] = l;
@@ -213,6 +230,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             }
         }
         lt_sync(team);
+        }
         // No CTA barrier here: a team's right-hand sides need only its own G, so the team that finishes first starts
         // while the other is still factorising.  The other team's rank (element status) is read after the CTA barrier
         // that follows.
@@ -319,6 +337,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                 const double* od0 = eo + (size_t)nhp * RP;
                 for (int rr = threadIdx.x >> 5; rr < rb; rr += 2 * LT / 32) {
                     double* out = a.fine != nullptr ? a.fine + ((long long)(r0 + rr) * a.E + e) * F : nullptr;
+                    double esum = 0.0, emax = 0.0;
                     for (int i = lane; i < F; i += 32) {
                         const int ih = min(i, F - 1 - i);
                         const double ev = eo[ih * RP + rr], od = od0[ih * RP + rr];
@@ -329,8 +348,16 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                             const double xi = (double)(2 * i - (F - 1)) / (double)(F - 1);
                             const double d = s - sinpi(kf * fma(0.5 * h, xi, xc));
                             const double wgt = ((i == 0 || i == F - 1) ? 0.5 : 1.0) * h / (double)(F - 1);
-                            atomicAdd(eacc + 2 * (r0 + rr), wgt * d * d);
-                            atomic_max_nonneg(eacc + 2 * (r0 + rr) + 1, fabs(d));
+                            esum = fma(wgt * d, d, esum);
+                            emax = fmax(emax, fabs(d));
+                        }
+                    }
+                    if (a.want_err) {      // one shared-memory update per warp and right-hand side
+                        esum = warp_sum(esum);
+                        emax = warp_max(emax);
+                        if (lane == 0) {
+                            atomicAdd(eacc + 2 * (r0 + rr), esum);
+                            atomic_max_nonneg(eacc + 2 * (r0 + rr) + 1, emax);
                         }
                     }
                 }
@@ -362,6 +389,7 @@ static int launch_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cu
     if (kc > pa.nh) kc = pa.nh;
     pa.kc = kc;
     pa.ldh = LDL;
+    pa.reuse = get_option_dual_reuse();
     const size_t smem = 2 * lt_team_bytes(kc) + common;
     if (smem > (size_t)max_smem) return HFL_ERR_UNSUPPORTED;
     HFL_CUDA_CHECK(cudaFuncSetAttribute(dual_parity_left_kernel<MAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -183,3 +183,36 @@ def test_team_kernel_small_system():
     ref = oracle_coef(nodes, u, M, 1e4, N, k=1.0)
     assert not status.any()
     assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL and rel(fine2, kkt.evaluate_fine(ref, 32)) <= TOL
+
+
+@pytest.mark.parametrize('mesh', ['fine', 'mixed'])
+def test_factor_reuse_is_bitwise(mesh):
+    """Left-looking kernel: while tau stays below half an ulp of every diagonal entry the element matrix K + tau J is
+    the same floating-point matrix, and the kernel keeps the factor of the previous element.  Same bits as
+    factorising every element ('dual_reuse_factor' = 0), on a fine mesh (every element after a CTA's first reuses)
+    and on a mesh that alternates coarse and fine elements (the cache must be dropped and rebuilt)."""
+    E, N, F, M, gamma = 3001, 128, 32, 13, 1e4           # more elements than resident CTAs: several per CTA
+    rng = np.random.default_rng(5)
+    w = rng.uniform(0.5e-4, 1.5e-4, E)
+    if mesh == 'mixed':
+        w[rng.uniform(size=E) < 0.3] = 2e-2
+    nodes = 0.1 + np.concatenate([[0.0], np.cumsum(w)])
+    ks = np.array([1.0, 3.0, 7.0])
+    u = np.stack([np.sin(k * np.pi * nodes) for k in ks])
+    out = {}
+    for reuse in (1, 0):
+        batch.set_option('dual_reuse_factor', reuse)
+        try:
+            out[reuse] = batch.lssvr_dual_multi(dev(nodes), dev(u), dev(ks), M, gamma, N=N, F=F, want_fine=True, want_status=True)
+            torch.cuda.synchronize()
+        finally:
+            batch.set_option('dual_reuse_factor', 1)
+    for x, y in zip(out[1], out[0]):
+        assert torch.equal(x, y)
+    assert not out[1][2].cpu().numpy().any()
+    # and the answer is the oracle's (sample of elements, fine ones)
+    fine_el = np.nonzero(w < 1e-3)[0][:6]
+    for e in fine_el:
+        ref = oracle_coef(nodes[e:e + 2], u[1][e:e + 2], M, gamma, N, k=ks[1])
+        fp = kkt.evaluate_fine(ref, F)
+        assert rel(out[1][1][1, e:e + 1].cpu().numpy(), fp) <= TOL
