@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                 if (want_fine) {
                     // this parity's share of u at the first half of the fine points, 8 points at a time (entries q >= MA of
                     // wq and of the table are zero)
-                    double* eor = eo + (size_t)team * nhp * RP + row;
-                    for (int i0 = 0; i0 < nhp; i0 += 8) {
+                    double* eor = eo + team * nhp * RP + row;        // rows nhalf..nhp-1 are padding (zeros from the table)
+                    for (int i0 = 0; i0 < nhp; i0 += 8, eor += 8 * RP) {
                         double acc[8];
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
@@ -306,8 +306,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                             }
                         }
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            if (i0 + jj < nhalf) eor[(i0 + jj) * RP] = acc[jj];
+                        for (int jj = 0; jj < 8; ++jj) eor[jj * RP] = acc[jj];
                     }
                 }
             }
@@ -332,32 +331,37 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             const int rb = min(LT, R - r0);
             if (want_fine) {
                 // one warp per right-hand side, lanes along the fine points: coalesced rows, no index division
-                const double xc = 0.5 * (xl + xr);
-                const int lane = threadIdx.x & 31;
-                const double* od0 = eo + (size_t)nhp * RP;
-                for (int rr = threadIdx.x >> 5; rr < rb; rr += 2 * LT / 32) {
-                    double* out = a.fine != nullptr ? a.fine + ((long long)(r0 + rr) * a.E + e) * F : nullptr;
-                    double esum = 0.0, emax = 0.0;
-                    for (int i = lane; i < F; i += 32) {
-                        const int ih = min(i, F - 1 - i);
-                        const double ev = eo[ih * RP + rr], od = od0[ih * RP + rr];
-                        const double s = (i == ih) ? ev + od : ev - od;
-                        if (out != nullptr) out[i] = s;
-                        if (a.want_err) {
-                            const double kf = a.kf ? a.kf[r0 + rr] : a.k_scalar;
-                            const double xi = (double)(2 * i - (F - 1)) / (double)(F - 1);
-                            const double d = s - sinpi(kf * fma(0.5 * h, xi, xc));
-                            const double wgt = ((i == 0 || i == F - 1) ? 0.5 : 1.0) * h / (double)(F - 1);
-                            esum = fma(wgt * d, d, esum);
-                            emax = fmax(emax, fabs(d));
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                const long long row_step = (long long)(2 * LT / 32) * a.E * F;
+                for (int i0 = 0; i0 < F; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool valid = i < F;
+                    const int ih = valid ? min(i, F - 1 - i) : 0;
+                    const bool mirrored = i != ih;
+                    const double* pe = eo + ih * RP;
+                    const double* po = pe + nhp * RP;
+                    if (a.fine != nullptr && valid) {
+                        double* out = a.fine + ((long long)(r0 + warp) * a.E + e) * F + i;
+                        for (int rr = warp; rr < rb; rr += 2 * LT / 32, out += row_step) {
+                            const double od = po[rr];
+                            *out = pe[rr] + (mirrored ? -od : od);
                         }
                     }
-                    if (a.want_err) {      // one shared-memory update per warp and right-hand side
-                        esum = warp_sum(esum);
-                        emax = warp_max(emax);
-                        if (lane == 0) {
-                            atomicAdd(eacc + 2 * (r0 + rr), esum);
-                            atomic_max_nonneg(eacc + 2 * (r0 + rr) + 1, emax);
+                    if (a.want_err) {
+                        const double xc = 0.5 * (xl + xr);
+                        const double xi = (double)(2 * i - (F - 1)) / (double)(F - 1);
+                        const double wgt = valid ? ((i == 0 || i == F - 1) ? 0.5 : 1.0) * h / (double)(F - 1) : 0.0;
+                        for (int rr = warp; rr < rb; rr += 2 * LT / 32) {
+                            const double od = po[rr];
+                            const double sv = pe[rr] + (mirrored ? -od : od);
+                            const double kf = a.kf ? a.kf[r0 + rr] : a.k_scalar;
+                            const double d = valid ? sv - sinpi(kf * fma(0.5 * h, xi, xc)) : 0.0;
+                            const double esum = warp_sum(wgt * d * d);      // one shared-memory update per warp and right-hand side
+                            const double emax = warp_max(fabs(d));
+                            if (lane == 0) {
+                                atomicAdd(eacc + 2 * (r0 + rr), esum);
+                                atomic_max_nonneg(eacc + 2 * (r0 + rr) + 1, emax);
+                            }
                         }
                     }
                 }
