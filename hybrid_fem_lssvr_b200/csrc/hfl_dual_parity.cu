@@ -75,10 +75,88 @@ __device__ __forceinline__ unsigned long long lt_key(bool alive, double dii, int
     return (alive && dii > 0.0) ? (((unsigned long long)__double_as_longlong(dii) & ~127ull) | (unsigned long long)(127 - row)) : 0ull;
 }
 
+// Right-hand side r of element e, parity par: w = G b.  b is built on the fly per pivot k: collocation rows carry the
+// (anti)symmetrised forcing (pc[k] = 2 p + 1 > 0), the constraint row (pc[k] < 0) the nodal value gpar.
+template <int MAPT>
+__device__ __forceinline__ double lt_rhs_weights(const DualArgs& a, int par, int r, long long e, double xl, double xr, double h,
+                                                 const double* bcv, const double* Gs, const double* Gg, int kc, int rank,
+                                                 const double* pc, const int* perm, double (&wq)[MAPT]) {
+    const int N = a.N, NHc = N / 2;
+    const double kf = a.kf ? a.kf[r] : a.k_scalar;
+    const double kk = (kf * 3.14159265358979323846) * (kf * 3.14159265358979323846);
+    double ul = a.u[(long long)r * (a.E + 1) + e], ur = a.u[(long long)r * (a.E + 1) + e + 1];
+    if (a.bc2 != nullptr) {     // bcv = {bc_left, bc_right, x_first, x_last, 1 / (x_last - x_first)}
+        ul += (bcv[0] * (bcv[3] - xl) + bcv[1] * (xl - bcv[2])) * bcv[4];
+        ur += (bcv[0] * (bcv[3] - xr) + bcv[1] * (xr - bcv[2])) * bcv[4];
+    }
+    const double gpar = par == 0 ? 0.5 * (ul + ur) : 0.5 * (ur - ul);
+    double S = 0.0, C = 0.0;
+    const bool sine = a.forcing == HFL_FORCING_SINE;
+    if (sine) sincospi(kf * (0.5 * (xl + xr)), &S, &C);
+    const double isig = 0.25 * (h * h);
+    const double amp = isig * kk * (par == 0 ? S : C);
+    const double tb = kf * h * (0.5 / (double)(N - 1));       // base angle / pi
+    const bool tiny = fabs(tb * (double)(N - 1)) < 0.0078125;  // every angle below 2^-7: Taylor (any fine mesh)
+    const double xb = 3.14159265358979323846 * tb;
+    auto rhs_entry = [&](int k) -> double {
+        const double c = pc[k];
+        if (c < 0.0) return gpar;
+        if (sine) {
+            if (tiny) {
+                const double x = xb * c, z = x * x;
+                if (par == 0)
+                    return amp * fma(z, fma(z, fma(z, fma(z, 2.48015873015873e-05, -1.388888888888889e-03), 4.1666666666666664e-02), -0.5), 1.0);
+                return amp * (x * fma(z, fma(z, fma(z, -1.984126984126984e-04, 8.333333333333333e-03), -1.6666666666666666e-01), 1.0));
+            }
+            double sj, cj;
+            sincospi(tb * c, &sj, &cj);
+            return amp * (par == 0 ? cj : sj);
+        }
+        const int pk = perm[k];
+        const double fp = a.f[((long long)r * N + NHc + pk) * a.E + e];
+        const double fm = a.f[((long long)r * N + NHc - 1 - pk) * a.E + e];
+        return isig * (par == 0 ? 0.5 * (fp + fm) : 0.5 * (fp - fm));
+    };
+#pragma unroll
+    for (int q = 0; q < MAPT; ++q) wq[q] = 0.0;
+    const int ks = min(rank, kc);
+    for (int k = 0; k < ks; ++k) lt_axpy<MAPT>(wq, Gs + k * LDL, rhs_entry(k));
+    for (int k = kc; k < rank; ++k) lt_axpy<MAPT>(wq, Gg + (size_t)(k - kc) * LDL, rhs_entry(k));
+    return gpar;
+}
+
+// This parity's share of u at 8 of the first half of the fine points (entries q >= MA of wq and of the table are zero).
+template <int MAPT>
+__device__ __forceinline__ void lt_half_points(const double (&wq)[MAPT], const double* vt, int nhp, double (&acc)[8]) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
+#pragma unroll
+    for (int q = 0; q < MAPT; ++q) {
+        const double2* vv = reinterpret_cast<const double2*>(vt + q * nhp);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const double2 t2 = vv[jj];
+            acc[2 * jj] = fma(wq[q], t2.x, acc[2 * jj]);
+            acc[2 * jj + 1] = fma(wq[q], t2.y, acc[2 * jj + 1]);
+        }
+    }
+}
+
 #ifndef HFL_DUAL_LEFT_MINB
 #define HFL_DUAL_LEFT_MINB 4      // <= 85 registers: 4 CTAs per SM
 #endif
 // MAPT: compile-time even bound on the coefficients per parity (extra rows of the factorisation, width of G).
+//
+// Two passes per CTA over its elements (a contiguous chunk of E / gridDim.x):
+//   STREAM (pa.reuse, no fused error norms): tau enters A only as fl(K_ii + tau) on the collocation rows; while tau
+//     stays below half an ulp of the smallest K_ii every such element sees the SAME floating-point matrix as tau = 0.
+//     The CTA factorises that matrix once and then streams the (element, right-hand side) pairs of all those elements
+//     through G without a single barrier: a pair of adjacent lanes per right-hand side (even / odd parity), w = G b in
+//     registers, half the fine points each, one shuffle to combine E +- O, 16-byte stores.  Bit for bit what a
+//     factorisation per element produces (tests/test_gpu_dual.py::test_factor_reuse_is_bitwise).
+//   TEAM: every other element (coarse meshes, or everything with pa.reuse = 0): factorise per element, 96 threads per
+//     parity, right-hand sides one per thread, combine through shared memory.  The factor of the previous element is
+//     still kept while consecutive elements share the matrix (pa.reuse with fused error norms).
 template <int MAPT>
 __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_kernel(const DualParityArgs pa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,18 +176,19 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
     unsigned long long* red = reinterpret_cast<unsigned long long*>(dval + 2 * LT);
     int* perm = reinterpret_cast<int*>(red + 8);
     int* rank_s = perm + LT;
-    double* Lg = pa.spill + ((size_t)blockIdx.x * 2 + team) * (size_t)(nh - kc) * LDL;   // columns kc.. (unused when kc = nh)
+    const size_t spill_team = (size_t)(nh - kc) * LDL;
+    double* Lg = pa.spill + ((size_t)blockIdx.x * 2 + team) * spill_team;   // columns kc.. (unused when kc = nh)
     double* eo = reinterpret_cast<double*>(smem_raw + 2 * team_bytes);     // [2][nhp][RP]: E / O of the first half of the fine points
     double* vh = eo + (size_t)2 * nhp * RP;                                  // [2][MAPT][nhp]: P_{2q+team}(xi_i), i < nhalf
     double* eacc = vh + (size_t)2 * MAPT * nhp;
+    double* bcv = eacc + 2 * R;                                              // {bc_left, bc_right, x_first, x_last, 1 / length}
     const int* rank_other = reinterpret_cast<const int*>(smem_raw + (1 - team) * team_bytes + ((size_t)kc * LDL + 4 * LT + 8) * 8) + LT;
     const bool want_fine = F > 0 && (a.fine != nullptr || a.want_err);
 
-    double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
-    if (a.bc2 != nullptr) {
-        bcl = a.bc2[0]; bcr = a.bc2[1];
-        x_first = a.nodes[0]; x_last = a.nodes[a.E];
-        invL = 1.0 / (x_last - x_first);
+    if (threadIdx.x == 0) {
+        double bl = 0.0, br = 0.0, xf = 0.0, xe = 1.0;
+        if (a.bc2 != nullptr) { bl = a.bc2[0]; br = a.bc2[1]; xf = a.nodes[0]; xe = a.nodes[a.E]; }
+        bcv[0] = bl; bcv[1] = br; bcv[2] = xf; bcv[3] = xe; bcv[4] = 1.0 / (xe - xf);
     }
     const double eps_tol = 2.220446049250313e-16 * (1.0 / 1024.0);
     for (int i = threadIdx.x; i < 2 * R; i += 2 * LT) eacc[i] = 0.0;
@@ -117,7 +196,6 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
         const int t = idx / (MAPT * nhp), rem = idx - t * (MAPT * nhp), q = rem / nhp, i = rem - q * nhp;
         vh[idx] = (q < pa.MA[t] && i < nhalf) ? __ldg(pa.Vt + (size_t)(2 * q + t) * F + i) : 0.0;
     }
-    __syncthreads();
     int nfail = 0;
     const double* Kp = pa.Kp[team];
     const double* Cp = pa.Cp[team];
@@ -133,154 +211,207 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
     const double* abase = live_row ? Kp + row : (ext_live ? Cp + q_ext : Kp);
     const int astride = live_row ? nh : (ext_live ? MA : 0);
     const bool active = live_row || ext_live;
-    // Reuse of the factor.  tau enters A only as fl(K_ii + tau) on the collocation rows: while tau stays below half an
-    // ulp of the smallest of those K_ii, every element sees the SAME floating-point matrix, so L, the pivot order and
-    // G of the previous element are bit for bit what a new factorisation would produce.  thr_same = min K_ii 2^-54.
+    // thr_same = min K_ii 2^-54 over the collocation rows of both parities: fl(K_ii + tau) = K_ii below it
     dval[row] = (live_row && row < NHc) ? kdiag : 1.7976931348623157e308;
-    lt_sync(team);
+    __syncthreads();
     double kmin = 1.7976931348623157e308;
-    for (int i = 0; i < NHc; ++i) kmin = fmin(kmin, dval[i]);
+    {
+        const double* d0 = reinterpret_cast<const double*>(smem_raw) + (size_t)kc * LDL + 2 * LT;
+        const double* d1 = reinterpret_cast<const double*>(smem_raw + team_bytes) + (size_t)kc * LDL + 2 * LT;
+        for (int i = 0; i < NHc; ++i) kmin = fmin(kmin, fmin(d0[i], d1[i]));
+    }
     const double thr_same = pa.reuse ? kmin * 5.551115123125783e-17 : -1.0;     // 2^-54
     bool cached = false;
     int rank = 0;
-    lt_sync(team);
+    __syncthreads();
 
-    for (long long e = blockIdx.x; e < a.E; e += gridDim.x) {
-        const double xl = a.nodes[e], xr = a.nodes[e + 1];
+    bool stream_pass = pa.reuse && !a.want_err;       // CTA-uniform
+    bool streamed = false;                            // elements below thr_same were handled by the STREAM pass
+    // this CTA's elements: a contiguous chunk (rows (r, e), (r, e + 1), ... of the fine grid are adjacent in memory)
+    const long long per_cta = (a.E + gridDim.x - 1) / gridDim.x;
+    const long long e_first = (long long)blockIdx.x * per_cta;
+    const long long e_end = e_first + per_cta < a.E ? e_first + per_cta : a.E;
+    long long e = e_first;
+    while ((stream_pass && e_first < e_end) || e < e_end) {
+        double xl = 0.0, xr = 1.0;
+        if (!stream_pass) { xl = a.nodes[e]; xr = a.nodes[e + 1]; }
         const double h = xr - xl, h2 = h * h;
-        const double isig = 0.25 * h2, th = 0.5 * (h2 * h2) * a.c_tau;
-        const bool same = th < thr_same;          // team-uniform (every thread holds the same th and threshold)
+        const double th = stream_pass ? 0.0 : 0.5 * (h2 * h2) * a.c_tau;
+        const bool same = th < thr_same;          // CTA-uniform (every thread holds the same th and threshold)
+        if (!stream_pass && streamed && same) { ++e; continue; }
         if (!(cached && same)) {
-        cached = same;
-        double dii = live_row ? kdiag + (row < NHc ? th : 0.0) : 0.0;    // running diagonal entry of this row
-        bool alive = live_row;
-        double dmax0 = 0.0;
-        rank = 0;
-        // red / dval buffer 0 are free: their last readers passed the CTA barrier that ended the previous element
-        lt_publish_key(lt_key(alive, dii, row), red, row);
-        dval[row] = dii;
-        lt_sync(team);
-        for (int k = 0; k < nh; ++k) {
-            const int buf = k & 1;
-            const unsigned long long* rk = red + 4 * buf;
-            const unsigned long long k0 = rk[0], k1 = rk[1], k2 = rk[2];
-            unsigned long long key = k0 > k1 ? k0 : k1;
-            key = key > k2 ? key : k2;
-            const double vkey = __longlong_as_double((long long)(key & ~127ull));
-            const int p = 127 - (int)(key & 127ull);
-            if (k == 0) dmax0 = vkey;
-            if (!(vkey > eps_tol * dmax0)) break;
-            const double v = dval[buf * LT + p];       // the pivot: running diagonal of row p (>= vkey > 0)
-            // this row's entry of column p of the current Schur complement (for an extra row: of C^T), two chains
-            // (the pivot row itself needs no entry: its Schur complement entry IS the running diagonal v)
-            double a0 = __ldg(abase + p * astride), a1 = 0.0;
-            const double* cp = Lc + p;
-            const int ks = min(k, kc);             // columns held in shared memory
-            int j = 0;
-#pragma unroll 2
-            for (; j + 1 < ks; j += 2) {
-                a0 = fma(-crow[j * LDL], cp[j * LDL], a0);
-                a1 = fma(-crow[(j + 1) * LDL], cp[(j + 1) * LDL], a1);
-            }
-            if (j < ks) a0 = fma(-crow[j * LDL], cp[j * LDL], a0);
-            for (j = kc; j < k; ++j) {             // spilled columns
-                const double* g = Lg + (size_t)(j - kc) * LDL;
-                a1 = fma(-g[stores ? row : 0], g[p], a1);
-            }
-            const double il = rsqrt(v);
-            const double l = (row == p) ? v * il : (((alive || ext_live) && active) ? (a0 + a1) * il : 0.0);
-            if (stores) {
-                if (k < kc) Lc[k * LDL + row] = l;
-                else Lg[(size_t)(k - kc) * LDL + row] = l;
-            }
-            dii = fma(-l, l, dii);
-            if (row == p) {
-                alive = false; perm[k] = p; invl[k] = il;
-                pc[k] = p < NHc ? (double)(2 * p + 1) : -1.0;
-            }
-            rank = k + 1;
-            lt_publish_key(lt_key(alive, dii, row), red + 4 * (buf ^ 1), row);
-            dval[(buf ^ 1) * LT + row] = dii;
+            cached = same;
+            double dii = live_row ? kdiag + (row < NHc ? th : 0.0) : 0.0;    // running diagonal entry of this row
+            bool alive = live_row;
+            double dmax0 = 0.0;
+            rank = 0;
+            // red / dval buffer 0 are free: their last readers passed the CTA barrier that ended the previous element
+            lt_publish_key(lt_key(alive, dii, row), red, row);
+            dval[row] = dii;
             lt_sync(team);
-        }
-        if (row == 0) *rank_s = rank;
-        // G L = Y^T, one extra row per thread, in place (only the thread's own entries are written; L, perm and invl were
-        // published by the team barrier that ends every pivot step)
-        if (ext_live) {
-            for (int k = rank - 1; k >= 0; --k) {
-                double acc, acc1 = 0.0;
-                if (k < kc) {
-                    const double* lk = Lc + k * LDL;
-                    acc = lk[row];
-                    const int js = min(rank, kc);
-                    int j = k + 1;
-                    for (; j + 1 < js; j += 2) {
-                        acc = fma(-lk[perm[j]], crow[j * LDL], acc);
-                        acc1 = fma(-lk[perm[j + 1]], crow[(j + 1) * LDL], acc1);
+            for (int k = 0; k < nh; ++k) {
+                const int buf = k & 1;
+                const unsigned long long* rk = red + 4 * buf;
+                const unsigned long long k0 = rk[0], k1 = rk[1], k2 = rk[2];
+                unsigned long long key = k0 > k1 ? k0 : k1;
+                key = key > k2 ? key : k2;
+                const double vkey = __longlong_as_double((long long)(key & ~127ull));
+                const int p = 127 - (int)(key & 127ull);
+                if (k == 0) dmax0 = vkey;
+                if (!(vkey > eps_tol * dmax0)) break;
+                const double v = dval[buf * LT + p];       // the pivot: running diagonal of row p (>= vkey > 0)
+                // this row's entry of column p of the current Schur complement (for an extra row: of C^T), two chains
+                // (the pivot row itself needs no entry: its Schur complement entry IS the running diagonal v)
+                double a0 = __ldg(abase + p * astride), a1 = 0.0;
+                const double* cp = Lc + p;
+                const int ks = min(k, kc);             // columns held in shared memory
+                int j = 0;
+#pragma unroll 2
+                for (; j + 1 < ks; j += 2) {
+                    a0 = fma(-crow[j * LDL], cp[j * LDL], a0);
+                    a1 = fma(-crow[(j + 1) * LDL], cp[(j + 1) * LDL], a1);
+                }
+                if (j < ks) a0 = fma(-crow[j * LDL], cp[j * LDL], a0);
+                for (j = kc; j < k; ++j) {             // spilled columns
+                    const double* g = Lg + (size_t)(j - kc) * LDL;
+                    a1 = fma(-g[stores ? row : 0], g[p], a1);
+                }
+                const double il = rsqrt(v);
+                const double l = (row == p) ? v * il : (((alive || ext_live) && active) ? (a0 + a1) * il : 0.0);
+                if (stores) {
+                    if (k < kc) Lc[k * LDL + row] = l;
+                    else Lg[(size_t)(k - kc) * LDL + row] = l;
+                }
+                dii = fma(-l, l, dii);
+                if (row == p) {
+                    alive = false; perm[k] = p; invl[k] = il;
+                    pc[k] = p < NHc ? (double)(2 * p + 1) : -1.0;
+                }
+                rank = k + 1;
+                lt_publish_key(lt_key(alive, dii, row), red + 4 * (buf ^ 1), row);
+                dval[(buf ^ 1) * LT + row] = dii;
+                lt_sync(team);
+            }
+            if (row == 0) *rank_s = rank;
+            // G L = Y^T, one extra row per thread, in place (only the thread's own entries are written; L, perm and invl
+            // were published by the team barrier that ends every pivot step)
+            if (ext_live) {
+                for (int k = rank - 1; k >= 0; --k) {
+                    double acc, acc1 = 0.0;
+                    if (k < kc) {
+                        const double* lk = Lc + k * LDL;
+                        acc = lk[row];
+                        const int js = min(rank, kc);
+                        int j = k + 1;
+                        for (; j + 1 < js; j += 2) {
+                            acc = fma(-lk[perm[j]], crow[j * LDL], acc);
+                            acc1 = fma(-lk[perm[j + 1]], crow[(j + 1) * LDL], acc1);
+                        }
+                        if (j < js) { acc = fma(-lk[perm[j]], crow[j * LDL], acc); ++j; }
+                        for (j = max(j, kc); j < rank; ++j) acc1 = fma(-lk[perm[j]], Lg[(size_t)(j - kc) * LDL + row], acc1);
+                        Lc[k * LDL + row] = (acc + acc1) * invl[k];
+                    } else {
+                        double* lk = Lg + (size_t)(k - kc) * LDL;
+                        acc = lk[row];
+                        for (int j = k + 1; j < rank; ++j) acc = fma(-lk[perm[j]], Lg[(size_t)(j - kc) * LDL + row], acc);
+                        lk[row] = acc * invl[k];
                     }
-                    if (j < js) { acc = fma(-lk[perm[j]], crow[j * LDL], acc); ++j; }
-                    for (j = max(j, kc); j < rank; ++j) acc1 = fma(-lk[perm[j]], Lg[(size_t)(j - kc) * LDL + row], acc1);
-                    Lc[k * LDL + row] = (acc + acc1) * invl[k];
-                } else {
-                    double* lk = Lg + (size_t)(k - kc) * LDL;
-                    acc = lk[row];
-                    for (int j = k + 1; j < rank; ++j) acc = fma(-lk[perm[j]], Lg[(size_t)(j - kc) * LDL + row], acc);
-                    lk[row] = acc * invl[k];
                 }
             }
+            lt_sync(team);
         }
-        lt_sync(team);
-        }
-        // No CTA barrier here: a team's right-hand sides need only its own G, so the team that finishes first starts
-        // while the other is still factorising.  The other team's rank (element status) is read after the CTA barrier
-        // that follows.
 
+        if (stream_pass) {
+            // ---- STREAM: every element of this CTA whose matrix is the tau = 0 matrix, a lane pair (l, l + 16) per right-hand side
+            stream_pass = false;
+            __syncthreads();                                   // both parities' G, pc, perm, rank
+            // parity per half-warp: the 128-bit shared loads of G and of the table (served a quarter-warp at a time) see
+            // one address each; the partner lane is 16 away
+            const int par = (threadIdx.x >> 4) & 1, pair = (threadIdx.x >> 5) * 16 + (threadIdx.x & 15);
+            const unsigned char* pb = smem_raw + par * team_bytes;
+            const double* Gs = reinterpret_cast<const double*>(pb) + goff;
+            const double* pc_p = reinterpret_cast<const double*>(pb) + (size_t)kc * LDL + LT;
+            const int* perm_p = reinterpret_cast<const int*>(pb + ((size_t)kc * LDL + 4 * LT + 8) * 8);
+            const int rank_p = perm_p[LT], rank_q = rank_other[0];
+            const double* Gg = pa.spill + ((size_t)blockIdx.x * 2 + par) * spill_team + goff;
+            const double* vt_p = vh + par * MAPT * nhp;
+            const int MA_p = pa.MA[par];
+            if (rank >= 1 && rank_q >= 1) {                    // CTA-uniform (rank / rank_q are the two teams' ranks)
+                streamed = true;
+                // task t = r * ne + j: consecutive lanes take consecutive elements of one right-hand side (coalesced
+                // loads of the nodal values, adjacent 256-byte rows of the fine grid)
+                const int ne = (int)(e_end - e_first);
+                const long long ntask = (long long)ne * R;
+                int r = pair / ne, j = pair % ne;
+                const int dr = LT / ne, dj = LT % ne;
+                const bool vec = (F % 16 == 0) && ((reinterpret_cast<size_t>(a.fine) & 15) == 0);
+                for (long long t0 = 0; t0 < ntask; t0 += LT) {
+                    const long long es = e_first + j;
+                    bool work = t0 + pair < ntask;
+                    double sxl = 0.0, sxr = 1.0;
+                    if (work) { sxl = a.nodes[es]; sxr = a.nodes[es + 1]; }
+                    const double sh = sxr - sxl, sh2 = sh * sh;
+                    work = work && (0.5 * (sh2 * sh2) * a.c_tau < thr_same);
+                    const unsigned mask = __ballot_sync(0xffffffffu, work);
+                    if (work) {
+                        double wq[MAPT];
+                        lt_rhs_weights<MAPT>(a, par, r, es, sxl, sxr, sh, bcv, Gs, Gg, kc, rank_p, pc_p, perm_p, wq);
+                        if (a.coef != nullptr) {
+                            double* w = a.coef + ((long long)r * a.E + es) * M;
+#pragma unroll
+                            for (int q = 0; q < MAPT; ++q)
+                                if (q < MA_p) w[2 * q + par] = wq[q];
+                        }
+                        if (r == 0 && par == 0 && a.status != nullptr) a.status[es] = 0;
+                        if (a.fine != nullptr && F > 0) {
+                            double* out = a.fine + ((long long)r * a.E + es) * F;
+                            for (int i0 = 0; i0 < nhp; i0 += 8) {
+                                double acc[8];
+                                lt_half_points<MAPT>(wq, vt_p + i0, nhp, acc);
+                                // even-parity lane: u(xi_i) = E + O at i = i0 + jj; odd-parity lane: u(-xi_i) = E - O at F - 1 - i
+#pragma unroll
+                                for (int jj = 0; jj < 8; ++jj) {
+                                    const double o = __shfl_xor_sync(mask, acc[jj], 16);
+                                    acc[jj] = par == 0 ? acc[jj] + o : o - acc[jj];
+                                }
+                                if (vec) {
+                                    if (par == 0) {
+#pragma unroll
+                                        for (int jj = 0; jj < 8; jj += 2)
+                                            *reinterpret_cast<double2*>(out + i0 + jj) = make_double2(acc[jj], acc[jj + 1]);
+                                    } else {
+#pragma unroll
+                                        for (int jj = 0; jj < 8; jj += 2)
+                                            *reinterpret_cast<double2*>(out + F - 2 - i0 - jj) = make_double2(acc[jj + 1], acc[jj]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int jj = 0; jj < 8; ++jj) {
+                                        const int i = i0 + jj;
+                                        if (i < nhalf && (par == 0 || F - 1 - i != i)) out[par == 0 ? i : F - 1 - i] = acc[jj];
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    r += dr; j += dj;
+                    if (j >= ne) { j -= ne; ++r; }
+                }
+            }
+            cached = false;       // the TEAM pass starts from its own factor (the tau = 0 one is not an element's)
+            __syncthreads();
+            continue;
+        }
+
+        // ---- TEAM: this element's right-hand sides, one per thread and parity.  No CTA barrier before them: a team's
+        // right-hand sides need only its own G, so the team that finishes first starts while the other is still
+        // factorising.  The other team's rank (element status) is read after the CTA barrier that follows.
         for (int r0 = 0; r0 < R; r0 += LT) {
             const int r = r0 + row;
             double gpar = 0.0;
             if (r < R) {
-                const double kf = a.kf ? a.kf[r] : a.k_scalar;
-                const double kk = (kf * 3.14159265358979323846) * (kf * 3.14159265358979323846);
-                double ul = a.u[(long long)r * (a.E + 1) + e], ur = a.u[(long long)r * (a.E + 1) + e + 1];
-                if (a.bc2 != nullptr) {
-                    ul += (bcl * (x_last - xl) + bcr * (xl - x_first)) * invL;
-                    ur += (bcl * (x_last - xr) + bcr * (xr - x_first)) * invL;
-                }
-                gpar = team == 0 ? 0.5 * (ul + ur) : 0.5 * (ur - ul);
-                double S = 0.0, C = 0.0;
-                const bool sine = a.forcing == HFL_FORCING_SINE;
-                if (sine) sincospi(kf * (0.5 * (xl + xr)), &S, &C);
-                const double amp = isig * kk * (team == 0 ? S : C);
-                const double tb = kf * h * (0.5 / (double)(N - 1));       // base angle / pi
-                const bool tiny = fabs(tb * (double)(N - 1)) < 0.0078125;  // every angle below 2^-7: Taylor (any fine mesh)
-                const double xb = 3.14159265358979323846 * tb;
-                // right-hand side entry of pivot k: collocation rows carry the (anti)symmetrised forcing, the last row
-                // the nodal constraint
-                auto rhs_entry = [&](int k) -> double {
-                    const double c = pc[k];
-                    if (c < 0.0) return gpar;
-                    if (sine) {
-                        if (tiny) {
-                            const double x = xb * c, z = x * x;
-                            if (team == 0)
-                                return amp * fma(z, fma(z, fma(z, fma(z, 2.48015873015873e-05, -1.388888888888889e-03), 4.1666666666666664e-02), -0.5), 1.0);
-                            return amp * (x * fma(z, fma(z, fma(z, -1.984126984126984e-04, 8.333333333333333e-03), -1.6666666666666666e-01), 1.0));
-                        }
-                        double sj, cj;
-                        sincospi(tb * c, &sj, &cj);
-                        return amp * (team == 0 ? cj : sj);
-                    }
-                    const int pk = perm[k];
-                    const double fp = a.f[((long long)r * N + NHc + pk) * a.E + e];
-                    const double fm = a.f[((long long)r * N + NHc - 1 - pk) * a.E + e];
-                    return isig * (team == 0 ? 0.5 * (fp + fm) : 0.5 * (fp - fm));
-                };
                 double wq[MAPT];
-#pragma unroll
-                for (int q = 0; q < MAPT; ++q) wq[q] = 0.0;
-                const int ks = min(rank, kc);
-                for (int k = 0; k < ks; ++k) lt_axpy<MAPT>(wq, Lc + k * LDL + goff, rhs_entry(k));
-                for (int k = kc; k < rank; ++k) lt_axpy<MAPT>(wq, Lg + (size_t)(k - kc) * LDL + goff, rhs_entry(k));
+                gpar = lt_rhs_weights<MAPT>(a, team, r, e, xl, xr, h, bcv, Lc + goff, Lg + goff, kc, rank, pc, perm, wq);
                 if (a.coef != nullptr) {
                     double* w = a.coef + ((long long)r * a.E + e) * M;
 #pragma unroll
@@ -288,23 +419,10 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                         if (q < MA) w[2 * q + team] = wq[q];
                 }
                 if (want_fine) {
-                    // this parity's share of u at the first half of the fine points, 8 points at a time (entries q >= MA of
-                    // wq and of the table are zero)
                     double* eor = eo + team * nhp * RP + row;        // rows nhalf..nhp-1 are padding (zeros from the table)
                     for (int i0 = 0; i0 < nhp; i0 += 8, eor += 8 * RP) {
                         double acc[8];
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
-#pragma unroll
-                        for (int q = 0; q < MAPT; ++q) {
-                            const double2* vv = reinterpret_cast<const double2*>(vht + q * nhp + i0);
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const double2 t2 = vv[jj];
-                                acc[2 * jj] = fma(wq[q], t2.x, acc[2 * jj]);
-                                acc[2 * jj + 1] = fma(wq[q], t2.y, acc[2 * jj + 1]);
-                            }
-                        }
+                        lt_half_points<MAPT>(wq, vht + i0, nhp, acc);
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) eor[jj * RP] = acc[jj];
                     }
@@ -368,6 +486,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             }
             __syncthreads();
         }
+        ++e;
     }
     if (a.err3 != nullptr) {
         __syncthreads();
@@ -386,7 +505,7 @@ static int launch_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cu
     const DualArgs& a = pa.d;
     if (lt_goff(pa.nh) + MAPT > LT) return HFL_ERR_UNSUPPORTED;            // block rows + extra rows: one thread each
     const int RB = a.R < LT ? a.R : LT, nhp = lt_nhalf_padded(a.F);
-    const size_t common = ((size_t)2 * nhp * (RB | 1) + (size_t)2 * MAPT * nhp + 2 * (size_t)a.R) * 8;
+    const size_t common = ((size_t)2 * nhp * (RB | 1) + (size_t)2 * MAPT * nhp + 2 * (size_t)a.R + 6) * 8;
     // as many columns of L in shared memory as keep 4 CTAs on an SM (56 KB each), between LT_KC_MIN and LT_KC_MAX
     int kc = pa.nh < LT_KC_MAX ? pa.nh : LT_KC_MAX;
     while (kc > LT_KC_MIN && 2 * lt_team_bytes(kc) + common > 56 * 1024) --kc;

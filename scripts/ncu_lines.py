@@ -13,8 +13,8 @@ for r in rows:
     if r[0] == 'Line No': hdr = r; continue
     if hdr is None or r[0] == '': continue
     iS = hdr.index('# Samples'); iI = hdr.index('Instructions Executed')
-    st = {h[6:]: int(r[i] or 0) for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h and i < len(r)}
-    out.append((fname, int(r[0]), r[1].strip()[:90], int(r[iI] or 0), int(r[iS] or 0), st))
+    st = {h[6:]: int(r[i] if r[i] not in ("", "-") else 0) for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h and i < len(r)}
+    out.append((fname, int(r[0]), r[1].strip()[:90], int(r[iI] if r[iI] not in ("", "-") else 0), int(r[iS] if r[iS] not in ("", "-") else 0), st))
 ti = sum(o[3] for o in out); ts = sum(o[4] for o in out)
 print('warp instructions %.1fM, samples %d' % (ti / 1e6, ts))
 for f, ln, src, n, s, st in out:
