@@ -232,10 +232,11 @@ def time_kernel_each(fn, reps):
     return ts[0], ts[len(ts) // 2]
 
 
-def dual_config4_record(dev, fp64_tflops, reps):
+def dual_config4_record(dev, fp64_tflops, hbm_peak, reps):
     """BASELINE configs[4]: dual form, N = 128 collocation points, R = 64 forcing frequencies sin(k pi x), k = 1..64, sharing
     one factorisation per element, Legendre degree 4 / 12 / 24 (M = 5 / 13 / 25).  Per (E, M): kernel time, RHS solves/s,
-    the flops the rank-revealing left-looking kernel executes (formula below) as a fraction of the measured FP64 FMA rate,
+    the time with the factor reuse switched off (every element factorised; same bits), the HBM fraction of the bytes it
+    must move, the flops it executes (formula below) as a fraction of the measured FP64 FMA rate,
     the achieved error against the primal KKT oracle on a sample (stated, not asserted: SURVEY.md fact 8), and the CPU
     port (oracle/dual.py, one LU solve per right-hand side) on a sample."""
     import numpy as np
@@ -257,13 +258,19 @@ def dual_config4_record(dev, fp64_tflops, reps):
             run = lambda: batch.lssvr_dual_multi(nodes, un, ks, Md, GAMMA, N=N, F=Fd, want_coef=False, want_fine=True)   # noqa: E731
             ms = time_kernel(run, max(3, reps // 4))
             _, fine, _ = run()
-            # executed flops per element: two parity blocks of nh = 65 rows, numerical rank r_p = number of basis functions
-            # of that parity (tau is below eps |K| on this mesh): left-looking factorisation r_p^2 nh each; per right-hand
-            # side two triangular solves (2 r_p^2), w = C^T z (2 r_p^2) and the fine grid (2 M F)
-            r_e, r_o = (Md - 1) // 2 + 1, (Md - 2) // 2 + 1
-            fl_fact = (r_e ** 2 + r_o ** 2) * (N // 2 + 1)
-            fl_rhs = 4 * (r_e ** 2 + r_o ** 2) + 2 * Md * Fd
-            flops = (fl_fact + R * fl_rhs) * Ed
+            # executed flops per element in the STREAM pass (every element of this mesh shares the tau = 0 matrix, so
+            # the factorisation runs once per CTA, not per element): per right-hand side and parity the right-hand side
+            # entries (degree-8 Taylor polynomial per collocation pivot, ~12 flops), w = G b (2 r MA) and this
+            # parity's half of the fine grid (2 MA F/2); r_p = MA_p + 1 pivots per parity
+            ma_e, ma_o = (Md - 1) // 2 + 1, (Md - 2) // 2 + 1
+            fl_rhs = sum(12 * (ma + 1) + 2 * (ma + 1) * ma + ma * Fd for ma in (ma_e, ma_o)) + Fd
+            flops = R * fl_rhs * Ed
+            out_bytes = Ed * R * Fd * 8 + 2 * R * (Ed + 1) * 8          # fine grid written, nodal values read
+            batch.set_option('dual_reuse_factor', 0)
+            try:
+                ms_every = time_kernel(run, 3)                            # factorising every element (same bits)
+            finally:
+                batch.set_option('dual_reuse_factor', 1)
             # achieved error on a sample: first 3 elements, 4 frequencies, against the primal KKT oracle
             sl, rs = slice(0, 3), (0, 7, 31, 63)
             worst = 0.0
@@ -273,7 +280,9 @@ def dual_config4_record(dev, fp64_tflops, reps):
                 fp = kkt.evaluate_fine(ref, Fd)
                 worst = max(worst, float(np.max(np.abs(fine[r, sl].cpu().numpy() - fp)) / np.max(np.abs(fp))))
             rows.append({'E': Ed, 'M': Md, 'kernel_ms': ms, 'rhs_solves_per_s': Ed * R / (ms * 1e-3),
-                         'executed_flops_per_element': fl_fact + R * fl_rhs,
+                         'kernel_ms_factorising_every_element': ms_every,
+                         'hbm_gbs': out_bytes / (ms * 1e-3) / 1e9, 'hbm_frac_of_measured_peak': out_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                         'executed_flops_per_element': R * fl_rhs,
                          'roofline_frac_fp64_executed_flops': flops / (ms * 1e-3) / 1e12 / fp64_tflops,
                          'achieved_rel_error_vs_primal_oracle_sample': worst, 'coarse_solves_64_rhs_ms': k1_ms})
     # CPU port on a sample: 4 elements x 8 frequencies per M, one core
@@ -289,7 +298,9 @@ def dual_config4_record(dev, fp64_tflops, reps):
             cnt += 4
         cpu['M=%d' % Md] = cnt / (time.perf_counter() - t0)
     return {'workload': 'BASELINE configs[4]: dual LSSVR, N=128, R=64 frequencies k=1..64, F=32, gamma=1e4, left-looking '
-                        'rank-revealing parity kernel (two 65 x 65 blocks per element)', 'rows': rows,
+                        'rank-revealing parity kernel (two 65 x 65 blocks per element); on this mesh tau is below half an ulp of the '
+                        'diagonal, every element shares the tau = 0 matrix bit for bit and the kernel factorises once per CTA '
+                        '(kernel_ms_factorising_every_element = the same launch with that reuse switched off)', 'rows': rows,
             'cpu_port_rhs_solves_per_s_per_core': cpu,
             'cpu_port_sample': '4 elements x 8 frequencies per M, oracle/dual.py (numpy LU of the 130 x 130 system per right-hand side), 1 core',
             'fp64_fma_probe_tflops': fp64_tflops}
@@ -603,7 +614,7 @@ def run_ours(args):
                 'fine_l2_vs_sin': dl2, 'fine_max_vs_sin': dmx}
         del fpr
         try:
-            dual4 = dual_config4_record(dev, fp64_tflops, reps)
+            dual4 = dual_config4_record(dev, fp64_tflops, peak, reps)
         except Exception as exc:     # the sub-record must not cost the headline line
             dual4 = {'error': '%s: %s' % (type(exc).__name__, exc)}
 
