@@ -217,6 +217,80 @@ __device__ __forceinline__ void lt_half_points(const double (&wq)[MAPT], const d
     }
 }
 
+// ---- Taylor-moment form of a resolved sine right-hand side ------------------------------------------------------------
+// With every collocation angle below 2^-7 (tiny; any mesh fine enough to matter for throughput) the right-hand side of
+// pivot k is amp cos(x_b c_k) (even parity) or amp sin(x_b c_k) (odd), c_k = 2 p_k + 1, a degree-8 / degree-9 Taylor
+// polynomial in x_b c_k, and the constraint pivot carries gpar.  Everything downstream is linear, so with y = x_b^2
+//     w   = fac sum_j y^j  m_j  + gpar m_c,     m_j = G (a_j c^(2j) or a_j c^(2j+1)) over the collocation pivots,
+//     u/2 = fac sum_j y^j  t_j  + gpar t_c,     t_j = V_half m_j              (fac = amp, or amp x_b for the odd parity)
+// with m_j (6 x MA) and t_j (6 x half the fine points) formed once per factorisation: a right-hand side costs 6 FMAs per
+// half point instead of a Taylor polynomial per pivot, r MA for w = G b and MA per half point.
+constexpr int LT_NMOM = 6;      // five Taylor moments + the constraint column
+__device__ __forceinline__ double lt_taylor_coef(int par, int j) {
+    // cos: 1, -1/2, 1/24, -1/720, 1/40320;  sin / x: 1, -1/6, 1/120, -1/5040, 1/362880
+    const double ce[5] = {1.0, -0.5, 4.1666666666666664e-02, -1.388888888888889e-03, 2.48015873015873e-05};
+    const double co[5] = {1.0, -1.6666666666666666e-01, 8.333333333333333e-03, -1.984126984126984e-04, 2.7557319223985893e-06};
+    return par == 0 ? ce[j] : co[j];
+}
+
+// Per right-hand side and element: nodal constraint value, amplitude and base angle of the sine forcing.
+struct LtTask {
+    double gpar, fac, y;
+    bool fast;          // sine forcing with every collocation angle below 2^-7: the moment form applies
+};
+__device__ __forceinline__ LtTask lt_task_setup(const DualArgs& a, int par, int r, long long e, double xl, double xr, const double* bcv) {
+    LtTask t;
+    const int N = a.N;
+    const double h = xr - xl;
+    const double kf = a.kf ? a.kf[r] : a.k_scalar;
+    const double kk = (kf * 3.14159265358979323846) * (kf * 3.14159265358979323846);
+    const long long ec = e < a.E ? e : a.E - 1;        // (groups of the STREAM pass may reach past the mesh: clamped, never stored)
+    double ul = a.u[(long long)r * (a.E + 1) + ec], ur = a.u[(long long)r * (a.E + 1) + ec + 1];
+    if (a.bc2 != nullptr) {     // bcv = {bc_left, bc_right, x_first, x_last, 1 / (x_last - x_first)}
+        ul += (bcv[0] * (bcv[3] - xl) + bcv[1] * (xl - bcv[2])) * bcv[4];
+        ur += (bcv[0] * (bcv[3] - xr) + bcv[1] * (xr - bcv[2])) * bcv[4];
+    }
+    t.gpar = par == 0 ? 0.5 * (ul + ur) : 0.5 * (ur - ul);
+    const double tb = kf * h * (0.5 / (double)(N - 1));       // base angle / pi
+    t.fast = a.forcing == HFL_FORCING_SINE && fabs(tb * (double)(N - 1)) < 0.0078125;
+    double S = 0.0, C = 0.0;
+    if (t.fast) sincospi(kf * (0.5 * (xl + xr)), &S, &C);
+    const double xb = 3.14159265358979323846 * tb;
+    const double amp = (0.25 * (h * h)) * kk * (par == 0 ? S : C);
+    t.fac = par == 0 ? amp : amp * xb;
+    t.y = xb * xb;
+    return t;
+}
+
+// 8 half points from the moment table tm [LT_NMOM][nhp] (pointer already offset to the first of the 8).
+__device__ __forceinline__ void lt_half_points_mom(const LtTask& t, const double* tm, int nhp, double (&acc)[8]) {
+#pragma unroll
+    for (int jj = 0; jj < 8; jj += 2) {
+        double2 p = *reinterpret_cast<const double2*>(tm + 4 * nhp + jj);
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            const double2 c = *reinterpret_cast<const double2*>(tm + j * nhp + jj);
+            p.x = fma(p.x, t.y, c.x);
+            p.y = fma(p.y, t.y, c.y);
+        }
+        const double2 tc = *reinterpret_cast<const double2*>(tm + 5 * nhp + jj);
+        acc[jj] = fma(t.gpar, tc.x, t.fac * p.x);
+        acc[jj + 1] = fma(t.gpar, tc.y, t.fac * p.y);
+    }
+}
+
+// The coefficients of this parity from the moment table mm [LT_NMOM][MAPT].
+template <int MAPT>
+__device__ __forceinline__ void lt_weights_mom(const LtTask& t, const double* mm, double (&wq)[MAPT]) {
+#pragma unroll
+    for (int q = 0; q < MAPT; ++q) {
+        double p = mm[4 * MAPT + q];
+#pragma unroll
+        for (int j = 3; j >= 0; --j) p = fma(p, t.y, mm[j * MAPT + q]);
+        wq[q] = fma(t.gpar, mm[5 * MAPT + q], t.fac * p);
+    }
+}
+
 #ifndef HFL_DUAL_LEFT_MINB
 #define HFL_DUAL_LEFT_MINB 4      // <= 85 registers: 4 CTAs per SM
 #endif
@@ -257,6 +331,8 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
     double* vh = eo + (size_t)2 * nhp * RP;                                  // [2][MAPT][nhp]: P_{2q+team}(xi_i), i < nhalf
     double* eacc = vh + (size_t)2 * MAPT * nhp;
     double* bcv = eacc + 2 * R;                                              // {bc_left, bc_right, x_first, x_last, 1 / length}
+    double* mom = bcv + 6;                                                   // [2][LT_NMOM][MAPT]: moments of G
+    double* tmom = mom + 2 * LT_NMOM * MAPT;                                 // [2][LT_NMOM][nhp]: their half-point values
     const int* rank_other = reinterpret_cast<const int*>(smem_raw + (1 - team) * team_bytes + ((size_t)kc * LDL + 4 * LT + 8) * 8) + LT;
     const bool want_fine = F > 0 && (a.fine != nullptr || a.want_err);
 
@@ -393,6 +469,37 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                     }
                 }
             }
+            // moments of G over the pivots (own entries only: no barrier needed yet), then their half-point values
+            double* Mm = mom + team * LT_NMOM * MAPT;
+            if (ext) {
+                double mj[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, mcn = 0.0;
+                if (ext_live)
+                    for (int k = 0; k < rank; ++k) {
+                        const double g = k < kc ? Lc[k * LDL + row] : Lg[(size_t)(k - kc) * LDL + row];
+                        const double c = pc[k];
+                        if (c < 0.0) {
+                            mcn += g;
+                        } else {
+                            const double c2 = c * c;
+                            double pw = team == 0 ? 1.0 : c;
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) {
+                                mj[j] = fma(g, lt_taylor_coef(team, j) * pw, mj[j]);
+                                pw *= c2;
+                            }
+                        }
+                    }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) Mm[j * MAPT + q_ext] = mj[j];
+                Mm[5 * MAPT + q_ext] = mcn;
+            }
+            lt_sync(team);          // G and its moments
+            for (int idx = row; idx < LT_NMOM * nhp; idx += LT) {
+                const int j = idx / nhp, i = idx - j * nhp;
+                double sum = 0.0;
+                for (int q = 0; q < MAPT; ++q) sum = fma(vht[q * nhp + i], Mm[j * MAPT + q], sum);
+                tmom[team * LT_NMOM * nhp + idx] = sum;
+            }
             lt_sync(team);
         }
 
@@ -438,10 +545,24 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                     work = any;
                     const unsigned mask = __ballot_sync(0xffffffffu, work);
                     if (work) {
-                        double wq[NE][MAPT];
                         // (an element of the group that is not streamed, or lies past the chunk, is carried along with
                         // clamped loads and never stored)
-                        lt_rhs_weights_n<MAPT, NE>(a, par, r, es, xn, bcv, Gs, Gg, kc, rank_p, pc_p, perm_p, wq);
+                        LtTask tk[NE];
+                        bool fast = true;
+#pragma unroll
+                        for (int n = 0; n < NE; ++n) {
+                            tk[n] = lt_task_setup(a, par, r, es + n, xn[n], xn[n + 1], bcv);
+                            fast = fast && (tk[n].fast || !use[n]);
+                        }
+                        const double* mm_p = mom + par * LT_NMOM * MAPT;
+                        const double* tm_p = tmom + par * LT_NMOM * nhp;
+                        double wq[NE][MAPT];
+                        if (!fast) {
+                            lt_rhs_weights_n<MAPT, NE>(a, par, r, es, xn, bcv, Gs, Gg, kc, rank_p, pc_p, perm_p, wq);
+                        } else if (a.coef != nullptr) {
+#pragma unroll
+                            for (int n = 0; n < NE; ++n) lt_weights_mom<MAPT>(tk[n], mm_p, wq[n]);
+                        }
 #pragma unroll
                         for (int n = 0; n < NE; ++n) {
                             if (!use[n]) continue;
@@ -457,20 +578,25 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                             double* out = a.fine + ((long long)r * a.E + es) * F;
                             for (int i0 = 0; i0 < nhp; i0 += 8) {
                                 double acc[NE][8];
+                                if (fast) {
 #pragma unroll
-                                for (int n = 0; n < NE; ++n)
+                                    for (int n = 0; n < NE; ++n) lt_half_points_mom(tk[n], tm_p + i0, nhp, acc[n]);
+                                } else {
 #pragma unroll
-                                    for (int jj = 0; jj < 8; ++jj) acc[n][jj] = 0.0;
+                                    for (int n = 0; n < NE; ++n)
 #pragma unroll
-                                for (int q = 0; q < MAPT; ++q) {
-                                    const double2* vv = reinterpret_cast<const double2*>(vt_p + q * nhp + i0);
+                                        for (int jj = 0; jj < 8; ++jj) acc[n][jj] = 0.0;
 #pragma unroll
-                                    for (int jj = 0; jj < 4; ++jj) {
-                                        const double2 t2 = vv[jj];
+                                    for (int q = 0; q < MAPT; ++q) {
+                                        const double2* vv = reinterpret_cast<const double2*>(vt_p + q * nhp + i0);
 #pragma unroll
-                                        for (int n = 0; n < NE; ++n) {
-                                            acc[n][2 * jj] = fma(wq[n][q], t2.x, acc[n][2 * jj]);
-                                            acc[n][2 * jj + 1] = fma(wq[n][q], t2.y, acc[n][2 * jj + 1]);
+                                        for (int jj = 0; jj < 4; ++jj) {
+                                            const double2 t2 = vv[jj];
+#pragma unroll
+                                            for (int n = 0; n < NE; ++n) {
+                                                acc[n][2 * jj] = fma(wq[n][q], t2.x, acc[n][2 * jj]);
+                                                acc[n][2 * jj + 1] = fma(wq[n][q], t2.y, acc[n][2 * jj + 1]);
+                                            }
                                         }
                                     }
                                 }
@@ -521,8 +647,11 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             const int r = r0 + row;
             double gpar = 0.0;
             if (r < R) {
+                const LtTask tk = lt_task_setup(a, team, r, e, xl, xr, bcv);
+                gpar = tk.gpar;
                 double wq[MAPT];
-                gpar = lt_rhs_weights<MAPT>(a, team, r, e, xl, xr, h, bcv, Lc + goff, Lg + goff, kc, rank, pc, perm, wq);
+                if (!tk.fast) lt_rhs_weights<MAPT>(a, team, r, e, xl, xr, h, bcv, Lc + goff, Lg + goff, kc, rank, pc, perm, wq);
+                else if (a.coef != nullptr) lt_weights_mom<MAPT>(tk, mom + team * LT_NMOM * MAPT, wq);
                 if (a.coef != nullptr) {
                     double* w = a.coef + ((long long)r * a.E + e) * M;
 #pragma unroll
@@ -533,7 +662,8 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                     double* eor = eo + team * nhp * RP + row;        // rows nhalf..nhp-1 are padding (zeros from the table)
                     for (int i0 = 0; i0 < nhp; i0 += 8, eor += 8 * RP) {
                         double acc[8];
-                        lt_half_points<MAPT>(wq, vht + i0, nhp, acc);
+                        if (tk.fast) lt_half_points_mom(tk, tmom + team * LT_NMOM * nhp + i0, nhp, acc);
+                        else lt_half_points<MAPT>(wq, vht + i0, nhp, acc);
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) eor[jj * RP] = acc[jj];
                     }
@@ -616,7 +746,8 @@ static int launch_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cu
     const DualArgs& a = pa.d;
     if (lt_goff(pa.nh) + MAPT > LT) return HFL_ERR_UNSUPPORTED;            // block rows + extra rows: one thread each
     const int RB = a.R < LT ? a.R : LT, nhp = lt_nhalf_padded(a.F);
-    const size_t common = ((size_t)2 * nhp * (RB | 1) + (size_t)2 * MAPT * nhp + 2 * (size_t)a.R + 6) * 8;
+    const size_t common = ((size_t)2 * nhp * (RB | 1) + (size_t)2 * MAPT * nhp + 2 * (size_t)a.R + 6 +
+                           (size_t)2 * LT_NMOM * (MAPT + nhp)) * 8;
     // as many columns of L in shared memory as keep 4 CTAs on an SM (56 KB each), between LT_KC_MIN and LT_KC_MAX
     int kc = pa.nh < LT_KC_MAX ? pa.nh : LT_KC_MAX;
     while (kc > LT_KC_MIN && 2 * lt_team_bytes(kc) + common > 56 * 1024) --kc;
