@@ -125,81 +125,6 @@ __device__ __forceinline__ double lt_rhs_weights(const DualArgs& a, int par, int
     return gpar;
 }
 
-// The same for NE neighbouring elements of one right-hand side at once (STREAM pass): every 128-bit load of G feeds
-// NE accumulations, which is what takes the shared-memory data pipe off the critical path.
-#ifndef HFL_STREAM_NE
-#define HFL_STREAM_NE 1
-#endif
-template <int MAPT, int NE>
-__device__ __forceinline__ void lt_rhs_weights_n(const DualArgs& a, int par, int r, long long e0, const double (&xn)[NE + 1],
-                                                 const double* bcv, const double* Gs, const double* Gg, int kc, int rank,
-                                                 const double* pc, const int* perm, double (&wq)[NE][MAPT]) {
-    const int N = a.N, NHc = N / 2;
-    const double kf = a.kf ? a.kf[r] : a.k_scalar;
-    const double kk = (kf * 3.14159265358979323846) * (kf * 3.14159265358979323846);
-    const bool sine = a.forcing == HFL_FORCING_SINE;
-    double un[NE + 1];
-#pragma unroll
-    for (int n = 0; n <= NE; ++n) {
-        un[n] = a.u[(long long)r * (a.E + 1) + min(e0 + n, a.E)];
-        if (a.bc2 != nullptr) un[n] += (bcv[0] * (bcv[3] - xn[n]) + bcv[1] * (xn[n] - bcv[2])) * bcv[4];
-    }
-    double gpar[NE], amp[NE], xb[NE], tb[NE], isig[NE];
-    bool tiny[NE];
-#pragma unroll
-    for (int n = 0; n < NE; ++n) {
-        const double h = xn[n + 1] - xn[n];
-        gpar[n] = par == 0 ? 0.5 * (un[n] + un[n + 1]) : 0.5 * (un[n + 1] - un[n]);
-        double S = 0.0, C = 0.0;
-        if (sine) sincospi(kf * (0.5 * (xn[n] + xn[n + 1])), &S, &C);
-        isig[n] = 0.25 * (h * h);
-        amp[n] = isig[n] * kk * (par == 0 ? S : C);
-        tb[n] = kf * h * (0.5 / (double)(N - 1));       // base angle / pi
-        tiny[n] = fabs(tb[n] * (double)(N - 1)) < 0.0078125;   // every angle below 2^-7: Taylor (any fine mesh)
-        xb[n] = 3.14159265358979323846 * tb[n];
-#pragma unroll
-        for (int q = 0; q < MAPT; ++q) wq[n][q] = 0.0;
-    }
-    auto step = [&](int k, const double* g) {
-        const double c = pc[k];
-        double b[NE];
-#pragma unroll
-        for (int n = 0; n < NE; ++n) {
-            if (c < 0.0) {
-                b[n] = gpar[n];
-            } else if (sine) {
-                if (tiny[n]) {
-                    const double x = xb[n] * c, z = x * x;
-                    b[n] = par == 0 ? amp[n] * fma(z, fma(z, fma(z, fma(z, 2.48015873015873e-05, -1.388888888888889e-03), 4.1666666666666664e-02), -0.5), 1.0)
-                                    : amp[n] * (x * fma(z, fma(z, fma(z, -1.984126984126984e-04, 8.333333333333333e-03), -1.6666666666666666e-01), 1.0));
-                } else {
-                    double sj, cj;
-                    sincospi(tb[n] * c, &sj, &cj);
-                    b[n] = amp[n] * (par == 0 ? cj : sj);
-                }
-            } else {
-                const int pk = perm[k];
-                const long long en = min(e0 + n, a.E - 1);
-                const double fp = a.f[((long long)r * N + NHc + pk) * a.E + en];
-                const double fm = a.f[((long long)r * N + NHc - 1 - pk) * a.E + en];
-                b[n] = isig[n] * (par == 0 ? 0.5 * (fp + fm) : 0.5 * (fp - fm));
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < MAPT; q += 2) {
-            const double2 gg = *reinterpret_cast<const double2*>(g + q);
-#pragma unroll
-            for (int n = 0; n < NE; ++n) {
-                wq[n][q] = fma(gg.x, b[n], wq[n][q]);
-                wq[n][q + 1] = fma(gg.y, b[n], wq[n][q + 1]);
-            }
-        }
-    };
-    const int ks = min(rank, kc);
-    for (int k = 0; k < ks; ++k) step(k, Gs + k * LDL);
-    for (int k = kc; k < rank; ++k) step(k, Gg + (size_t)(k - kc) * LDL);
-}
-
 // This parity's share of u at 8 of the first half of the fine points (entries q >= MA of wq and of the table are zero).
 template <int MAPT>
 __device__ __forceinline__ void lt_half_points(const double (&wq)[MAPT], const double* vt, int nhp, double (&acc)[8]) {
@@ -215,6 +140,32 @@ __device__ __forceinline__ void lt_half_points(const double (&wq)[MAPT], const d
             acc[2 * jj + 1] = fma(wq[q], t2.y, acc[2 * jj + 1]);
         }
     }
+}
+
+// General right-hand side (sampled forcing, or a sine the element does not resolve): w = G b pivot by pivot, then this
+// parity's half points from the Legendre table into hp [i * hp_stride] (if asked for); the coefficients go to global
+// memory if asked for.  Kept out of line: its MAPT + 8 live doubles would otherwise set the register budget of the
+// moment path below.
+template <int MAPT>
+__device__ __noinline__ double lt_general_task(const DualArgs& a, int par, int r, long long e, double xl, double xr, const double* bcv,
+                                               const double* Gs, const double* Gg, int kc, int rank, const double* pc, const int* perm,
+                                               const double* vt, int nhp, int MA, double* hp, int hp_stride) {
+    double wq[MAPT];
+    const double gpar = lt_rhs_weights<MAPT>(a, par, r, e, xl, xr, xr - xl, bcv, Gs, Gg, kc, rank, pc, perm, wq);
+    if (a.coef != nullptr) {
+        double* w = a.coef + ((long long)r * a.E + e) * a.M;
+#pragma unroll
+        for (int q = 0; q < MAPT; ++q)
+            if (q < MA) w[2 * q + par] = wq[q];
+    }
+    if (hp != nullptr)
+        for (int i0 = 0; i0 < nhp; i0 += 8) {
+            double acc[8];
+            lt_half_points<MAPT>(wq, vt + i0, nhp, acc);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) hp[(i0 + jj) * hp_stride] = acc[jj];
+        }
+    return gpar;
 }
 
 // ---- Taylor-moment form of a resolved sine right-hand side ------------------------------------------------------------
@@ -297,15 +248,17 @@ __device__ __forceinline__ void lt_weights_mom(const LtTask& t, const double* mm
 // MAPT: compile-time even bound on the coefficients per parity (extra rows of the factorisation, width of G).
 //
 // Two passes per CTA over its elements (a contiguous chunk of E / gridDim.x):
-//   STREAM (pa.reuse, no fused error norms): tau enters A only as fl(K_ii + tau) on the collocation rows; while tau
-//     stays below half an ulp of the smallest K_ii every such element sees the SAME floating-point matrix as tau = 0.
-//     The CTA factorises that matrix once and then streams the (element, right-hand side) pairs of all those elements
-//     through G without a single barrier: a pair of adjacent lanes per right-hand side (even / odd parity), w = G b in
-//     registers, half the fine points each, one shuffle to combine E +- O, 16-byte stores.  Bit for bit what a
-//     factorisation per element produces (tests/test_gpu_dual.py::test_factor_reuse_is_bitwise).
-//   TEAM: every other element (coarse meshes, or everything with pa.reuse = 0): factorise per element, 96 threads per
-//     parity, right-hand sides one per thread, combine through shared memory.  The factor of the previous element is
-//     still kept while consecutive elements share the matrix (pa.reuse with fused error norms).
+//   STREAM (pa.reuse, sine forcing, no fused error norms): tau enters A only as fl(K_ii + tau) on the collocation rows;
+//     while tau stays below half an ulp of the smallest K_ii every such element sees the SAME floating-point matrix as
+//     tau = 0.  The CTA factorises that matrix once, forms the moment tables, and then streams the (element,
+//     right-hand side) pairs of all elements that also resolve every frequency (k_max h / 2 < 2^-7) without a single
+//     barrier: a lane pair (l, l + 16) per right-hand side (even / odd parity), 6 FMAs per half point from the moment
+//     table, one shuffle to combine E +- O, 16-byte stores.  Bit for bit what a factorisation per element produces
+//     (tests/test_gpu_dual.py::test_factor_reuse_is_bitwise).
+//   TEAM: every other element (coarse meshes, sampled forcing, unresolved frequencies, fused error norms, or everything
+//     with pa.reuse = 0): factorise per element, 96 threads per parity, right-hand sides one per thread (moment form where
+//     it applies, pivot by pivot otherwise), halves combined through shared memory.  The factor of the previous element
+//     is still kept while consecutive elements share the matrix.
 template <int MAPT>
 __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_kernel(const DualParityArgs pa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -376,7 +329,19 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
     int rank = 0;
     __syncthreads();
 
-    bool stream_pass = pa.reuse && !a.want_err;       // CTA-uniform
+    // An element goes through the STREAM pass when its matrix is the tau = 0 matrix AND every right-hand side is a sine
+    // it resolves (all collocation angles below 2^-7, the moment form): decided from h alone, CTA-uniform.
+    double kfmax = fabs(a.k_scalar);
+    if (a.kf != nullptr) {
+        kfmax = 0.0;
+        for (int rr = 0; rr < R; ++rr) kfmax = fmax(kfmax, fabs(a.kf[rr]));
+    }
+    const bool sine_forcing = a.forcing == HFL_FORCING_SINE;
+    auto streamable = [&](double hh) -> bool {
+        const double hh2 = hh * hh;
+        return sine_forcing && 0.5 * (hh2 * hh2) * a.c_tau < thr_same && fabs(kfmax * hh * 0.5) < 0.0078125;
+    };
+    bool stream_pass = pa.reuse && !a.want_err && sine_forcing;       // CTA-uniform
     bool streamed = false;                            // elements below thr_same were handled by the STREAM pass
     // this CTA's elements: a contiguous chunk (rows (r, e), (r, e + 1), ... of the fine grid are adjacent in memory)
     const long long per_cta = (a.E + gridDim.x - 1) / gridDim.x;
@@ -389,7 +354,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
         const double h = xr - xl, h2 = h * h;
         const double th = stream_pass ? 0.0 : 0.5 * (h2 * h2) * a.c_tau;
         const bool same = th < thr_same;          // CTA-uniform (every thread holds the same th and threshold)
-        if (!stream_pass && streamed && same) { ++e; continue; }
+        if (!stream_pass && streamed && streamable(h)) { ++e; continue; }
         if (!(cached && same)) {
             cached = same;
             double dii = live_row ? kdiag + (row < NHc ? th : 0.0) : 0.0;    // running diagonal entry of this row
@@ -520,119 +485,66 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             const int MA_p = pa.MA[par];
             if (rank >= 1 && rank_q >= 1) {                    // CTA-uniform (rank / rank_q are the two teams' ranks)
                 streamed = true;
-                // task t = r * ng + j: consecutive lanes take consecutive groups of NE elements of one right-hand side
-                // (coalesced loads of the nodal values, adjacent 256-byte rows of the fine grid)
-                constexpr int NE = HFL_STREAM_NE;
-                const int ne = (int)(e_end - e_first), ng = (ne + NE - 1) / NE;
-                const long long ntask = (long long)ng * R;
-                int r = pair / ng, j = pair % ng;
-                const int dr = LT / ng, dj = LT % ng;
+                // task t = r * ne + j: consecutive lanes take consecutive elements of one right-hand side (coalesced
+                // loads of the nodal values, adjacent 256-byte rows of the fine grid)
+                const int ne = (int)(e_end - e_first);
+                const long long ntask = (long long)ne * R;
+                int r = pair / ne, j = pair % ne;
+                const int dr = LT / ne, dj = LT % ne;
                 const bool vec = (F % 16 == 0) && ((reinterpret_cast<size_t>(a.fine) & 15) == 0);
+                const double* mm_p = mom + par * LT_NMOM * MAPT;
+                const double* tm_p = tmom + par * LT_NMOM * nhp;
                 for (long long t0 = 0; t0 < ntask; t0 += LT) {
-                    const long long es = e_first + (long long)j * NE;
+                    const long long es = e_first + j;
                     bool work = t0 + pair < ntask;
-                    double xn[NE + 1];
-                    bool use[NE];
-                    bool any = false;
-#pragma unroll
-                    for (int n = 0; n <= NE; ++n) xn[n] = (work && es + n <= e_end) ? a.nodes[es + n] : (double)n;
-#pragma unroll
-                    for (int n = 0; n < NE; ++n) {
-                        const double sh = xn[n + 1] - xn[n], sh2 = sh * sh;
-                        use[n] = work && es + n < e_end && (0.5 * (sh2 * sh2) * a.c_tau < thr_same);
-                        any = any || use[n];
-                    }
-                    work = any;
+                    double sxl = 0.0, sxr = 1.0;
+                    if (work) { sxl = a.nodes[es]; sxr = a.nodes[es + 1]; }
+                    work = work && streamable(sxr - sxl);
                     const unsigned mask = __ballot_sync(0xffffffffu, work);
                     if (work) {
-                        // (an element of the group that is not streamed, or lies past the chunk, is carried along with
-                        // clamped loads and never stored)
-                        LtTask tk[NE];
-                        bool fast = true;
+                        const LtTask tk = lt_task_setup(a, par, r, es, sxl, sxr, bcv);       // tk.fast holds (streamable)
+                        if (a.coef != nullptr) {
+                            double wq[MAPT];
+                            lt_weights_mom<MAPT>(tk, mm_p, wq);
+                            double* w = a.coef + ((long long)r * a.E + es) * M;
 #pragma unroll
-                        for (int n = 0; n < NE; ++n) {
-                            tk[n] = lt_task_setup(a, par, r, es + n, xn[n], xn[n + 1], bcv);
-                            fast = fast && (tk[n].fast || !use[n]);
+                            for (int q = 0; q < MAPT; ++q)
+                                if (q < MA_p) w[2 * q + par] = wq[q];
                         }
-                        const double* mm_p = mom + par * LT_NMOM * MAPT;
-                        const double* tm_p = tmom + par * LT_NMOM * nhp;
-                        double wq[NE][MAPT];
-                        if (!fast) {
-                            lt_rhs_weights_n<MAPT, NE>(a, par, r, es, xn, bcv, Gs, Gg, kc, rank_p, pc_p, perm_p, wq);
-                        } else if (a.coef != nullptr) {
-#pragma unroll
-                            for (int n = 0; n < NE; ++n) lt_weights_mom<MAPT>(tk[n], mm_p, wq[n]);
-                        }
-#pragma unroll
-                        for (int n = 0; n < NE; ++n) {
-                            if (!use[n]) continue;
-                            if (a.coef != nullptr) {
-                                double* w = a.coef + ((long long)r * a.E + es + n) * M;
-#pragma unroll
-                                for (int q = 0; q < MAPT; ++q)
-                                    if (q < MA_p) w[2 * q + par] = wq[n][q];
-                            }
-                            if (r == 0 && par == 0 && a.status != nullptr) a.status[es + n] = 0;
-                        }
+                        if (r == 0 && par == 0 && a.status != nullptr) a.status[es] = 0;
                         if (a.fine != nullptr && F > 0) {
                             double* out = a.fine + ((long long)r * a.E + es) * F;
                             for (int i0 = 0; i0 < nhp; i0 += 8) {
-                                double acc[NE][8];
-                                if (fast) {
-#pragma unroll
-                                    for (int n = 0; n < NE; ++n) lt_half_points_mom(tk[n], tm_p + i0, nhp, acc[n]);
-                                } else {
-#pragma unroll
-                                    for (int n = 0; n < NE; ++n)
-#pragma unroll
-                                        for (int jj = 0; jj < 8; ++jj) acc[n][jj] = 0.0;
-#pragma unroll
-                                    for (int q = 0; q < MAPT; ++q) {
-                                        const double2* vv = reinterpret_cast<const double2*>(vt_p + q * nhp + i0);
-#pragma unroll
-                                        for (int jj = 0; jj < 4; ++jj) {
-                                            const double2 t2 = vv[jj];
-#pragma unroll
-                                            for (int n = 0; n < NE; ++n) {
-                                                acc[n][2 * jj] = fma(wq[n][q], t2.x, acc[n][2 * jj]);
-                                                acc[n][2 * jj + 1] = fma(wq[n][q], t2.y, acc[n][2 * jj + 1]);
-                                            }
-                                        }
-                                    }
-                                }
+                                double acc[8];
+                                lt_half_points_mom(tk, tm_p + i0, nhp, acc);
                                 // even-parity lane: u(xi_i) = E + O at i = i0 + jj; odd-parity lane: u(-xi_i) = E - O at F - 1 - i
 #pragma unroll
-                                for (int n = 0; n < NE; ++n) {
+                                for (int jj = 0; jj < 8; ++jj) {
+                                    const double o = __shfl_xor_sync(mask, acc[jj], 16);
+                                    acc[jj] = par == 0 ? acc[jj] + o : o - acc[jj];
+                                }
+                                if (vec) {
+                                    if (par == 0) {
 #pragma unroll
-                                    for (int jj = 0; jj < 8; ++jj) {
-                                        const double o = __shfl_xor_sync(mask, acc[n][jj], 16);
-                                        acc[n][jj] = par == 0 ? acc[n][jj] + o : o - acc[n][jj];
-                                    }
-                                    if (!use[n]) continue;
-                                    double* on = out + (long long)n * F;
-                                    if (vec) {
-                                        if (par == 0) {
-#pragma unroll
-                                            for (int jj = 0; jj < 8; jj += 2)
-                                                *reinterpret_cast<double2*>(on + i0 + jj) = make_double2(acc[n][jj], acc[n][jj + 1]);
-                                        } else {
-#pragma unroll
-                                            for (int jj = 0; jj < 8; jj += 2)
-                                                *reinterpret_cast<double2*>(on + F - 2 - i0 - jj) = make_double2(acc[n][jj + 1], acc[n][jj]);
-                                        }
+                                        for (int jj = 0; jj < 8; jj += 2)
+                                            *reinterpret_cast<double2*>(out + i0 + jj) = make_double2(acc[jj], acc[jj + 1]);
                                     } else {
 #pragma unroll
-                                        for (int jj = 0; jj < 8; ++jj) {
-                                            const int i = i0 + jj;
-                                            if (i < nhalf && (par == 0 || F - 1 - i != i)) on[par == 0 ? i : F - 1 - i] = acc[n][jj];
-                                        }
+                                        for (int jj = 0; jj < 8; jj += 2)
+                                            *reinterpret_cast<double2*>(out + F - 2 - i0 - jj) = make_double2(acc[jj + 1], acc[jj]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int jj = 0; jj < 8; ++jj) {
+                                        const int i = i0 + jj;
+                                        if (i < nhalf && (par == 0 || F - 1 - i != i)) out[par == 0 ? i : F - 1 - i] = acc[jj];
                                     }
                                 }
                             }
                         }
                     }
                     r += dr; j += dj;
-                    if (j >= ng) { j -= ng; ++r; }
+                    if (j >= ne) { j -= ne; ++r; }
                 }
             }
             cached = false;       // the TEAM pass starts from its own factor (the tau = 0 one is not an element's)
@@ -649,21 +561,22 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             if (r < R) {
                 const LtTask tk = lt_task_setup(a, team, r, e, xl, xr, bcv);
                 gpar = tk.gpar;
-                double wq[MAPT];
-                if (!tk.fast) lt_rhs_weights<MAPT>(a, team, r, e, xl, xr, h, bcv, Lc + goff, Lg + goff, kc, rank, pc, perm, wq);
-                else if (a.coef != nullptr) lt_weights_mom<MAPT>(tk, mom + team * LT_NMOM * MAPT, wq);
-                if (a.coef != nullptr) {
+                if (!tk.fast) {
+                    lt_general_task<MAPT>(a, team, r, e, xl, xr, bcv, Lc + goff, Lg + goff, kc, rank, pc, perm, vht, nhp, MA,
+                                          want_fine ? eo + team * nhp * RP + row : nullptr, RP);
+                } else if (a.coef != nullptr) {
+                    double wq[MAPT];
+                    lt_weights_mom<MAPT>(tk, mom + team * LT_NMOM * MAPT, wq);
                     double* w = a.coef + ((long long)r * a.E + e) * M;
 #pragma unroll
                     for (int q = 0; q < MAPT; ++q)
                         if (q < MA) w[2 * q + team] = wq[q];
                 }
-                if (want_fine) {
+                if (want_fine && tk.fast) {
                     double* eor = eo + team * nhp * RP + row;        // rows nhalf..nhp-1 are padding (zeros from the table)
                     for (int i0 = 0; i0 < nhp; i0 += 8, eor += 8 * RP) {
                         double acc[8];
-                        if (tk.fast) lt_half_points_mom(tk, tmom + team * LT_NMOM * nhp + i0, nhp, acc);
-                        else lt_half_points<MAPT>(wq, vht + i0, nhp, acc);
+                        lt_half_points_mom(tk, tmom + team * LT_NMOM * nhp + i0, nhp, acc);
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) eor[jj * RP] = acc[jj];
                     }
