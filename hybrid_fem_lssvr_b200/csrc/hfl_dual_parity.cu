@@ -213,6 +213,30 @@ __device__ __forceinline__ LtTask lt_task_setup(const DualArgs& a, int par, int 
     return t;
 }
 
+// Both parities of a streamable task (sine forcing, resolved) from one set of loads and one sincospi.
+__device__ __forceinline__ void lt_task_setup2(const DualArgs& a, int r, long long e, double xl, double xr, const double* bcv,
+                                               LtTask& te, LtTask& to) {
+    const int N = a.N;
+    const double h = xr - xl;
+    const double kf = a.kf ? a.kf[r] : a.k_scalar;
+    const double kk = (kf * 3.14159265358979323846) * (kf * 3.14159265358979323846);
+    double ul = a.u[(long long)r * (a.E + 1) + e], ur = a.u[(long long)r * (a.E + 1) + e + 1];
+    if (a.bc2 != nullptr) {
+        ul += (bcv[0] * (bcv[3] - xl) + bcv[1] * (xl - bcv[2])) * bcv[4];
+        ur += (bcv[0] * (bcv[3] - xr) + bcv[1] * (xr - bcv[2])) * bcv[4];
+    }
+    te.gpar = 0.5 * (ul + ur);
+    to.gpar = 0.5 * (ur - ul);
+    double S, C;
+    sincospi(kf * (0.5 * (xl + xr)), &S, &C);
+    const double xb = 3.14159265358979323846 * (kf * h * (0.5 / (double)(N - 1)));
+    const double ak = (0.25 * (h * h)) * kk;
+    te.fac = ak * S;
+    to.fac = (ak * C) * xb;
+    te.y = to.y = xb * xb;
+    te.fast = to.fast = true;
+}
+
 // 8 half points from the moment table tm [LT_NMOM][nhp] (pointer already offset to the first of the 8).
 __device__ __forceinline__ void lt_half_points_mom(const LtTask& t, const double* tm, int nhp, double (&acc)[8]) {
 #pragma unroll
@@ -469,76 +493,80 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
         }
 
         if (stream_pass) {
-            // ---- STREAM: every element of this CTA whose matrix is the tau = 0 matrix, a lane pair (l, l + 16) per right-hand side
+            // ---- STREAM: every element of this CTA whose matrix is the tau = 0 matrix and that resolves every frequency.
+            // Each lane sets up one (element, right-hand side) task - nodal values, amplitudes, y = x_b^2 for both
+            // parities from one sincospi.  The warp then walks its 32 tasks two at a time: 16 lanes per task, lane c
+            // owning half point c with its 2 x 6 moment-table entries in registers (no shared-memory read in the loop),
+            // 12 FMAs for E and O, and two coalesced stores per task: u(xi_c) = E + O forwards, u(-xi_c) = E - O backwards.
             stream_pass = false;
-            __syncthreads();                                   // both parities' G, pc, perm, rank
-            // parity per half-warp: the 128-bit shared loads of G and of the table (served a quarter-warp at a time) see
-            // one address each; the partner lane is 16 away
-            const int par = (threadIdx.x >> 4) & 1, pair = (threadIdx.x >> 5) * 16 + (threadIdx.x & 15);
-            const unsigned char* pb = smem_raw + par * team_bytes;
-            const double* Gs = reinterpret_cast<const double*>(pb) + goff;
-            const double* pc_p = reinterpret_cast<const double*>(pb) + (size_t)kc * LDL + LT;
-            const int* perm_p = reinterpret_cast<const int*>(pb + ((size_t)kc * LDL + 4 * LT + 8) * 8);
-            const int rank_p = perm_p[LT], rank_q = rank_other[0];
-            const double* Gg = pa.spill + ((size_t)blockIdx.x * 2 + par) * spill_team + goff;
-            const double* vt_p = vh + par * MAPT * nhp;
-            const int MA_p = pa.MA[par];
+            __syncthreads();                                   // both parities' moment tables and ranks
+            const int rank_q = rank_other[0];
             if (rank >= 1 && rank_q >= 1) {                    // CTA-uniform (rank / rank_q are the two teams' ranks)
                 streamed = true;
                 // task t = r * ne + j: consecutive lanes take consecutive elements of one right-hand side (coalesced
-                // loads of the nodal values, adjacent 256-byte rows of the fine grid)
+                // loads of the nodal values, adjacent rows of the fine grid)
+                const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
                 const int ne = (int)(e_end - e_first);
                 const long long ntask = (long long)ne * R;
-                int r = pair / ne, j = pair % ne;
-                const int dr = LT / ne, dj = LT % ne;
-                const bool vec = (F % 16 == 0) && ((reinterpret_cast<size_t>(a.fine) & 15) == 0);
-                const double* mm_p = mom + par * LT_NMOM * MAPT;
-                const double* tm_p = tmom + par * LT_NMOM * nhp;
-                for (long long t0 = 0; t0 < ntask; t0 += LT) {
+                int r = (int)threadIdx.x / ne, j = (int)threadIdx.x % ne;
+                const int dr = 2 * LT / ne, dj = 2 * LT % ne;
+                for (long long t0 = 0; t0 < ntask; t0 += 2 * LT) {
                     const long long es = e_first + j;
-                    bool work = t0 + pair < ntask;
+                    bool work = t0 + threadIdx.x < ntask;
                     double sxl = 0.0, sxr = 1.0;
                     if (work) { sxl = a.nodes[es]; sxr = a.nodes[es + 1]; }
                     work = work && streamable(sxr - sxl);
-                    const unsigned mask = __ballot_sync(0xffffffffu, work);
+                    LtTask te_k, to_k;                         // this lane's task, even and odd parity
+                    te_k.gpar = to_k.gpar = te_k.fac = to_k.fac = te_k.y = 0.0;
+                    long long off = 0;
                     if (work) {
-                        const LtTask tk = lt_task_setup(a, par, r, es, sxl, sxr, bcv);       // tk.fast holds (streamable)
+                        lt_task_setup2(a, r, es, sxl, sxr, bcv, te_k, to_k);
+                        off = ((long long)r * a.E + es) * F;
                         if (a.coef != nullptr) {
                             double wq[MAPT];
-                            lt_weights_mom<MAPT>(tk, mm_p, wq);
                             double* w = a.coef + ((long long)r * a.E + es) * M;
+                            lt_weights_mom<MAPT>(te_k, mom, wq);
 #pragma unroll
                             for (int q = 0; q < MAPT; ++q)
-                                if (q < MA_p) w[2 * q + par] = wq[q];
+                                if (q < pa.MA[0]) w[2 * q] = wq[q];
+                            lt_weights_mom<MAPT>(to_k, mom + LT_NMOM * MAPT, wq);
+#pragma unroll
+                            for (int q = 0; q < MAPT; ++q)
+                                if (q < pa.MA[1]) w[2 * q + 1] = wq[q];
                         }
-                        if (r == 0 && par == 0 && a.status != nullptr) a.status[es] = 0;
-                        if (a.fine != nullptr && F > 0) {
-                            double* out = a.fine + ((long long)r * a.E + es) * F;
-                            for (int i0 = 0; i0 < nhp; i0 += 8) {
-                                double acc[8];
-                                lt_half_points_mom(tk, tm_p + i0, nhp, acc);
-                                // even-parity lane: u(xi_i) = E + O at i = i0 + jj; odd-parity lane: u(-xi_i) = E - O at F - 1 - i
+                        if (r == 0 && a.status != nullptr) a.status[es] = 0;
+                    }
+                    const unsigned vmask = __ballot_sync(0xffffffffu, work);
+                    if (a.fine != nullptr && vmask != 0u) {
+                        for (int ib = 0; ib < nhalf; ib += 16) {
+                            const int ih = ib + hl;
+                            const bool inb = ih < nhalf;
+                            double tbe[LT_NMOM], tbo[LT_NMOM];
 #pragma unroll
-                                for (int jj = 0; jj < 8; ++jj) {
-                                    const double o = __shfl_xor_sync(mask, acc[jj], 16);
-                                    acc[jj] = par == 0 ? acc[jj] + o : o - acc[jj];
+                            for (int q = 0; q < LT_NMOM; ++q) {
+                                tbe[q] = tmom[q * nhp + (inb ? ih : 0)];
+                                tbo[q] = tmom[(LT_NMOM + q) * nhp + (inb ? ih : 0)];
+                            }
+                            const bool centre = F - 1 - ih == ih;          // odd F: the middle point is written once
+#pragma unroll 4
+                            for (int sstep = 0; sstep < 16; ++sstep) {
+                                if (((vmask >> (2 * sstep)) & 3u) == 0u) continue;          // warp-uniform
+                                const int src = 2 * sstep + half;
+                                const double y = __shfl_sync(0xffffffffu, te_k.y, src);
+                                const double fe = __shfl_sync(0xffffffffu, te_k.fac, src), fo = __shfl_sync(0xffffffffu, to_k.fac, src);
+                                const double ge = __shfl_sync(0xffffffffu, te_k.gpar, src), go = __shfl_sync(0xffffffffu, to_k.gpar, src);
+                                const long long o2 = __shfl_sync(0xffffffffu, off, src);
+                                double pe = tbe[4], po = tbo[4];
+#pragma unroll
+                                for (int q = 3; q >= 0; --q) {
+                                    pe = fma(pe, y, tbe[q]);
+                                    po = fma(po, y, tbo[q]);
                                 }
-                                if (vec) {
-                                    if (par == 0) {
-#pragma unroll
-                                        for (int jj = 0; jj < 8; jj += 2)
-                                            *reinterpret_cast<double2*>(out + i0 + jj) = make_double2(acc[jj], acc[jj + 1]);
-                                    } else {
-#pragma unroll
-                                        for (int jj = 0; jj < 8; jj += 2)
-                                            *reinterpret_cast<double2*>(out + F - 2 - i0 - jj) = make_double2(acc[jj + 1], acc[jj]);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int jj = 0; jj < 8; ++jj) {
-                                        const int i = i0 + jj;
-                                        if (i < nhalf && (par == 0 || F - 1 - i != i)) out[par == 0 ? i : F - 1 - i] = acc[jj];
-                                    }
+                                const double ev = fma(ge, tbe[5], fe * pe), od = fma(go, tbo[5], fo * po);
+                                if (((vmask >> src) & 1u) && inb) {
+                                    double* out = a.fine + o2;
+                                    out[ih] = ev + od;
+                                    if (!centre) out[F - 1 - ih] = ev - od;
                                 }
                             }
                         }
