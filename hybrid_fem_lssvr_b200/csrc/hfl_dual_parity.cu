@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
     const size_t spill_team = (size_t)(nh - kc) * LDL;
     double* Lg = pa.spill + ((size_t)blockIdx.x * 2 + team) * spill_team;   // columns kc.. (unused when kc = nh)
     double* eo = reinterpret_cast<double*>(smem_raw + 2 * team_bytes);     // [2][nhp][RP]: E / O of the first half of the fine points
-    double* vh = eo + (size_t)2 * nhp * RP;                                  // [2][MAPT][nhp]: P_{2q+team}(xi_i), i < nhalf
+    double* vh = eo + max(2 * nhp * RP, 2 * LT * LT_NMOM);                   // [2][MAPT][nhp]: P_{2q+team}(xi_i), i < nhalf
     double* eacc = vh + (size_t)2 * MAPT * nhp;
     double* bcv = eacc + 2 * R;                                              // {bc_left, bc_right, x_first, x_last, 1 / length}
     double* mom = bcv + 6;                                                   // [2][LT_NMOM][MAPT]: moments of G
@@ -538,6 +538,14 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                     }
                     const unsigned vmask = __ballot_sync(0xffffffffu, work);
                     if (a.fine != nullptr && vmask != 0u) {
+                        // the six numbers of every task go through a per-warp staging area (the E / O buffer of the TEAM
+                        // pass, idle here): three broadcast 128-bit loads per step instead of twelve shuffles
+                        double2* stage = reinterpret_cast<double2*>(eo) + (threadIdx.x >> 5) * 96;
+                        __syncwarp();                              // the previous iteration's readers are done
+                        stage[3 * lane] = make_double2(te_k.y, te_k.fac);
+                        stage[3 * lane + 1] = make_double2(to_k.fac, te_k.gpar);
+                        stage[3 * lane + 2] = make_double2(to_k.gpar, __longlong_as_double(off));
+                        __syncwarp();
                         for (int ib = 0; ib < nhalf; ib += 16) {
                             const int ih = ib + hl;
                             const bool inb = ih < nhalf;
@@ -547,15 +555,17 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                                 tbe[q] = tmom[q * nhp + (inb ? ih : 0)];
                                 tbo[q] = tmom[(LT_NMOM + q) * nhp + (inb ? ih : 0)];
                             }
-                            const bool centre = F - 1 - ih == ih;          // odd F: the middle point is written once
+                            // odd F: the middle point is written once
+                            const bool w_lo = inb, w_hi = inb && F - 1 - ih != ih;
+                            double* out_lo = a.fine + ih;
+                            double* out_hi = a.fine + (F - 1 - ih);
 #pragma unroll 4
                             for (int sstep = 0; sstep < 16; ++sstep) {
                                 if (((vmask >> (2 * sstep)) & 3u) == 0u) continue;          // warp-uniform
                                 const int src = 2 * sstep + half;
-                                const double y = __shfl_sync(0xffffffffu, te_k.y, src);
-                                const double fe = __shfl_sync(0xffffffffu, te_k.fac, src), fo = __shfl_sync(0xffffffffu, to_k.fac, src);
-                                const double ge = __shfl_sync(0xffffffffu, te_k.gpar, src), go = __shfl_sync(0xffffffffu, to_k.gpar, src);
-                                const long long o2 = __shfl_sync(0xffffffffu, off, src);
+                                const double2 s0 = stage[3 * src], s1 = stage[3 * src + 1], s2 = stage[3 * src + 2];
+                                const double y = s0.x, fe = s0.y, fo = s1.x, ge = s1.y, go = s2.x;
+                                const long long o2 = __double_as_longlong(s2.y);
                                 double pe = tbe[4], po = tbo[4];
 #pragma unroll
                                 for (int q = 3; q >= 0; --q) {
@@ -563,10 +573,9 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                                     po = fma(po, y, tbo[q]);
                                 }
                                 const double ev = fma(ge, tbe[5], fe * pe), od = fma(go, tbo[5], fo * po);
-                                if (((vmask >> src) & 1u) && inb) {
-                                    double* out = a.fine + o2;
-                                    out[ih] = ev + od;
-                                    if (!centre) out[F - 1 - ih] = ev - od;
+                                if ((vmask >> src) & 1u) {
+                                    if (w_lo) out_lo[o2] = ev + od;
+                                    if (w_hi) out_hi[o2] = ev - od;
                                 }
                             }
                         }
@@ -687,7 +696,9 @@ static int launch_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cu
     const DualArgs& a = pa.d;
     if (lt_goff(pa.nh) + MAPT > LT) return HFL_ERR_UNSUPPORTED;            // block rows + extra rows: one thread each
     const int RB = a.R < LT ? a.R : LT, nhp = lt_nhalf_padded(a.F);
-    const size_t common = ((size_t)2 * nhp * (RB | 1) + (size_t)2 * MAPT * nhp + 2 * (size_t)a.R + 6 +
+    size_t eo_doubles = (size_t)2 * nhp * (RB | 1);
+    if (eo_doubles < (size_t)2 * LT * LT_NMOM) eo_doubles = (size_t)2 * LT * LT_NMOM;      // staging area of the STREAM pass
+    const size_t common = (eo_doubles + (size_t)2 * MAPT * nhp + 2 * (size_t)a.R + 6 +
                            (size_t)2 * LT_NMOM * (MAPT + nhp)) * 8;
     // as many columns of L in shared memory as keep 4 CTAs on an SM (56 KB each), between LT_KC_MIN and LT_KC_MAX
     int kc = pa.nh < LT_KC_MAX ? pa.nh : LT_KC_MAX;
