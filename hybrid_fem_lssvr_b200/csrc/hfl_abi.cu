@@ -303,6 +303,7 @@ double* hfl::plan_scratch(const hfl_plan* p, cudaStream_t s, size_t bytes) {
 extern "C" int hfl_plan_destroy(hfl_plan_t* p) {
     if (!p) return HFL_OK;
     if (p->d_tables) cudaFree(p->d_tables);
+    if (p->d_dual0) cudaFree(p->d_dual0);
     for (auto& kv : p->scratch)
         if (kv.second.first) cudaFree(kv.second.first);
     delete p;

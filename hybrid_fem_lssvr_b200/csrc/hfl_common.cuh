@@ -75,6 +75,10 @@ struct hfl_plan {
     double* d_tables = nullptr;
     // Scratch buffers owned by the plan, one per stream that asked for one (kernels on one stream serialise, so a
     // buffer per stream is race-free); grown on demand, released by hfl_plan_destroy.
+    // Left-looking dual kernel: moment tables and ranks of the tau = 0 factorisation (a function of the plan alone),
+    // computed by the first launch that can use them and read by every later one (hfl_dual_parity.cu).
+    mutable double* d_dual0 = nullptr;
+    mutable bool dual0_ready = false;
     mutable std::mutex scratch_mu;
     mutable std::map<cudaStream_t, std::pair<void*, size_t>> scratch;
     size_t off_De, off_Do, off_Ge, off_Go, off_fineE, off_fineO, off_D2, off_V, off_Ct, off_K0, off_Cpe, off_Cpo, off_Kpe, off_Kpo, off_D0, off_D1, off_Vt, n_tables;

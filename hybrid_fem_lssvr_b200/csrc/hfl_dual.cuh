@@ -38,6 +38,8 @@ struct DualParityArgs {
     double* spill;          // left-looking kernel: global scratch for L columns kc.. (per CTA and team)
     int kc;                 // L columns held in shared memory
     int reuse;              // left-looking kernel: keep the factor while the element matrix is bitwise unchanged
+    double* dual0;          // left-looking kernel: plan-level tables of the tau = 0 factorisation {mom, tmom, ranks} or NULL
+    int dual0_mode;         // 0: factorise in the kernel; 1: read dual0; 2: this launch (one CTA) only fills dual0
 };
 
 // hfl_dual_parity.cu (left-looking parity kernel); returns false when the shape is not covered (nh > 96 or not

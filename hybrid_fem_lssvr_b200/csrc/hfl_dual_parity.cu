@@ -379,7 +379,14 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
         const double th = stream_pass ? 0.0 : 0.5 * (h2 * h2) * a.c_tau;
         const bool same = th < thr_same;          // CTA-uniform (every thread holds the same th and threshold)
         if (!stream_pass && streamed && streamable(h)) { ++e; continue; }
-        if (!(cached && same)) {
+        const int n_mom = LT_NMOM * (MAPT + nhp);       // per parity: mom [LT_NMOM][MAPT] then tmom [LT_NMOM][nhp]
+        if (stream_pass && pa.dual0_mode == 1) {
+            // the tau = 0 tables of this plan were computed by an earlier launch: {mom, tmom} of both parities, two ranks
+            for (int idx = threadIdx.x; idx < 2 * LT_NMOM * MAPT; idx += 2 * LT) mom[idx] = pa.dual0[idx];
+            for (int idx = threadIdx.x; idx < 2 * LT_NMOM * nhp; idx += 2 * LT) tmom[idx] = pa.dual0[2 * LT_NMOM * MAPT + idx];
+            rank = (int)pa.dual0[2 * n_mom + team];
+            if (row == 0) *rank_s = rank;
+        } else if (!(cached && same)) {
             cached = same;
             double dii = live_row ? kdiag + (row < NHc ? th : 0.0) : 0.0;    // running diagonal entry of this row
             bool alive = live_row;
@@ -501,6 +508,12 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
             stream_pass = false;
             __syncthreads();                                   // both parities' moment tables and ranks
             const int rank_q = rank_other[0];
+            if (pa.dual0_mode == 2) {                          // this launch only fills the plan's tables
+                for (int idx = threadIdx.x; idx < 2 * LT_NMOM * MAPT; idx += 2 * LT) pa.dual0[idx] = mom[idx];
+                for (int idx = threadIdx.x; idx < 2 * LT_NMOM * nhp; idx += 2 * LT) pa.dual0[2 * LT_NMOM * MAPT + idx] = tmom[idx];
+                if (row == 0) pa.dual0[2 * n_mom + team] = (double)rank;
+                return;
+            }
             if (rank >= 1 && rank_q >= 1) {                    // CTA-uniform (rank / rank_q are the two teams' ranks)
                 streamed = true;
                 // task t = r * ne + j: consecutive lanes take consecutive elements of one right-hand side (coalesced
@@ -716,6 +729,35 @@ static int launch_left(DualParityArgs pa, int max_smem, const hfl_plan* plan, cu
     long long grid = a.E;
     const long long cap = (long long)sm_count() * per_sm;
     if (grid > cap) grid = cap;
+    // Plan-level tables of the tau = 0 factorisation (STREAM pass): filled once per plan by a one-CTA launch of this
+    // kernel, synchronised before the flag is set so that launches on other streams may read them.  Not under stream
+    // capture (the synchronisation is illegal there): such launches factorise in the kernel as before.
+    pa.dual0 = nullptr;
+    pa.dual0_mode = 0;
+    const bool stream_pass_possible = pa.reuse && !a.want_err && a.forcing == HFL_FORCING_SINE;
+    if (stream_pass_possible) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        (void)cudaStreamIsCapturing(s, &cap);
+        std::lock_guard<std::mutex> guard(plan->scratch_mu);
+        const size_t n0 = (size_t)2 * LT_NMOM * (MAPT + nhp) + 2;
+        if (!plan->dual0_ready && cap == cudaStreamCaptureStatusNone) {
+            if (plan->d_dual0 == nullptr) HFL_CUDA_CHECK(cudaMalloc(&plan->d_dual0, n0 * sizeof(double)));
+            DualParityArgs pp = pa;
+            pp.dual0 = plan->d_dual0;
+            pp.dual0_mode = 2;
+            pp.spill = nullptr;
+            if (pp.kc < pp.nh) {
+                HFL_CUDA_CHECK(cudaMallocAsync(&pp.spill, (size_t)2 * (pp.nh - pp.kc) * LDL * sizeof(double), s));
+            }
+            dual_parity_left_kernel<MAPT><<<1, 2 * LT, smem, s>>>(pp);
+            if (pp.spill != nullptr) HFL_CUDA_CHECK(cudaFreeAsync(pp.spill, s));
+            HFL_CUDA_CHECK(cudaStreamSynchronize(s));
+            HFL_CUDA_CHECK(cudaGetLastError());
+            plan->dual0_ready = true;
+            count_launch();
+        }
+        if (plan->dual0_ready) { pa.dual0 = plan->d_dual0; pa.dual0_mode = 1; }
+    }
     pa.spill = nullptr;
     if (pa.kc < pa.nh) {
         // grid x 2 teams x (nh - kc) columns of LDL doubles
