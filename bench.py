@@ -258,12 +258,10 @@ def dual_config4_record(dev, fp64_tflops, hbm_peak, reps):
             run = lambda: batch.lssvr_dual_multi(nodes, un, ks, Md, GAMMA, N=N, F=Fd, want_coef=False, want_fine=True)   # noqa: E731
             ms = time_kernel(run, max(3, reps // 4))
             _, fine, _ = run()
-            # executed flops per element in the STREAM pass (every element of this mesh shares the tau = 0 matrix, so
-            # the factorisation runs once per CTA, not per element): per right-hand side and parity the right-hand side
-            # entries (degree-8 Taylor polynomial per collocation pivot, ~12 flops), w = G b (2 r MA) and this
-            # parity's half of the fine grid (2 MA F/2); r_p = MA_p + 1 pivots per parity
-            ma_e, ma_o = (Md - 1) // 2 + 1, (Md - 2) // 2 + 1
-            fl_rhs = sum(12 * (ma + 1) + 2 * (ma + 1) * ma + ma * Fd for ma in (ma_e, ma_o)) + Fd
+            # executed flops per element in the STREAM pass (every element of this mesh shares the tau = 0 matrix and
+            # resolves every frequency: the factorisation and the moment tables come from the plan): per right-hand
+            # side the set-up (~40 flops, one sincospi), 6 FMAs per half point and parity (2 x F/2 x 12) and E +- O (F)
+            fl_rhs = 40 + 2 * ((Fd + 1) // 2) * 12 + Fd
             flops = R * fl_rhs * Ed
             out_bytes = Ed * R * Fd * 8 + 2 * R * (Ed + 1) * 8          # fine grid written, nodal values read
             batch.set_option('dual_reuse_factor', 0)
@@ -281,7 +279,9 @@ def dual_config4_record(dev, fp64_tflops, hbm_peak, reps):
                 worst = max(worst, float(np.max(np.abs(fine[r, sl].cpu().numpy() - fp)) / np.max(np.abs(fp))))
             rows.append({'E': Ed, 'M': Md, 'kernel_ms': ms, 'rhs_solves_per_s': Ed * R / (ms * 1e-3),
                          'kernel_ms_factorising_every_element': ms_every,
-                         'hbm_gbs': out_bytes / (ms * 1e-3) / 1e9, 'hbm_frac_of_measured_peak': out_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                         'roofline': {'bound': 'hbm', 'achieved': out_bytes / (ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                                      'frac': out_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                                      'algorithmic_bytes_per_rhs': Fd * 8 + 16},
                          'executed_flops_per_element': R * fl_rhs,
                          'roofline_frac_fp64_executed_flops': flops / (ms * 1e-3) / 1e12 / fp64_tflops,
                          'achieved_rel_error_vs_primal_oracle_sample': worst, 'coarse_solves_64_rhs_ms': k1_ms})
@@ -299,8 +299,9 @@ def dual_config4_record(dev, fp64_tflops, hbm_peak, reps):
         cpu['M=%d' % Md] = cnt / (time.perf_counter() - t0)
     return {'workload': 'BASELINE configs[4]: dual LSSVR, N=128, R=64 frequencies k=1..64, F=32, gamma=1e4, left-looking '
                         'rank-revealing parity kernel (two 65 x 65 blocks per element); on this mesh tau is below half an ulp of the '
-                        'diagonal, every element shares the tau = 0 matrix bit for bit and the kernel factorises once per CTA '
-                        '(kernel_ms_factorising_every_element = the same launch with that reuse switched off)', 'rows': rows,
+                        'diagonal, every element shares the tau = 0 matrix bit for bit, and the kernel streams the right-hand sides '
+                        'through moment tables of that one factorisation (kernel_ms_factorising_every_element = the same launch with '
+                        'the reuse switched off: same bits)', 'rows': rows,
             'cpu_port_rhs_solves_per_s_per_core': cpu,
             'cpu_port_sample': '4 elements x 8 frequencies per M, oracle/dual.py (numpy LU of the 130 x 130 system per right-hand side), 1 core',
             'fp64_fma_probe_tflops': fp64_tflops}
