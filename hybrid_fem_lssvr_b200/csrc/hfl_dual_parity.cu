@@ -520,6 +520,12 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                 // loads of the nodal values, adjacent rows of the fine grid)
                 const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
                 const int ne = (int)(e_end - e_first);
+                // does the TEAM pass have anything left to do in this chunk?  (one coalesced sweep over the nodes instead of
+                // a serial walk over every element just to skip it)
+                bool leftover = false;
+                for (long long ee = e_first + threadIdx.x; ee < e_end; ee += 2 * LT)
+                    leftover = leftover || !streamable(a.nodes[ee + 1] - a.nodes[ee]);
+                if (__syncthreads_count(leftover) == 0) e = e_end;
                 const long long ntask = (long long)ne * R;
                 int r = (int)threadIdx.x / ne, j = (int)threadIdx.x % ne;
                 const int dr = 2 * LT / ne, dj = 2 * LT % ne;

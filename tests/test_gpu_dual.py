@@ -185,14 +185,15 @@ def test_team_kernel_small_system():
     assert rel(fine, kkt.evaluate_fine(ref, 32)) <= TOL and rel(fine2, kkt.evaluate_fine(ref, 32)) <= TOL
 
 
-@pytest.mark.parametrize('mesh', ['fine', 'mixed', 'fine_high_k'])
+@pytest.mark.parametrize('mesh', ['fine', 'mixed', 'fine_high_k', 'fine_many_rhs'])
 def test_factor_reuse_is_bitwise(mesh):
     """Left-looking kernel: while tau stays below half an ulp of every diagonal entry the element matrix K + tau J is
     the same floating-point matrix, and the kernel keeps the factor of the previous element.  Same bits as
     factorising every element ('dual_reuse_factor' = 0), on a fine mesh (every element after a CTA's first reuses)
     and on a mesh that alternates coarse and fine elements (the cache must be dropped and rebuilt).  'fine_high_k': one
     frequency the fine elements do not resolve to the Taylor bound (k h / 2 >= 2^-7), which keeps the elements out of the
-    barrier-free pass: factor kept per team, that right-hand side pivot by pivot, the others through the moment tables."""
+    barrier-free pass: factor kept per team, that right-hand side pivot by pivot, the others through the moment tables.
+    'fine_many_rhs': 64 frequencies, so that every CTA runs several iterations of the barrier-free loop."""
     E, N, F, M, gamma = 3001, 128, 32, 13, 1e4           # more elements than resident CTAs: several per CTA
     rng = np.random.default_rng(5)
     w = rng.uniform(0.5e-4, 1.5e-4, E)
@@ -200,6 +201,8 @@ def test_factor_reuse_is_bitwise(mesh):
         w[rng.uniform(size=E) < 0.3] = 2e-2
     nodes = 0.1 + np.concatenate([[0.0], np.cumsum(w)])
     ks = np.array([1.0, 3.0, 200.0 if mesh == 'fine_high_k' else 7.0])
+    if mesh == 'fine_many_rhs':          # BASELINE configs[4] count: several passes of the barrier-free loop per CTA
+        ks = np.arange(1.0, 65.0)
     u = np.stack([np.sin(k * np.pi * nodes) for k in ks])
     out = {}
     for reuse in (1, 0):
