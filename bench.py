@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument('--store', type=int, default=0, help='primal store path: 0 auto, 1 direct, 2 smem, 3 tma')
     ap.add_argument('--cpu-sample', type=int, default=0, help='elements in the CPU baseline sample (0 = auto)')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'],
-                    help='N = 1: replay the step (5 K1 launches + the element launch) as a CUDA graph')
+                    help='replay the step (5 K1 launches [+ the peer-memory exchange] + the element launch) as a CUDA graph')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -413,15 +413,16 @@ def run_ours(args):
     for _ in range(warmup):
         step()
     barrier()
-    # N = 1: the step is six dependent launches of 8-480 us; replaying them as a CUDA graph removes the per-launch host
-    # work and most of the gap between dependent kernels.  N > 1 keeps stream launches (the exchange kernel takes its
-    # epoch as a launch argument).
+    # The step is six (N = 1) or seven (N > 1: + the interface exchange) dependent launches of 8-480 us; replaying them as
+    # a CUDA graph removes the per-launch host work and most of the gap between dependent kernels.  The peer-memory
+    # exchange keeps its epoch on the device, so the captured launch is the same every step; with the NCCL exchange
+    # (--exchange nccl or the fallback) the step stays on stream launches.
     graph = None
-    if world == 1 and args.graph != 'off':
+    if (world == 1 or exchange is not None) and args.graph != 'off':
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                step()
+                bc2_graph = step()          # the interface values of the captured step live in the graph's memory pool
             g.replay()
             torch.cuda.synchronize()
             graph = g
@@ -435,7 +436,7 @@ def run_ours(args):
         lpg = _lib.launch_count()
         eager_step()
         lpg = _lib.launch_count() - lpg         # our launches per step, counted once outside the graph
-        step = lambda: graph.replay()           # noqa: E731
+        step = lambda: (graph.replay(), bc2_graph)[1]           # noqa: E731
         for _ in range(3):
             step()
         torch.cuda.synchronize()

@@ -12,6 +12,11 @@
 // so a late or dead peer poisons every downstream result instead of passing off the stale payload of an older epoch,
 // and the kernel returns instead of hanging the GPU.
 //
+// The epoch of a call is either given by the host or, with epoch = HFL_PEER_EPOCH_DEVICE (0xFFFFFFFF), kept on the device:
+// a per-channel counter behind the words of the rank's own buffer, advanced by the kernel itself.  Every rank makes the
+// same sequence of calls, so the counters agree without communication - and a launch no longer carries a number that
+// changes from step to step, which is what lets a whole multi-GPU step be captured once and replayed as a CUDA graph.
+//
 // Buffers are plain cudaMalloc allocations exported with cudaIpcGetMemHandle; the host side (dist.PeerExchange)
 // swaps the 64-byte handles through torch.distributed and opens them with cudaIpcOpenMemHandle.
 #include <string.h>
@@ -22,7 +27,9 @@ namespace hfl {
 constexpr int PEER_MAX_RANKS = 64;
 constexpr int PEER_MAX_DOUBLES = 4;
 constexpr int PEER_CHANNELS = 4;
-constexpr int PEER_WORDS = PEER_CHANNELS * 2 * PEER_MAX_RANKS * PEER_MAX_DOUBLES * 2;   // 64-bit words per buffer
+constexpr int PEER_WORDS = PEER_CHANNELS * 2 * PEER_MAX_RANKS * PEER_MAX_DOUBLES * 2;   // 64-bit payload words per buffer
+constexpr unsigned int PEER_EPOCH_DEVICE = 0xFFFFFFFFu;                                 // epoch kept in the buffer's tail
+constexpr size_t PEER_BYTES = (size_t)PEER_WORDS * sizeof(unsigned long long) + 64;     // + per-channel epoch counters
 
 __device__ __forceinline__ unsigned long long* peer_slot(void* buf, int channel, unsigned int epoch, int src_rank) {
     return reinterpret_cast<unsigned long long*>(buf) +
@@ -37,8 +44,20 @@ __global__ void peer_allgather_kernel(int G, int rank, int W, const double* __re
                                       double uL, double uR, double* __restrict__ bc2, long long max_spin) {
     __shared__ unsigned int halves[PEER_MAX_RANKS * PEER_MAX_DOUBLES * 2];
     __shared__ int s_expired;
-    if (threadIdx.x == 0) s_expired = 0;
+    __shared__ unsigned int s_epoch;
+    if (threadIdx.x == 0) {
+        s_expired = 0;
+        s_epoch = epoch;
+        if (epoch == PEER_EPOCH_DEVICE) {       // this rank's counter of the channel: 1, 2, ... (0 is the cleared state)
+            unsigned int* ctr = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned long long*>(bufs[rank]) + PEER_WORDS) + channel;
+            unsigned int e = *ctr + 1u;
+            if (e == 0u || e == PEER_EPOCH_DEVICE) e = (e & 1u) ? 1u : 2u;      // wrap-around keeps the parity alternating
+            *ctr = e;
+            s_epoch = e;
+        }
+    }
     __syncthreads();
+    epoch = s_epoch;
     const int nw = 2 * W;
     for (int t = threadIdx.x; t < G * nw; t += blockDim.x) {
         const int p = t / nw, j = t - p * nw;
@@ -83,7 +102,7 @@ __global__ void peer_allgather_kernel(int G, int rank, int W, const double* __re
 
 using namespace hfl;
 
-extern "C" size_t hfl_peer_buffer_bytes(void) { return (size_t)PEER_WORDS * sizeof(unsigned long long); }
+extern "C" size_t hfl_peer_buffer_bytes(void) { return PEER_BYTES; }
 
 extern "C" int hfl_peer_buffer_create(void** d_buf, unsigned char* ipc_handle64) {
     HFL_REQUIRE(d_buf != nullptr && ipc_handle64 != nullptr, "hfl_peer_buffer_create: NULL argument");

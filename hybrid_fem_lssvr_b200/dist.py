@@ -76,15 +76,15 @@ class PeerExchange:
                 raise _lib.HflError('peer-memory buffer could not be opened on a rank: %s' % (err or 'another rank'))
         self.bufs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.epoch = {}
+        # epochs live on the device (HFL_PEER_EPOCH_DEVICE): every launch is identical from step to step, so a step that
+        # contains an exchange can be captured once and replayed as a CUDA graph
+        self.EPOCH_DEVICE = 0xFFFFFFFF
 
     def all_gather(self, src, channel, out=None):
         """out [G, W] <- every rank's src [W] (W <= 4 float64), stream-ordered on the current stream."""
         W = src.numel()
         out = torch.empty((self.world, W), dtype=torch.float64, device=src.device) if out is None else out
-        e = self.epoch.get(channel, 0) + 1
-        self.epoch[channel] = e
-        _lib.check(self._lib.hfl_peer_allgather(self.world, self.rank, W, batch._ptr(src), batch._ptr(self.bufs), e, channel,
+        _lib.check(self._lib.hfl_peer_allgather(self.world, self.rank, W, batch._ptr(src), batch._ptr(self.bufs), self.EPOCH_DEVICE, channel,
                                                 batch._ptr(out), batch._ptr(self.status), batch._stream()),
                    'hfl_peer_allgather')
         return out
@@ -94,9 +94,7 @@ class PeerExchange:
         gathered = torch.empty(4 * self.world, dtype=torch.float64, device=iface4.device)
         bc2 = torch.empty(2, dtype=torch.float64, device=iface4.device)
         ch = self.CHANNEL_INTERFACE
-        e = self.epoch.get(ch, 0) + 1
-        self.epoch[ch] = e
-        _lib.check(self._lib.hfl_peer_spike_exchange(self.world, self.rank, batch._ptr(iface4), batch._ptr(self.bufs), e, ch,
+        _lib.check(self._lib.hfl_peer_spike_exchange(self.world, self.rank, batch._ptr(iface4), batch._ptr(self.bufs), self.EPOCH_DEVICE, ch,
                                                      float(u_left), float(u_right), batch._ptr(gathered), batch._ptr(bc2),
                                                      batch._ptr(self.status), batch._stream()), 'hfl_peer_spike_exchange')
         return bc2

@@ -120,6 +120,7 @@ int hfl_spike_interface_solve_device(int G, const double* d_gathered, double u_l
  * on expiry *d_status (optional) becomes 1 and the doubles that did not arrive are delivered as NaN (hfl_peer_spike_exchange
  * then also writes NaN interface values), so a late or dead peer poisons the results instead of passing off stale data.
  * Replaces the dist.all_gather_into_tensor calls a torch.distributed port of P:117-145 / K5 would make. */
+#define HFL_PEER_EPOCH_DEVICE 0xFFFFFFFFu   /* epoch argument: use and advance the per-channel counter kept in the buffer (graph-replayable) */
 size_t hfl_peer_buffer_bytes(void);
 int hfl_peer_buffer_create(void** d_buf, unsigned char* ipc_handle64);
 int hfl_peer_buffer_open(const unsigned char* ipc_handle64, void** d_peer);
