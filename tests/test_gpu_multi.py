@@ -1,5 +1,6 @@
 """Two-GPU checks of the partitioned path (skipped on a single-GPU box): the peer-memory exchange against NCCL, and the
-partitioned coarse solve + element solves against the single-GPU result.  One process per GPU, NCCL for the plumbing."""
+partitioned coarse solve + element solves against the single-GPU result, by stream launches and replayed as a CUDA graph.
+One process per GPU, NCCL for the plumbing."""
 import os
 import socket
 
@@ -49,6 +50,29 @@ def _worker(rank, world, port, E, out_dir):
         assert torch.equal(res['peer'][0], res['nccl'][0]) and torch.equal(res['peer'][1], res['nccl'][1])
         # the L2 accumulator is a floating-point atomicAdd: the two runs may differ in the last bits
         assert abs(res['peer'][2] - res['nccl'][2]) <= 1e-9 * res['nccl'][2] and res['peer'][3:] == res['nccl'][3:]
+        assert not px.timed_out()
+        # 3. the same step captured once and replayed as a CUDA graph (the exchange keeps its epoch on the device, so the
+        # captured launch is valid for every later step): same bits as the stream launches, replay after replay
+        u_g = torch.empty_like(nodes)
+        fine_g = torch.empty_like(res['peer'][1])
+        err_g = batch.new_error_accumulator(dev)
+        def step():
+            _, b = hdist.fem_p1_solve_distributed(nodes, exchange=px, out=u_g)
+            batch.lssvr_primal_batch(nodes, u_g, 9, 1e4, N=12, F=32, bc2=b, want_coef=False, want_fine=True, fine_out=fine_g,
+                                     err3=err_g)
+            return b
+        step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            bc2_g = step()
+        for _ in range(3):
+            fine_g.fill_(float('nan'))
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(bc2_g, res['peer'][0]), (rank, bc2_g.tolist(), res['peer'][0].tolist())
+            assert torch.equal(fine_g, res['peer'][1]), (rank, float((fine_g - res['peer'][1]).abs().max()))
         assert not px.timed_out()
         np.save(os.path.join(out_dir, 'fine_%d.npy' % rank), res['peer'][1].cpu().numpy())
         if rank == 0:
