@@ -116,7 +116,8 @@ int hfl_spike_interface_solve_device(int G, const double* d_gathered, double u_l
  * transport), every rank opens its peers' buffers and keeps the G device pointers in a device array d_bufs[G]
  * (its own buffer at [rank]).  hfl_peer_allgather: d_out[G][W] <- every rank's d_src[W] (W <= 4), stream-ordered;
  * all ranks must call it with the same (epoch, channel, W); epoch != 0 increases by one per call on a channel
- * (channel < 4 separates call sites).  The receive spin is bounded (2^24 polls, ~8 s; hfl_set_option "peer_spin_log2"):
+ * (channel < 4 separates call sites), or every call passes HFL_PEER_EPOCH_DEVICE and the kernel keeps the counter in the
+ * rank's own buffer (do not mix the two on one channel).  The receive spin is bounded (2^24 polls, ~8 s; hfl_set_option "peer_spin_log2"):
  * on expiry *d_status (optional) becomes 1 and the doubles that did not arrive are delivered as NaN (hfl_peer_spike_exchange
  * then also writes NaN interface values), so a late or dead peer poisons the results instead of passing off stale data.
  * Replaces the dist.all_gather_into_tensor calls a torch.distributed port of P:117-145 / K5 would make. */
