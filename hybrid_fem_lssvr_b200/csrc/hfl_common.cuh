@@ -77,6 +77,9 @@ struct hfl_plan {
     // buffer per stream is race-free); grown on demand, released by hfl_plan_destroy.
     // Left-looking dual kernel: moment tables and ranks of the tau = 0 factorisation (a function of the plan alone),
     // computed by the first launch that can use them and read by every later one (hfl_dual_parity.cu).
+    // Register dual kernel (N <= 14): the host-built DualSmallTables of this plan (pivot order, permuted blocks, moment
+    // tables), built by the first launch (hfl_dual_small.cu)
+    mutable std::vector<unsigned char> dual_small_tables;
     mutable double* d_dual0 = nullptr;
     mutable bool dual0_ready = false;
     mutable std::mutex scratch_mu;

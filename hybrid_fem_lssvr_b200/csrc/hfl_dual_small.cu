@@ -18,7 +18,8 @@ namespace hfl {
 
 // Pivot order of diagonally pivoted Cholesky on the n x n PSD matrix K (long double); indices whose remaining
 // diagonal is negligible are appended in natural order.
-static void pivot_order(int n, std::vector<long double> K, int* perm) {
+// Returns the number of pivots taken (the numerical rank at 1e-13 of the largest diagonal entry).
+static int pivot_order(int n, std::vector<long double> K, int* perm) {
     std::vector<int> rem(n);
     for (int i = 0; i < n; ++i) rem[i] = i;
     long double dmax0 = 0.0L;
@@ -38,7 +39,67 @@ static void pivot_order(int n, std::vector<long double> K, int* perm) {
         for (int i = 0; i < n; ++i)
             for (int k = 0; k < n; ++k) K[(size_t)i * n + k] -= l[i] * l[k];
     }
+    const int rank = cnt;
     for (int r : rem) perm[cnt++] = r;
+    return rank;
+}
+
+// Moment tables of one parity block (see DualSmallTables): G = C_P^T (C_P C_P^T)^-1 over the first `rank` pivots
+// (Cholesky in long double), then mom[m][q] = sum_k G[q][k] a_m c_k^(2m) (even) or a_m c_k^(2m+1) (odd) over the
+// collocation pivots, c_k = 2 j_k + 1, and mom[5][q] = G[q][constraint pivot].  K, C in pivot order.
+static void moment_tables(int NE, int NHD, int ma, int rank, const std::vector<long double>& Kp, const std::vector<long double>& Cp,
+                          const int* perm, bool odd, double* mom /* [6][ma] */) {
+    const int r = rank;
+    std::vector<long double> L((size_t)r * r, 0.0L);
+    for (int j = 0; j < r; ++j) {
+        long double d = Kp[(size_t)j * NE + j];
+        for (int k = 0; k < j; ++k) d -= L[(size_t)j * r + k] * L[(size_t)j * r + k];
+        const long double ljj = sqrtl(d);
+        L[(size_t)j * r + j] = ljj;
+        for (int i = j + 1; i < r; ++i) {
+            long double v = Kp[(size_t)i * NE + j];
+            for (int k = 0; k < j; ++k) v -= L[(size_t)i * r + k] * L[(size_t)j * r + k];
+            L[(size_t)i * r + j] = v / ljj;
+        }
+    }
+    // G[q][k] = sum_i C[i][q] Z[i][k], Z = A_PP^-1 (column k = solve for the unit vector e_k)
+    std::vector<long double> G((size_t)ma * r, 0.0L), z(r);
+    for (int k = 0; k < r; ++k) {
+        for (int i = 0; i < r; ++i) {
+            long double v = (i == k) ? 1.0L : 0.0L;
+            for (int j = 0; j < i; ++j) v -= L[(size_t)i * r + j] * z[j];
+            z[i] = v / L[(size_t)i * r + i];
+        }
+        for (int i = r - 1; i >= 0; --i) {
+            long double v = z[i];
+            for (int j = i + 1; j < r; ++j) v -= L[(size_t)j * r + i] * z[j];
+            z[i] = v / L[(size_t)i * r + i];
+        }
+        for (int q = 0; q < ma; ++q) {
+            long double acc = 0.0L;
+            for (int i = 0; i < r; ++i) acc += Cp[(size_t)i * ma + q] * z[i];
+            G[(size_t)q * r + k] = acc;
+        }
+    }
+    // Taylor coefficients: cos x = sum a_m x^(2m), sin x = sum a_m x^(2m+1)
+    const long double ae[5] = {1.0L, -1.0L / 2, 1.0L / 24, -1.0L / 720, 1.0L / 40320};
+    const long double ao[5] = {1.0L, -1.0L / 6, 1.0L / 120, -1.0L / 5040, 1.0L / 362880};
+    for (int q = 0; q < ma; ++q) {
+        for (int m = 0; m < 6; ++m) mom[(size_t)m * ma + q] = 0.0;
+        long double acc[5] = {0.0L, 0.0L, 0.0L, 0.0L, 0.0L}, con = 0.0L;
+        for (int k = 0; k < r; ++k) {
+            const int j = perm[k];
+            if (j >= NHD) { con += G[(size_t)q * r + k]; continue; }
+            const long double c = (long double)(2 * j + 1);
+            long double pw = odd ? c : 1.0L;
+            for (int m = 0; m < 5; ++m) {
+                acc[m] += G[(size_t)q * r + k] * (odd ? ao[m] : ae[m]) * pw;
+                pw *= c * c;
+            }
+        }
+        for (int m = 0; m < 5; ++m) mom[(size_t)m * ma + q] = (double)acc[m];
+        mom[(size_t)5 * ma + q] = (double)con;
+    }
 }
 
 template <int M, int NHD>
@@ -61,8 +122,8 @@ static void build_tables(const hfl_plan* plan, DualSmallTables<M, NHD>& dt) {
         return K;
     };
     std::vector<long double> Ke = gram(Ce, MEA), Ko = gram(Co, MOA);
-    pivot_order(NE, Ke, dt.perm_e);
-    pivot_order(NE, Ko, dt.perm_o);
+    const int rank_e = pivot_order(NE, Ke, dt.perm_e);
+    const int rank_o = pivot_order(NE, Ko, dt.perm_o);
     for (int i = 0; i < NE; ++i) {
         dt.je[i] = dt.perm_e[i] < NHD ? 1.0 : 0.0;
         dt.jo[i] = dt.perm_o[i] < NHD ? 1.0 : 0.0;
@@ -73,13 +134,50 @@ static void build_tables(const hfl_plan* plan, DualSmallTables<M, NHD>& dt) {
         for (int a = 0; a < MEA; ++a) dt.Ce[i][a] = (double)Ce[(size_t)dt.perm_e[i] * MEA + a];
         for (int b = 0; b < MOA; ++b) dt.Co[i][b] = (double)Co[(size_t)dt.perm_o[i] * MOA + b];
     }
+    // moment form of the tau = 0 solve (DMOM kernels), from the double-rounded tables the kernels use
+    {
+        std::vector<long double> Kpe((size_t)NE * NE), Kpo((size_t)NE * NE), Cpe((size_t)NE * MEA), Cpo((size_t)NE * MOA);
+        long double kmin = 1e300L;
+        for (int i = 0; i < NE; ++i) {
+            for (int j = 0; j < NE; ++j) {
+                const int lo = i > j ? j : i, hi = i > j ? i : j;
+                Kpe[(size_t)i * NE + j] = (long double)dt.Ke[hi * (hi + 1) / 2 + lo];
+                Kpo[(size_t)i * NE + j] = (long double)dt.Ko[hi * (hi + 1) / 2 + lo];
+            }
+            for (int a = 0; a < MEA; ++a) Cpe[(size_t)i * MEA + a] = (long double)dt.Ce[i][a];
+            for (int b = 0; b < MOA; ++b) Cpo[(size_t)i * MOA + b] = (long double)dt.Co[i][b];
+            if (dt.je[i] != 0.0) kmin = std::min(kmin, (long double)dt.Ke[i * (i + 1) / 2 + i]);
+            if (dt.jo[i] != 0.0) kmin = std::min(kmin, (long double)dt.Ko[i * (i + 1) / 2 + i]);
+        }
+        moment_tables(NE, NHD, MEA, rank_e, Kpe, Cpe, dt.perm_e, false, &dt.mom_e[0][0]);
+        moment_tables(NE, NHD, MOA, rank_o, Kpo, Cpo, dt.perm_o, true, &dt.mom_o[0][0]);
+        dt.thr_same = (double)kmin * 5.551115123125783e-17;     // 2^-54
+    }
 }
 
 template <int M>
 static int launch_m(const hfl_plan* plan, const PrimalArgs& a, bool err, cudaStream_t s) {
     DualSmallTables<M, 6> dt;
-    memset(&dt, 0, sizeof(dt));
-    build_tables<M, 6>(plan, dt);
+    {
+        // the tables depend on the plan alone: built once (long double, a few hundred microseconds), then copied
+        std::lock_guard<std::mutex> guard(plan->scratch_mu);
+        if (plan->dual_small_tables.size() != sizeof(dt)) {
+            memset(&dt, 0, sizeof(dt));
+            build_tables<M, 6>(plan, dt);
+            plan->dual_small_tables.assign(reinterpret_cast<unsigned char*>(&dt), reinterpret_cast<unsigned char*>(&dt) + sizeof(dt));
+        }
+        memcpy(&dt, plan->dual_small_tables.data(), sizeof(dt));
+    }
+    if (!get_option_dual_reuse()) dt.thr_same = -1.0;
+    // sine forcing: the kernels that take the moment form wherever an element allows it (everything else out of line);
+    // sampled forcing: the kernels with the factorisation in line
+    if (a.forcing == HFL_FORCING_SINE && get_option_dual_reuse()) {
+        if (a.coef != nullptr)
+            return err ? launch_fast<M, 16, true, STORE_TMA, 6, true, true>(plan, a, s, &dt)
+                       : launch_fast<M, 16, false, STORE_TMA, 6, true, true>(plan, a, s, &dt);
+        return err ? launch_fast<M, 16, true, STORE_TMA, 6, false, true>(plan, a, s, &dt)
+                   : launch_fast<M, 16, false, STORE_TMA, 6, false, true>(plan, a, s, &dt);
+    }
     return err ? launch_fast<M, 16, true, STORE_TMA, 6>(plan, a, s, &dt)
                : launch_fast<M, 16, false, STORE_TMA, 6>(plan, a, s, &dt);
 }

@@ -40,6 +40,14 @@ struct DualSmallTables {
     double je[NE], jo[NE];                                 // 1 if the pivot is a collocation row (gets tau/2)
     double Ce[NE][MEA], Co[NE][MOA];                       // rows of [-D+; 1] in pivot order
     int perm_e[NE], perm_o[NE];                            // pivot k = natural row perm[k]
+    // Moment form (DMOM kernels): tau enters only as fl(K_jj + tau/2) on the collocation pivots, so below thr_same
+    // (2^-54 of the smallest of those K_jj) every element has the tau = 0 matrix bit for bit and its solution is ONE linear
+    // map of the right-hand side, G = C_P^T (C_P C_P^T)^-1 over the numerical-rank pivots.  For a sine forcing the element
+    // resolves (collocation angles below 2^-7) the right-hand side is amp cos / sin(x_b (2 j + 1)), a Taylor polynomial in
+    // y = x_b^2, hence  w_par = fac sum_m y^m mom[m] + g_par mom[5]  with mom[m] = G (a_m c^(2m) or a_m c^(2m+1)) formed
+    // on the host in long double (hfl_dual_small.cu): 6 FMAs per coefficient instead of the factorisation.
+    double mom_e[6][MEA], mom_o[6][MOA];
+    double thr_same;
 };
 template <int M>
 struct DualSmallTables<M, 0> { int unused; };
@@ -144,12 +152,21 @@ __device__ __forceinline__ int ldl_solve_skip(double (&A)[n * (n + 1) / 2], doub
 
 // COEF: the coefficient-output path is compiled in (a separate instantiation, so that the fine-grid-only kernel
 // keeps its register budget).
-template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true>
+// Dual form, everything that is not the moment form: right-hand side, gather into the pivot order, two LDL^T solves with
+// the skip rule, w = C^T z.  The DMOM kernels keep it out of line (its 2 x 28 matrix entries would otherwise set their
+// register budget) and get the result through the thread's shared-memory slots: slot[q * kThreads], q = 0.. MEA - 1 the
+// even coefficients {w0, re[]}, then the odd ones {w1, ro[]}.  Returns the number-of-pivots test (false: fall back).
+template <int M, int NHD>
+__device__ __noinline__ bool dual_small_solve_slots(const PrimalArgs& a, const DualSmallTables<M, NHD>& dt, long long e, double xl,
+                                                    double xr, double abar, double bbar, double* slot);
+
+template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true, bool DMOM = false>
 #ifndef HFL_DUAL_SMALL_MINB
 #define HFL_DUAL_SMALL_MINB 3      // 168 registers, no spills since the Horner / Taylor epilogue (round 2): 0.645 against 0.72 ms per 1e7 elements
                                    // at 2 CTAs (254 registers); 4 CTAs (128 registers) spill and run at 0.89 ms.  Round 1's epilogue spilled at 3.
 #endif
-__global__ void __launch_bounds__(kThreads, NHD > 0 ? HFL_DUAL_SMALL_MINB : min_ctas(M, ERR, COEF))
+__global__ void __launch_bounds__(kThreads, NHD > 0 ? (DMOM ? (COEF ? 2 : 3) : HFL_DUAL_SMALL_MINB) : min_ctas(M, ERR, COEF))
+// (DMOM at 4 CTAs / 128 registers spills 200 bytes and runs at 0.59 ms per 1e7 elements against 0.50 ms at 3 CTAs)
 lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant__ PrimalTables<M, FH> t,
               const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DualSmallTables<M, NHD> dt) {
     constexpr int ME = n_even(M), MO = n_odd(M);
@@ -229,7 +246,46 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
         double S = 0.0, C = 0.0;   // sin / cos of k pi x_c
         bool ok = true;
         double w0, w1;
-        if constexpr (NHD > 0) {
+        if constexpr (NHD > 0 && DMOM) {
+            // ---- DUAL form through the moment tables (see DualSmallTables); anything else out of line
+            constexpr int MEA = ME + 1;
+            if (a.forcing == HFL_FORCING_SINE && 0.5 * tau < dt.thr_same && fabs(0.5 * a.k_freq * h) < 0.0078125) {
+                sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
+                const double xb = 3.14159265358979323846 * (a.k_freq * h * a.cN);
+                const double y = xb * xb, ak = isig * a.kk;
+                const double fe = ak * S, fo = (ak * C) * xb;
+                auto mom_e = [&](int q) {
+                    return fma(abar, dt.mom_e[5][q], fe * fma(fma(fma(fma(dt.mom_e[4][q], y, dt.mom_e[3][q]), y, dt.mom_e[2][q]), y, dt.mom_e[1][q]), y, dt.mom_e[0][q]));
+                };
+                auto mom_o = [&](int q) {
+                    return fma(bbar, dt.mom_o[5][q], fo * fma(fma(fma(fma(dt.mom_o[4][q], y, dt.mom_o[3][q]), y, dt.mom_o[2][q]), y, dt.mom_o[1][q]), y, dt.mom_o[0][q]));
+                };
+                w0 = mom_e(0);
+                w1 = mom_o(0);
+#pragma unroll
+                for (int i = 0; i < ME; ++i) re[i] = mom_e(1 + i);
+#pragma unroll
+                for (int i = 0; i < MO; ++i) ro[i] = mom_o(1 + i);
+            } else {
+                if (ERR) sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
+                double* slot = sPerm + threadIdx.x;
+                ok = dual_small_solve_slots<M, NHD>(a, dt, e, xl, xr, abar, bbar, slot);
+                w0 = slot[0];
+                w1 = slot[MEA * kThreads];
+#pragma unroll
+                for (int i = 0; i < ME; ++i) re[i] = slot[(1 + i) * kThreads];
+#pragma unroll
+                for (int i = 0; i < MO; ++i) ro[i] = slot[(MEA + 1 + i) * kThreads];
+                if (!ok) {
+#pragma unroll
+                    for (int i = 0; i < ME; ++i) re[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < MO; ++i) ro[i] = 0.0;
+                    w0 = abar; w1 = bbar;
+                    if (valid) ++nfail;
+                }
+            }
+        } else if constexpr (NHD > 0) {
             // ---- DUAL form, parity-split: two (NHD + 1)-unknown systems in the plan's static pivot order
             constexpr int NE = NHD + 1;
             double be[NE], bo[NE];
@@ -691,6 +747,85 @@ lssvr_element_kernel(const __grid_constant__ PrimalArgs a, const __grid_constant
 }
 
 
+template <int M, int NHD>
+__device__ __noinline__ bool dual_small_solve_slots(const PrimalArgs& a, const DualSmallTables<M, NHD>& dt, long long e, double xl,
+                                                    double xr, double abar, double bbar, double* slot) {
+    constexpr int NE = NHD + 1, ME = n_even(M), MO = n_odd(M), MEA = ME + 1;
+    const double h = xr - xl, h2 = h * h;
+    const double isig = 0.25 * h2, tau = (h2 * h2) * a.c_tau;
+    double be[NE], bo[NE];
+    if (a.forcing == HFL_FORCING_SINE) {
+        double S, C, sb, cb;
+        sincospi(a.k_freq * (0.5 * (xl + xr)), &S, &C);
+        sincospi_base(a.k_freq * h * a.cN, &sb, &cb);
+        const double s2 = 2.0 * sb * cb, c2 = fma(-2.0 * sb, sb, 1.0);
+        double s = sb, c = cb;                      // N even
+        const double fE = isig * a.kk * S, fO = isig * a.kk * C;
+#pragma unroll
+        for (int j = 0; j < NHD; ++j) {
+            be[j] = fE * c;
+            bo[j] = fO * s;
+            rotate(s, c, s2, c2);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NHD; ++j) {
+            const double fp = __ldg(a.f + (long long)(NHD + j) * a.E + e);
+            const double fm = __ldg(a.f + (long long)(NHD - 1 - j) * a.E + e);
+            be[j] = isig * (0.5 * (fp + fm));
+            bo[j] = isig * (0.5 * (fp - fm));
+        }
+    }
+    be[NHD] = abar;
+    bo[NHD] = bbar;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) { slot[j * kThreads] = be[j]; slot[(NE + j) * kThreads] = bo[j]; }
+#pragma unroll
+    for (int k = 0; k < NE; ++k) { be[k] = slot[dt.perm_e[k] * kThreads]; bo[k] = slot[(NE + dt.perm_o[k]) * kThreads]; }
+    const double th = 0.5 * tau;
+    bool ok;
+    {
+        double A[NE * (NE + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < NE; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+                A[i * (i + 1) / 2 + j] = (i == j) ? fma(dt.je[i], th, dt.Ke[i * (i + 1) / 2 + j]) : dt.Ke[i * (i + 1) / 2 + j];
+        ok = ldl_solve_skip<NE>(A, be) >= 1;
+    }
+    {
+        double A[NE * (NE + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < NE; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+                A[i * (i + 1) / 2 + j] = (i == j) ? fma(dt.jo[i], th, dt.Ko[i * (i + 1) / 2 + j]) : dt.Ko[i * (i + 1) / 2 + j];
+        ok = (ldl_solve_skip<NE>(A, bo) >= 1) && ok;
+    }
+    // w = C^T z, into the slots
+    double w0 = 0.0, w1 = 0.0, re[ME], ro[MO > 0 ? MO : 1];
+#pragma unroll
+    for (int i = 0; i < ME; ++i) re[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < MO; ++i) ro[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        w0 = fma(dt.Ce[k][0], be[k], w0);
+        w1 = fma(dt.Co[k][0], bo[k], w1);
+#pragma unroll
+        for (int i = 0; i < ME; ++i) re[i] = fma(dt.Ce[k][1 + i], be[k], re[i]);
+#pragma unroll
+        for (int i = 0; i < MO; ++i) ro[i] = fma(dt.Co[k][1 + i], bo[k], ro[i]);
+    }
+    slot[0] = w0;
+    slot[MEA * kThreads] = w1;
+#pragma unroll
+    for (int i = 0; i < ME; ++i) slot[(1 + i) * kThreads] = re[i];
+#pragma unroll
+    for (int i = 0; i < MO; ++i) slot[(MEA + 1 + i) * kThreads] = ro[i];
+    return ok;
+}
+
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -753,7 +888,7 @@ static void fill_horner_tables(PrimalTables<M, FH>& t) {
     }
 }
 
-template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true>
+template <int M, int FH, bool ERR, int STORE, int NHD = 0, bool COEF = true, bool DMOM = false>
 static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t stream,
                        const DualSmallTables<M, NHD>* dtp = nullptr) {
     constexpr int ME = n_even(M), MO = n_odd(M), F = 2 * FH;
@@ -799,7 +934,7 @@ static int launch_fast(const hfl_plan* plan, const PrimalArgs& a, cudaStream_t s
                                       (kTmaPerWarp && STORE == STORE_TMA) ? 32 : kThreads);
         if (rc != HFL_OK) return rc;
     }
-    auto kern = lssvr_element_kernel<M, FH, ERR, STORE, NHD, COEF>;
+    auto kern = lssvr_element_kernel<M, FH, ERR, STORE, NHD, COEF, DMOM>;
     DualSmallTables<M, NHD> dt;
     if (dtp) dt = *dtp; else memset(&dt, 0, sizeof(dt));
     const size_t smem = (size_t)kWarps * tile_bytes<STORE>(F) +

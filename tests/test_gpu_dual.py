@@ -221,3 +221,38 @@ def test_factor_reuse_is_bitwise(mesh):
         ref = oracle_coef(nodes[e:e + 2], u[1][e:e + 2], M, gamma, N, k=ks[1])
         fp = kkt.evaluate_fine(ref, F)
         assert rel(out[1][1][1, e:e + 1].cpu().numpy(), fp) <= TOL
+
+
+@pytest.mark.parametrize('M', [5, 9, 12])
+@pytest.mark.parametrize('fused', [False, True])
+def test_register_kernel_moment_form_matches_factorisation(M, fused):
+    """N = 12 register kernel: on elements whose tau is below half an ulp of the diagonal and that resolve the forcing, the
+    solution is the plan's one linear map of the right-hand side (moment tables built on the host in long double); every
+    other element of the same launch takes the factorisation, out of line.  A mesh that mixes both kinds: the two forms
+    agree to rounding, with and without the fused error norms (the elements that take the factorisation bit for bit), and the
+    moment form sits on the primal oracle."""
+    E, N, F, gamma, k = 5003, 12, 32, 1e4, 3.0
+    rng = np.random.default_rng(M)
+    w = rng.uniform(0.5e-4, 1.5e-4, E)
+    coarse = rng.uniform(size=E) < 0.25
+    w[coarse] = 3e-2
+    nodes = 0.05 + np.concatenate([[0.0], np.cumsum(w)])
+    u = np.sin(k * np.pi * nodes)
+    out = {}
+    for reuse in (1, 0):
+        batch.set_option('dual_reuse_factor', reuse)
+        try:
+            err3 = torch.zeros(3, dtype=torch.float64, device='cuda') if fused else None
+            coef, fine, status = batch.lssvr_dual_batch(dev(nodes), dev(u), M, gamma, N=N, F=F, k_freq=k, want_fine=True,
+                                                        want_status=True, err3=err3)
+            torch.cuda.synchronize()
+            out[reuse] = (coef.cpu().numpy(), fine.cpu().numpy(), status.cpu().numpy())
+        finally:
+            batch.set_option('dual_reuse_factor', 1)
+    assert not out[1][2].any() and not out[0][2].any()
+    assert rel(out[1][1], out[0][1]) <= 1e-12 and rel(out[1][0], out[0][0]) <= 1e-12
+    assert not np.array_equal(out[1][1][~coarse], out[0][1][~coarse])          # the moment form did run on the fine elements
+    assert np.array_equal(out[1][1][coarse], out[0][1][coarse])                # and the coarse ones took the same factorisation
+    for e in np.nonzero(~coarse)[0][:6]:
+        ref = oracle_coef(nodes[e:e + 2], u[e:e + 2], M, gamma, N, k=k)
+        check_dual('moment_form/M=%d' % M, rel(out[1][1][e:e + 1], kkt.evaluate_fine(ref, F)))
