@@ -152,6 +152,17 @@ __global__ void __launch_bounds__(GT, 3) general_kernel(const GeneralArgs g) {
 // CTAs per SM the register budget is sized for: the packed (M-2) x (M-2) Gram matrix lives in registers.  M = 9: 126
 // registers without spills at 4 CTAs (1.92 ms per 1e7 elements; 2.27 ms at 3 CTAs / 160 registers, 3.5 ms at 5 with spills).
 __host__ __device__ constexpr int general_minb(int M) { return M <= 9 ? 4 : (M <= 10 ? 3 : 2); }
+// The coefficient samples a, a', c, f of collocation point j ([N][E] arrays: one 8-byte load per thread, array and point)
+// arrive through a ring of GD asynchronous copy groups (cp.async, 8 bytes, each thread copying and reading only its own
+// words: no barrier), GD points ahead of their use and running on into the next tile: ncu had 60 % of the stall samples
+// of the one-point-ahead register prefetch waiting on these loads (DRAM latency ~1500 cycles against ~300 of work per point).
+#ifndef HFL_GENERAL_GD
+#define HFL_GENERAL_GD 5
+#endif
+constexpr int GD = HFL_GENERAL_GD;
+__device__ __forceinline__ void cp_async8(uint32_t dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 template <int M, int FH>
 __global__ void __launch_bounds__(GT, general_minb(M)) general_fast_kernel(const GeneralArgs g, const __grid_constant__ GeneralFineTables<M, FH> ft,
                                                               const __grid_constant__ CUtensorMap tmap) {
@@ -161,9 +172,11 @@ __global__ void __launch_bounds__(GT, general_minb(M)) general_fast_kernel(const
     double* sP0 = reinterpret_cast<double*>(gsm_raw + TILE);
     const int N = g.N;
     double* sP1 = sP0 + N * M; double* sP2 = sP1 + N * M;
+    double* ring = sP2 + N * M;                          // [GD][4][GT]: a, a', c, f of GD points in flight
     for (int i = threadIdx.x; i < N * M; i += GT) { sP0[i] = g.P0[i]; sP1[i] = g.P1[i]; sP2[i] = g.P2[i]; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const uint32_t ring_s = smem_u32(ring) + threadIdx.x * 8;
     double bcl = 0.0, bcr = 0.0, x_first = 0.0, x_last = 0.0, invL = 0.0;
     if (g.bc2 != nullptr) {
         bcl = g.bc2[0]; bcr = g.bc2[1];
@@ -172,6 +185,26 @@ __global__ void __launch_bounds__(GT, general_minb(M)) general_fast_kernel(const
     }
     bool store_pending = false;
     const long long nct = (g.E + GT - 1) / GT;
+    // producer side of the ring: (tile, point) of the next group to issue; an empty group once the tiles are exhausted
+    long long p_ct = blockIdx.x;
+    int p_j = 0, p_slot = 0;
+    auto issue_next = [&]() {
+        if (p_ct < nct) {
+            const long long pe = min(p_ct * GT + threadIdx.x, g.E - 1);
+            const long long o = (long long)p_j * g.E + pe;
+            const uint32_t dst = ring_s + p_slot * (4 * GT * 8);
+            cp_async8(dst, g.a + o);
+            if (g.da) cp_async8(dst + GT * 8, g.da + o);
+            if (g.c) cp_async8(dst + 2 * GT * 8, g.c + o);
+            cp_async8(dst + 3 * GT * 8, g.f + o);
+            if (++p_j == N) { p_j = 0; p_ct += gridDim.x; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        p_slot = p_slot + 1 == GD ? 0 : p_slot + 1;
+    };
+#pragma unroll
+    for (int d = 0; d < GD; ++d) issue_next();
+    int c_slot = 0;
     for (long long ct = blockIdx.x; ct < nct; ct += gridDim.x) {
         const long long e_raw = ct * GT + threadIdx.x;
         const bool valid = e_raw < g.E;
@@ -192,19 +225,15 @@ __global__ void __launch_bounds__(GT, general_minb(M)) general_fast_kernel(const
             for (int j = 0; j <= i; ++j)
                 H[i * (i + 1) / 2 + j] = (((i ^ j) & 1) == 0) ? (i == j ? 2.0 * tau : tau) : 0.0;
         }
-        double na = __ldg(g.a + e), nd = g.da ? __ldg(g.da + e) : 0.0, nc = g.c ? __ldg(g.c + e) : 0.0, nf = __ldg(g.f + e);
 #pragma unroll 1
         for (int j = 0; j < N; ++j) {
-            const double aj = na;
-            const double dj = nd * hh;        // a' h/2
-            const double cj = nc * isig;      // c h^2/4
-            const double fj = nf * isig;      // f / sigma
-            if (j + 1 < N) {
-                const long long o = (long long)(j + 1) * g.E + e;
-                na = __ldg(g.a + o); nf = __ldg(g.f + o);
-                if (g.da) nd = __ldg(g.da + o);
-                if (g.c) nc = __ldg(g.c + o);
-            }
+            asm volatile("cp.async.wait_group %0;" ::"n"(GD - 1) : "memory");      // the oldest group in flight has landed
+            const double* slot = ring + c_slot * (4 * GT) + threadIdx.x;
+            const double aj = slot[0];
+            const double dj = (g.da ? slot[GT] : 0.0) * hh;          // a' h/2
+            const double cj = (g.c ? slot[2 * GT] : 0.0) * isig;     // c h^2/4
+            const double fj = slot[3 * GT] * isig;                   // f / sigma
+            c_slot = c_slot + 1 == GD ? 0 : c_slot + 1;
             const double* p0 = sP0 + j * M; const double* p1 = sP1 + j * M; const double* p2 = sP2 + j * M;
             const double A0 = cj;
             const double A1 = fma(cj, p0[1], -dj);
@@ -221,6 +250,7 @@ __global__ void __launch_bounds__(GT, general_minb(M)) general_fast_kernel(const
 #pragma unroll
                 for (int k = 0; k <= i; ++k) H[i * (i + 1) / 2 + k] = fma(row[i], row[k], H[i * (i + 1) / 2 + k]);
             }
+            issue_next();       // into the slot just consumed (its values are in registers by now)
         }
         const bool ok = ldl_solve<m>(H, rhs);
         double w[M];
@@ -294,6 +324,7 @@ __global__ void __launch_bounds__(GT, general_minb(M)) general_fast_kernel(const
             store_pending = true;
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (store_pending) {
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncthreads();
@@ -327,7 +358,7 @@ static int launch_general_fast(const GeneralArgs& g, cudaStream_t s) {
     int rc = make_fine_tensor_map(&tmap, g.fine, g.E, F);
     if (rc != HFL_OK) return rc;
     auto kern = general_fast_kernel<M, FH>;
-    const size_t smem = (size_t)(F / 16) * GT * 128 + (size_t)3 * g.N * M * sizeof(double);
+    const size_t smem = (size_t)(F / 16) * GT * 128 + ((size_t)3 * g.N * M + (size_t)GD * 4 * GT) * sizeof(double);
     HFL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     HFL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GT, smem));
