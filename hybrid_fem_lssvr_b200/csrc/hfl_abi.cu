@@ -104,8 +104,9 @@ extern "C" int hfl_set_option(const char* key, int value) {
         g_opt_peer_spin_log2.store(value);
         return HFL_OK;
     }
-    // left-looking dual kernel: 1 = keep the factor of the previous element while K + tau J is the same floating-point
-    // matrix (tau below half an ulp of every diagonal entry); 0 = factorise every element (same results, bit for bit)
+    // dual kernels: 1 = elements whose K + tau J is the tau = 0 matrix bit for bit (tau below half an ulp of every diagonal
+    // entry) take that matrix's solution map from plan tables (left-looking kernel: same bits as a factorisation per element;
+    // register kernel: equal to rounding); 0 = factorise every element
     if (strcmp(key, "dual_reuse_factor") == 0) {
         HFL_REQUIRE(value == 0 || value == 1, "dual_reuse_factor must be 0 or 1");
         g_opt_dual_reuse.store(value);

@@ -206,7 +206,7 @@ int hfl_error_nodal(int64_t n_nodes, const double* d_nodes, const double* d_u, d
 /* ---- tuning / introspection (bench and tests) */
 int hfl_set_option(const char* key, int value);   /* "peer_spin_log2": 4..40; "fem_top_smem_kb": 64..227; "primal_store": 0 auto, 1 direct, 2 smem, 3 tma, 4 tma rows, 5 warp-cooperative;
                                                       "dual_team": 1 generic warp kernel for N = 12, 2 full-system team kernel, 3 parity split in shared memory;
-                                                      "dual_reuse_factor": 0 factorise every element in the left-looking dual kernel (default 1: reuse while bitwise the same matrix);
+                                                      "dual_reuse_factor": 0 factorise every element in the dual kernels (default 1: elements whose tau is below half an ulp of the diagonal share the tau = 0 matrix bit for bit and take its solution map - plan tables - instead of a factorisation);
                                                       "primal_debug": profiling aid */
 int hfl_get_option(const char* key, int* value);
 int64_t hfl_launch_count(void);                    /* kernels launched by this library so far */
