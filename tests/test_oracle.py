@@ -197,3 +197,59 @@ def test_general_operator_oracle_matches_mpmath(M, h):
     wm = general.lssvr_general_mp(nodes[0], nodes[1], u[0], u[1], a[0], da[0], c[0], f[0], M, 1e4)
     V = np.polynomial.legendre.legvander(np.linspace(-1, 1, 32), M - 1)
     assert np.max(np.abs(V @ w - V @ wm)) <= 1e-12 * np.max(np.abs(V @ wm))
+
+
+@pytest.mark.parametrize('M,N', [(9, 12), (5, 12), (13, 128), (25, 128)])
+def test_moment_form_of_the_dual_solution(M, N):
+    """The identity the dual kernels' table paths rest on (csrc/hfl_dual_small.cu, csrc/hfl_dual_parity.cu), restated in
+    numpy and checked against the primal KKT oracle.  Once tau is negligible the parity blocks C C^T of the dual system
+    are element independent, the solution is the linear map G = C_P^T (C_P C_P^T)^-1 of the right-hand side over the
+    pivots of a rank-revealing Cholesky, and for a resolved sine forcing the right-hand side is a Taylor polynomial in
+    y = x_b^2, so  w_par = fac sum_m y^m mom[m] + g_par mom[5]  with six element-independent vectors per parity."""
+    import math
+    from numpy.polynomial import legendre as npleg
+    gamma, kf = 1e4, 3.0
+    _, D, _ = kkt.reference_tables(M, N)
+    nhd = N // 2
+    blocks = []
+    for par in (0, 1):
+        cols = np.arange(par, M, 2)
+        C = np.vstack([-D[nhd:, cols], np.ones((1, len(cols)))]).astype(np.longdouble)      # rows xi+_j, then the constraint
+        K = C @ C.T
+        # diagonally pivoted Cholesky, stopped at 1e-13 of the largest diagonal entry
+        perm, Kw, d0 = [], K.copy(), np.max(np.diag(K))
+        rem = list(range(nhd + 1))
+        while rem:
+            j = max(rem, key=lambda i: Kw[i, i])
+            if not Kw[j, j] > 1e-13 * d0:
+                break
+            perm.append(j); rem.remove(j)
+            l = Kw[:, j] / np.sqrt(Kw[j, j])
+            Kw = Kw - np.outer(l, l)
+        P = np.array(perm)
+        G = C[P].T @ np.linalg.inv(K[np.ix_(P, P)].astype(np.float64)).astype(np.longdouble)    # (ma, r)
+        coll = P < nhd
+        c = (2 * P[coll] + 1).astype(np.longdouble)
+        tay = [1.0, -1.0 / 2, 1.0 / 24, -1.0 / 720, 1.0 / 40320] if par == 0 else [1.0, -1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880]
+        mom = [G[:, coll] @ (tay[m] * c ** (2 * m + par)) for m in range(5)]
+        mom.append(G[:, ~coll].sum(axis=1))
+        blocks.append((cols, np.array(mom, dtype=np.float64)))
+    # a few fine elements around x = 0.3
+    nodes = 0.3 + np.array([0.0, 1.1e-4, 1.9e-4, 3.2e-4])
+    u = np.sin(kf * np.pi * nodes) + 1e-3 * np.array([0.3, -0.2, 0.5, 0.1])
+    xs = np.linspace(nodes[:-1], nodes[1:], N, axis=0).T
+    ref = kkt.lssvr_primal_kkt_batch(nodes, u, (kf * np.pi) ** 2 * np.sin(kf * np.pi * xs), M, gamma)
+    for e in range(3):
+        xl, xr = nodes[e], nodes[e + 1]
+        h = xr - xl
+        xb = np.pi * kf * h * 0.5 / (N - 1)
+        y, ak = xb * xb, 0.25 * h * h * (kf * np.pi) ** 2
+        S, Cc = math.sin(kf * np.pi * 0.5 * (xl + xr)), math.cos(kf * np.pi * 0.5 * (xl + xr))
+        w = np.zeros(M)
+        for par, (cols, mom) in enumerate(blocks):
+            fac = ak * S if par == 0 else ak * Cc * xb
+            gpar = 0.5 * (u[e] + u[e + 1]) if par == 0 else 0.5 * (u[e + 1] - u[e])
+            w[cols] = fac * sum(y ** m * mom[m] for m in range(5)) + gpar * mom[5]
+        fine_w = npleg.legval(np.linspace(-1, 1, 33), w)
+        fine_r = npleg.legval(np.linspace(-1, 1, 33), ref[e])
+        assert np.max(np.abs(fine_w - fine_r)) <= 1e-10 * np.max(np.abs(fine_r)), (M, N, e)
