@@ -256,3 +256,25 @@ def test_register_kernel_moment_form_matches_factorisation(M, fused):
     for e in np.nonzero(~coarse)[0][:6]:
         ref = oracle_coef(nodes[e:e + 2], u[e:e + 2], M, gamma, N, k=k)
         check_dual('moment_form/M=%d' % M, rel(out[1][1][e:e + 1], kkt.evaluate_fine(ref, F)))
+
+
+@pytest.mark.parametrize('F', [20, 33, 64])
+@pytest.mark.parametrize('scale', [1.0, 1e-3])
+def test_left_looking_kernel_many_rhs_and_fine_grids(F, scale):
+    """Left-looking parity kernel with more right-hand sides than a team has threads (R = 100 > 96: two passes of the TEAM
+    loop) and fine grids that are odd, not a multiple of 16, or wider than one 16-half-point block, on a coarse mesh (TEAM
+    pass, factorisation per element) and a fine one (barrier-free STREAM pass): every right-hand side equals the
+    single-right-hand-side launch, the fine grid is the evaluation of the returned coefficients, status is clean."""
+    E, N, M, gamma, R = 700, 32, 7, 1e4, 100
+    nodes = jittered_mesh(E, seed=F) * scale + 0.2
+    ks = np.linspace(0.5, 3.0, R)
+    u = np.stack([np.sin(k * np.pi * nodes) for k in ks])
+    coef, fine, status = batch.lssvr_dual_multi(dev(nodes), dev(u), dev(ks), M, gamma, N=N, F=F, want_fine=True, want_status=True)
+    torch.cuda.synchronize()
+    coef, fine = coef.cpu().numpy(), fine.cpu().numpy()
+    assert not status.cpu().numpy().any()
+    assert not np.isnan(fine).any() and not np.isnan(coef).any()
+    for r in (0, 57, 95, 96, 99):
+        assert rel(fine[r], kkt.evaluate_fine(coef[r], F)) <= 1e-13
+        c1, f1, _ = _run_dual(nodes, u[r], M, gamma, N=N, F=F, k=ks[r])
+        assert rel(coef[r], c1) <= 1e-12 and rel(fine[r], f1) <= 1e-12
