@@ -4,7 +4,10 @@
 
 namespace hfl {
 
-constexpr int FT = 256;           // threads per CTA
+#ifndef HFL_FEM_FT
+#define HFL_FEM_FT 256
+#endif
+constexpr int FT = HFL_FEM_FT;    // threads per CTA
 constexpr int FS = 8;             // nodes per thread chunk (head + 7 interior)
 constexpr int FTS = FT * FS;      // nodes per tile
 constexpr int TOPT = 1024;        // threads of the top-level CTA
