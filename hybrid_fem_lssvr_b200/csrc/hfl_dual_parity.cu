@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                             const bool w_lo = inb, w_hi = inb && F - 1 - ih != ih;
                             double* out_lo = a.fine + ih;
                             double* out_hi = a.fine + (F - 1 - ih);
-#pragma unroll 4
+#pragma unroll
                             for (int sstep = 0; sstep < 16; ++sstep) {
                                 if (((vmask >> (2 * sstep)) & 3u) == 0u) continue;          // warp-uniform
                                 const int src = 2 * sstep + half;
