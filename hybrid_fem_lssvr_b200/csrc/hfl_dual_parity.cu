@@ -25,6 +25,7 @@
 // Round-1 form (two barriers per step, forward/backward solve per right-hand side, full-table fine grid): 58.7 k warp
 // instructions per element at M = 25, R = 64; see profiles/ for the line-level breakdown that led here.
 #include "hfl_dual.cuh"
+#include <type_traits>
 
 namespace hfl {
 
@@ -578,25 +579,31 @@ __global__ void __launch_bounds__(2 * LT, HFL_DUAL_LEFT_MINB) dual_parity_left_k
                             const bool w_lo = inb, w_hi = inb && F - 1 - ih != ih;
                             double* out_lo = a.fine + ih;
                             double* out_hi = a.fine + (F - 1 - ih);
+                            // (ALL: every lane of the warp has a task - the common case - so the per-step validity tests go)
+                            auto steps = [&](auto all_tag) {
+                                constexpr bool ALL = decltype(all_tag)::value;
 #pragma unroll
-                            for (int sstep = 0; sstep < 16; ++sstep) {
-                                if (((vmask >> (2 * sstep)) & 3u) == 0u) continue;          // warp-uniform
-                                const int src = 2 * sstep + half;
-                                const double2 s0 = stage[3 * src], s1 = stage[3 * src + 1], s2 = stage[3 * src + 2];
-                                const double y = s0.x, fe = s0.y, fo = s1.x, ge = s1.y, go = s2.x;
-                                const long long o2 = __double_as_longlong(s2.y);
-                                double pe = tbe[4], po = tbo[4];
+                                for (int sstep = 0; sstep < 16; ++sstep) {
+                                    if (!ALL && ((vmask >> (2 * sstep)) & 3u) == 0u) continue;          // warp-uniform
+                                    const int src = 2 * sstep + half;
+                                    const double2 s0 = stage[3 * src], s1 = stage[3 * src + 1], s2 = stage[3 * src + 2];
+                                    const double y = s0.x, fe = s0.y, fo = s1.x, ge = s1.y, go = s2.x;
+                                    const long long o2 = __double_as_longlong(s2.y);
+                                    double pe = tbe[4], po = tbo[4];
 #pragma unroll
-                                for (int q = 3; q >= 0; --q) {
-                                    pe = fma(pe, y, tbe[q]);
-                                    po = fma(po, y, tbo[q]);
+                                    for (int q = 3; q >= 0; --q) {
+                                        pe = fma(pe, y, tbe[q]);
+                                        po = fma(po, y, tbo[q]);
+                                    }
+                                    const double ev = fma(ge, tbe[5], fe * pe), od = fma(go, tbo[5], fo * po);
+                                    if (ALL || ((vmask >> src) & 1u)) {
+                                        if (w_lo) out_lo[o2] = ev + od;
+                                        if (w_hi) out_hi[o2] = ev - od;
+                                    }
                                 }
-                                const double ev = fma(ge, tbe[5], fe * pe), od = fma(go, tbo[5], fo * po);
-                                if ((vmask >> src) & 1u) {
-                                    if (w_lo) out_lo[o2] = ev + od;
-                                    if (w_hi) out_hi[o2] = ev - od;
-                                }
-                            }
+                            };
+                            if (vmask == 0xffffffffu) steps(std::true_type{});
+                            else steps(std::false_type{});
                         }
                     }
                     r += dr; j += dj;
